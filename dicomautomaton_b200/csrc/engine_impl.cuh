@@ -1,0 +1,609 @@
+// dcma_b200 -- Engine<T, STRICT>: owns the HBM buffers and launches the kernels of one registration.
+// Included by exactly three translation units (engine_f64.cu, engine_f64_strict.cu, engine_f32.cu), each with its own
+// DCMA_NS so that no device function compiled with different flags (-fmad=false for STRICT) can be shared by accident.
+//
+// Mirrors the reference engine (src/Alignment_Demons.cc:52-704):
+//   ctor                      -> cc:54-75, 152-187 (buffers; gradient is recomputed on the fly, never stored)
+//   load()                    -> cc:181-186
+//   run()                     -> AlignViaDemons' loop cc:980-995 over compute_single_iteration cc:81-108
+//   stage()                   -> the engine's private methods, one at a time (stage-level parity tests)
+//   get(DEFORMATION)          -> export_deformation_volume cc:110-113
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <vector>
+
+#include "demons_kernels.cuh"
+#include "engine.h"
+#include "smooth_kernels.cuh"
+
+namespace DCMA_NS {
+using namespace ::dcma;
+
+template <typename T>
+struct SmoothPlan {
+    bool active = false;  // sigma > 0 (cc:564-566)
+    bool fast = false;    // fused k_smooth3d usable (equal radii <= kMaxFastRadius)
+    int r[3] = {0, 0, 0};
+    std::vector<double> w[3];  // normalised weights per axis (cc:587-597)
+    SmoothWeights<T> W;
+    T *tab[3] = {nullptr, nullptr, nullptr};        // per-position wsum (STRICT) or 1/wsum
+    double *dw[3] = {nullptr, nullptr, nullptr};    // weights in global memory for k_smooth_axis
+};
+
+template <typename T, bool STRICT>
+class Engine final : public EngineBase {
+  public:
+    Engine(const dcma_b200_geom &geom, const dcma_b200_demons_params &params, void *stream_in) : p_(params) {
+        if (geom.slices < 1 || geom.rows < 1 || geom.cols < 1 || geom.channels < 1)
+            throw std::invalid_argument("volume extents and channel count must be >= 1");
+        if (!(geom.pxl_dx > 0.0) || !(geom.pxl_dy > 0.0) || !(geom.pxl_dz > 0.0))
+            throw std::invalid_argument("voxel spacing must be > 0");
+        if (geom.slices > 32767 * 64LL || geom.rows > (1 << 22) || geom.cols > (1 << 22))
+            throw std::invalid_argument("volume extent too large");
+        const long long N = geom.slices * geom.rows * geom.cols;
+        if (N * 3 >= (1LL << 40)) throw std::invalid_argument("volume too large");
+        g_.S = static_cast<int>(geom.slices);
+        g_.R = static_cast<int>(geom.rows);
+        g_.C = static_cast<int>(geom.cols);
+        g_.CH = static_cast<int>(geom.channels);
+        g_.N = N;
+        g_.px = geom.pxl_dx;
+        g_.py = geom.pxl_dy;
+        g_.pz = geom.pxl_dz;
+        g_.ipx = 1.0 / geom.pxl_dx;
+        g_.ipy = 1.0 / geom.pxl_dy;
+        g_.ipz = 1.0 / geom.pxl_dz;
+        g_.is2d = (geom.slices == 1) ? 1 : 0;
+
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError(cudaErrorNoDevice, "no CUDA device is available (dcma_b200 has no CPU fallback)");
+        if (p_.device >= 0) {
+            DCMA_CUDA(cudaSetDevice(p_.device));
+            dev_ = p_.device;
+        } else {
+            DCMA_CUDA(cudaGetDevice(&dev_));
+        }
+        cudaDeviceProp prop;
+        DCMA_CUDA(cudaGetDeviceProperties(&prop, dev_));
+        if (prop.major < 10)
+            throw CudaError(cudaErrorInvalidDevice, std::string("dcma_b200 kernels are built for sm_100a only; device is ") +
+                                                        prop.name + " (sm_" + std::to_string(prop.major) +
+                                                        std::to_string(prop.minor) + ")");
+        sms_ = prop.multiProcessorCount;
+        if (stream_in) {
+            stream_ = static_cast<cudaStream_t>(stream_in);
+        } else {
+            DCMA_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+            own_stream_ = true;
+        }
+
+        ntx_ = (g_.C + kTileX - 1) / kTileX;
+        nty_ = (g_.R + kTileY - 1) / kTileY;
+        ntiles_ = static_cast<long long>(ntx_) * nty_ * g_.S;
+        grid_vox_ = static_cast<int>(std::min<long long>(ntiles_, static_cast<long long>(sms_) * 8));
+        grid_lin_ = static_cast<int>(std::min<long long>((3 * N + 255) / 256, static_cast<long long>(sms_) * 16));
+
+        dF_ = alloc<float>(N * g_.CH);
+        dM_ = alloc<float>(N * g_.CH);
+        dD_ = alloc<T>(3 * N);
+        dU_ = alloc<T>(3 * N);
+        dTmp_ = alloc<T>(3 * N);
+        d_part_sum_ = alloc<double>(grid_vox_);
+        d_part_cnt_ = alloc<long long>(grid_vox_);
+        d_ctrl_ = alloc<Ctrl>(1);
+        DCMA_CUDA(cudaMallocHost(&h_ctrl_, sizeof(Ctrl)));
+
+        build_plan(plan_u_, p_.update_field_smoothing_sigma);
+        build_plan(plan_d_, p_.deformation_field_smoothing_sigma);
+        reset_ctrl();
+        DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * N, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(T) * 3 * N, stream_));
+    }
+
+    ~Engine() override {
+        cudaSetDevice(dev_);
+        cudaStreamSynchronize(stream_);
+        for (void *p : allocs_) cudaFree(p);
+        if (h_ctrl_) cudaFreeHost(h_ctrl_);
+        if (own_stream_) cudaStreamDestroy(stream_);
+    }
+
+    int device() const override { return dev_; }
+    int64_t device_bytes() const override { return bytes_; }
+    void sync() override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    // ---- cc:181-186 ------------------------------------------------------------------------------------------
+    void load(const float *fixed, const float *moving, bool on_device) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        const size_t bytes = sizeof(float) * g_.N * g_.CH;
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        DCMA_CUDA(cudaMemcpyAsync(dF_, fixed, bytes, kind, stream_));
+        DCMA_CUDA(cudaMemcpyAsync(dM_, moving, bytes, kind, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * g_.N, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(T) * 3 * g_.N, stream_));
+        w_src_ = 0;  // W := M (cc:183)
+        reset_ctrl();
+        if (!on_device) DCMA_CUDA(cudaStreamSynchronize(stream_));  // host buffers may be released by the caller
+        loaded_ = true;
+    }
+
+    // ---- AlignViaDemons loop, cc:980-995 -----------------------------------------------------------------------
+    void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        if (!loaded_) throw std::logic_error("engine_run called before engine_load");
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        if (max_iterations <= 0) return;
+        reset_ctrl();
+        double *d_hist = nullptr;
+        DCMA_CUDA(cudaMalloc(&d_hist, sizeof(double) * max_iterations));
+        launches_ = 0;
+        prof_.clear();
+        profiling_ = profile;
+
+        cudaEvent_t ev0, ev1;
+        DCMA_CUDA(cudaEventCreate(&ev0));
+        DCMA_CUDA(cudaEventCreate(&ev1));
+        DCMA_CUDA(cudaEventRecord(ev0, stream_));
+
+        // The stop rule runs on the device (k_reduce_final); the host only polls it.  With threshold <= 0 the rule
+        // `|prev-mse| < threshold` can never fire, so no poll is needed at all.
+        const bool can_converge = (p_.convergence_threshold > 0.0);
+        const int64_t poll = (p_.check_every > 0) ? p_.check_every : 4;
+        int64_t it = 0;
+        for (; it < max_iterations; ++it) {
+            iteration(it, d_hist);
+            if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations)) {
+                DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+                DCMA_CUDA(cudaStreamSynchronize(stream_));
+                if (h_ctrl_->converged_at != kNotConverged) {
+                    ++it;
+                    break;
+                }
+            }
+        }
+        DCMA_CUDA(cudaEventRecord(ev1, stream_));
+        DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+        const int64_t done = h_ctrl_->iters_done;
+        if (mse_history_host && done > 0)
+            DCMA_CUDA(cudaMemcpy(mse_history_host, d_hist, sizeof(double) * done, cudaMemcpyDeviceToHost));
+        if (p_.verbosity >= 1) {
+            std::vector<double> h(done);
+            if (done > 0) DCMA_CUDA(cudaMemcpy(h.data(), d_hist, sizeof(double) * done, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < done; ++i) std::fprintf(stderr, "Iteration %lld: MSE = %.17g\n", (long long)i, h[i]);
+            if (h_ctrl_->converged_at != kNotConverged)
+                std::fprintf(stderr, "Converged after %lld iterations\n", (long long)h_ctrl_->converged_at);
+        }
+        cudaFree(d_hist);
+        float ms = 0.f;
+        DCMA_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        if (stats) {
+            stats->iterations_done = done;
+            stats->kernel_launches = launches_;
+            stats->loop_ms = ms;
+            for (auto &pr : prof_) {
+                float t = 0.f;
+                cudaEventElapsedTime(&t, pr.a, pr.b);
+                stats->stage_ms[pr.stage] += t;
+                stats->stage_launches[pr.stage] += pr.launches;
+            }
+        }
+        for (auto &pr : prof_) {
+            cudaEventDestroy(pr.a);
+            cudaEventDestroy(pr.b);
+        }
+        prof_.clear();
+        profiling_ = false;
+    }
+
+    // ---- one reference engine method at a time ------------------------------------------------------------------
+    void stage(int stage, double sigma_mm, double *mse_out, int64_t *n_valid_out) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        if (!loaded_) throw std::logic_error("engine_stage called before engine_load");
+        const long long it = 0;  // stage calls are never skipped: converged_at is reset below
+        reset_ctrl();
+        switch (stage) {
+            case DCMA_B200_STAGE_FORCE: {
+                materialise_warped();
+                launch_force(2, it, nullptr, 0, 0);
+                DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+                DCMA_CUDA(cudaStreamSynchronize(stream_));
+                if (mse_out) *mse_out = h_ctrl_->last_mse;
+                if (n_valid_out) *n_valid_out = h_ctrl_->last_n;
+                break;
+            }
+            case DCMA_B200_STAGE_SMOOTH_U:
+            case DCMA_B200_STAGE_SMOOTH_D: {
+                SmoothPlan<T> &pl = plan_for(sigma_mm);
+                smooth(stage == DCMA_B200_STAGE_SMOOTH_U ? dU_ : dD_, pl, it);
+                break;
+            }
+            case DCMA_B200_STAGE_ADD: launch_add(it); break;
+            case DCMA_B200_STAGE_COMPOSE: launch_compose(it); break;
+            case DCMA_B200_STAGE_WARP:
+                launch_warp_to_buffer();
+                w_src_ = 2;
+                break;
+            default: throw std::invalid_argument("unknown stage id");
+        }
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void get(int buffer, void *host) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        const long long N = g_.N;
+        switch (buffer) {
+            case DCMA_B200_BUF_FIXED:
+            case DCMA_B200_BUF_MOVING:
+                DCMA_CUDA(cudaMemcpyAsync(host, buffer == DCMA_B200_BUF_FIXED ? dF_ : dM_, sizeof(float) * N * g_.CH,
+                                          cudaMemcpyDeviceToHost, stream_));
+                break;
+            case DCMA_B200_BUF_WARPED:
+                materialise_warped();
+                DCMA_CUDA(cudaMemcpyAsync(host, dW_, sizeof(float) * N * g_.CH, cudaMemcpyDeviceToHost, stream_));
+                break;
+            case DCMA_B200_BUF_GRADIENT: {
+                double *tmp = nullptr;
+                DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
+                k_gradient<<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dF_, tmp, g_, ntx_, nty_, ntiles_);
+                DCMA_CUDA(cudaGetLastError());
+                DCMA_CUDA(cudaMemcpyAsync(host, tmp, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream_));
+                DCMA_CUDA(cudaStreamSynchronize(stream_));
+                cudaFree(tmp);
+                break;
+            }
+            case DCMA_B200_BUF_UPDATE:
+            case DCMA_B200_BUF_DEFORMATION: {
+                double *tmp = nullptr;
+                DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
+                k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, tmp, N);
+                DCMA_CUDA(cudaGetLastError());
+                DCMA_CUDA(cudaMemcpyAsync(host, tmp, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream_));
+                DCMA_CUDA(cudaStreamSynchronize(stream_));
+                cudaFree(tmp);
+                break;
+            }
+            default: throw std::invalid_argument("unknown buffer id");
+        }
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void set(int buffer, const void *host) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        const long long N = g_.N;
+        switch (buffer) {
+            case DCMA_B200_BUF_FIXED:
+            case DCMA_B200_BUF_MOVING:
+                DCMA_CUDA(cudaMemcpyAsync(buffer == DCMA_B200_BUF_FIXED ? dF_ : dM_, host, sizeof(float) * N * g_.CH,
+                                          cudaMemcpyHostToDevice, stream_));
+                break;
+            case DCMA_B200_BUF_WARPED:
+                ensure_warped_buffer();
+                DCMA_CUDA(cudaMemcpyAsync(dW_, host, sizeof(float) * N * g_.CH, cudaMemcpyHostToDevice, stream_));
+                w_src_ = 2;
+                break;
+            case DCMA_B200_BUF_UPDATE:
+            case DCMA_B200_BUF_DEFORMATION: {
+                double *tmp = nullptr;
+                DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
+                DCMA_CUDA(cudaMemcpyAsync(tmp, host, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, stream_));
+                k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(tmp, buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, N);
+                DCMA_CUDA(cudaGetLastError());
+                DCMA_CUDA(cudaStreamSynchronize(stream_));
+                cudaFree(tmp);
+                break;
+            }
+            default: throw std::invalid_argument("buffer is not writable");
+        }
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void export_deformation_device(double *device_out) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(dD_, device_out, g_.N);
+        DCMA_CUDA(cudaGetLastError());
+    }
+
+  private:
+    struct ProfRec {
+        int stage;
+        int launches;
+        cudaEvent_t a, b;
+    };
+
+    template <typename X>
+    X *alloc(long long n) {
+        void *p = nullptr;
+        const size_t bytes = sizeof(X) * static_cast<size_t>(std::max<long long>(n, 1));
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            for (void *q : allocs_) cudaFree(q);
+            allocs_.clear();
+            throw CudaError(e, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " +
+                                   cudaGetErrorString(e));
+        }
+        allocs_.push_back(p);
+        bytes_ += static_cast<int64_t>(bytes);
+        return static_cast<X *>(p);
+    }
+
+    void reset_ctrl() {
+        Ctrl c;
+        c.prev_mse = std::numeric_limits<double>::infinity();
+        c.last_mse = 0.0;
+        c.last_n = 0;
+        c.iters_done = 0;
+        c.converged_at = kNotConverged;
+        c.threshold = p_.convergence_threshold;
+        *h_ctrl_ = c;
+        DCMA_CUDA(cudaMemcpyAsync(d_ctrl_, h_ctrl_, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));  // h_ctrl_ is reused as the D2H landing buffer
+    }
+
+    // Gaussian weights and per-position weight sums, cc:574-600 (host side, identical arithmetic and order).
+    void build_plan(SmoothPlan<T> &pl, double sigma_mm) {
+        pl.active = (sigma_mm > 0.0);
+        if (!pl.active) return;
+        const double pxl[3] = {g_.px, g_.py, g_.pz};
+        const int extent[3] = {g_.C, g_.R, g_.S};
+        for (int a = 0; a < 3; ++a) {
+            const long long rad = std::max<long long>(1, static_cast<long long>(3.0 * sigma_mm / pxl[a]));
+            if (rad > 100000) throw std::invalid_argument("smoothing radius too large");
+            pl.r[a] = static_cast<int>(rad);
+            const double sigma_pix = sigma_mm / pxl[a];
+            std::vector<double> k(2 * rad + 1);
+            double sum = 0.0;
+            for (long long i = -rad; i <= rad; ++i) {
+                const double v = std::exp(-0.5 * (static_cast<double>(i * i)) / (sigma_pix * sigma_pix));
+                k[static_cast<size_t>(i + rad)] = v;
+                sum += v;
+            }
+            for (auto &v : k) v /= sum;
+            pl.w[a] = k;
+            pl.dw[a] = alloc<double>(2 * rad + 1);
+            DCMA_CUDA(cudaMemcpy(pl.dw[a], k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice));
+        }
+        pl.fast = (p_.fused != 0) && (pl.r[0] == pl.r[1]) && (pl.r[1] == pl.r[2]) && (pl.r[0] <= kMaxFastRadius);
+        if (pl.fast) {
+            for (int a = 0; a < 3; ++a) {
+                const int rad = pl.r[a];
+                for (int k = 0; k < 2 * rad + 1; ++k) pl.W.w[a][k] = static_cast<T>(pl.w[a][k]);
+                std::vector<T> tab(extent[a]);
+                for (int pos = 0; pos < extent[a]; ++pos) {
+                    // in-order accumulation over the in-grid taps, in the kernel's own type (cc:620-631)
+                    T wsum = 0;
+                    for (int k = -rad; k <= rad; ++k) {
+                        const int q = pos + k;
+                        if (q >= 0 && q < extent[a]) wsum += pl.W.w[a][k + rad];
+                    }
+                    tab[pos] = STRICT ? wsum : static_cast<T>(1.0 / static_cast<double>(wsum));
+                }
+                pl.tab[a] = alloc<T>(extent[a]);
+                DCMA_CUDA(cudaMemcpy(pl.tab[a], tab.data(), sizeof(T) * tab.size(), cudaMemcpyHostToDevice));
+            }
+        }
+    }
+
+    SmoothPlan<T> &plan_for(double sigma_mm) {
+        if (sigma_mm == p_.update_field_smoothing_sigma) return plan_u_;
+        if (sigma_mm == p_.deformation_field_smoothing_sigma) return plan_d_;
+        auto it = extra_plans_.find(sigma_mm);
+        if (it == extra_plans_.end()) {
+            it = extra_plans_.emplace(sigma_mm, SmoothPlan<T>()).first;
+            build_plan(it->second, sigma_mm);
+        }
+        return it->second;
+    }
+
+    void prof_begin(int stage) {
+        if (!profiling_) return;
+        ProfRec r;
+        r.stage = stage;
+        r.launches = 0;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream_);
+        prof_.push_back(r);
+        prof_launch_mark_ = launches_;
+    }
+    void prof_end() {
+        if (!profiling_) return;
+        cudaEventRecord(prof_.back().b, stream_);
+        prof_.back().launches = static_cast<int>(launches_ - prof_launch_mark_);
+    }
+
+    // compute_single_iteration, cc:81-108, with warp_moving moved to the front of the NEXT iteration's force kernel.
+    void iteration(long long it, double *d_hist) {
+        const bool diffeo = (p_.use_diffeomorphic != 0);
+        if (p_.fused) {
+            prof_begin(DCMA_B200_STAGE_FORCE);
+            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false);
+            prof_end();
+        } else {
+            if (w_src_ == 1) {
+                prof_begin(DCMA_B200_STAGE_WARP);
+                launch_warp_to_buffer(it);
+                prof_end();
+                w_src_ = 2;
+            }
+            prof_begin(DCMA_B200_STAGE_FORCE);
+            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false);
+            prof_end();
+        }
+        prof_begin(DCMA_B200_STAGE_REDUCE);
+        launch_reduce(it, d_hist, it, 1);
+        prof_end();
+        if (diffeo && plan_u_.active) {
+            prof_begin(DCMA_B200_STAGE_SMOOTH_U);
+            smooth(dU_, plan_u_, it);
+            prof_end();
+        }
+        if (!diffeo) {
+            prof_begin(DCMA_B200_STAGE_ADD);
+            launch_add(it);
+            prof_end();
+        } else {
+            prof_begin(DCMA_B200_STAGE_COMPOSE);
+            launch_compose(it);
+            prof_end();
+        }
+        if (plan_d_.active) {
+            prof_begin(DCMA_B200_STAGE_SMOOTH_D);
+            smooth(dD_, plan_d_, it);
+            prof_end();
+        }
+        w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
+    }
+
+    void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true) {
+        if (w_src == 2) ensure_warped_buffer();
+        const double norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
+        k_warp_force<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(
+            dF_, dM_, dW_, dD_, dU_, g_, w_src, norm_eps, 1.0 / norm_eps, p_.max_update_magnitude, ntx_, nty_, ntiles_,
+            d_part_sum_, d_part_cnt_, d_ctrl_, it);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+        if (reduce) launch_reduce(it, d_hist, hist_idx, count_iter && d_hist != nullptr ? 1 : 0);
+    }
+    void launch_reduce(long long it, double *d_hist, long long hist_idx, int count_iter) {
+        k_reduce_final<<<1, 256, 0, stream_>>>(d_part_sum_, d_part_cnt_, grid_vox_, d_ctrl_, d_hist, it, hist_idx,
+                                               count_iter);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    void launch_add(long long it) {
+        k_add_update<T><<<grid_lin_, 256, 0, stream_>>>(dD_, dU_, g_.N, g_.px, g_.py, g_.pz, d_ctrl_, it);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    void launch_compose(long long it) {
+        k_compose<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, ntx_, nty_, ntiles_, d_ctrl_, it);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    void ensure_warped_buffer() {
+        if (!dW_) {
+            dW_ = alloc<float>(g_.N * g_.CH);
+            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_, sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
+        }
+    }
+    void launch_warp_to_buffer(long long it = 0) {
+        (void)it;
+        ensure_warped_buffer();
+        k_warp<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dM_, dD_, dW_, g_, ntx_, nty_, ntiles_, 0, 0.f);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    // bring the explicit `warped` buffer up to date with the engine state
+    void materialise_warped() {
+        ensure_warped_buffer();
+        if (w_src_ == 0) {
+            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_, sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
+        } else if (w_src_ == 1) {
+            launch_warp_to_buffer();
+        }
+        w_src_ = 2;
+    }
+
+    // smooth_on_device, cc:563-702.  Result ends in `field` (pointer swap instead of the reference's copy-back).
+    void smooth(T *&field, SmoothPlan<T> &pl, long long it) {
+        if (!pl.active) return;
+        if (pl.fast) {
+            launch_smooth3d(field, dTmp_, pl, it);
+            std::swap(field, dTmp_);
+        } else {
+            T *bufs[2] = {field, dTmp_};
+            for (int a = 0; a < 3; ++a) {  // x: field->tmp (cc:609), y: tmp->field (cc:638), z: field->tmp (cc:667)
+                k_smooth_axis<T><<<grid_lin_, 256, 0, stream_>>>(bufs[a & 1], bufs[(a + 1) & 1], g_, a, pl.r[a], pl.dw[a],
+                                                              d_ctrl_, it);
+                DCMA_CUDA(cudaGetLastError());
+                ++launches_;
+            }
+            // three passes: field -> tmp -> field -> tmp; the result is in dTmp_
+            std::swap(field, dTmp_);
+        }
+    }
+
+    template <int R, int TX, int TY, int NT, bool VEC>
+    void launch_smooth3d_cfg(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+        using Cfg = Smooth3dCfg<T, R, TX, TY, NT>;
+        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, VEC>;
+        static thread_local bool attr_set[64] = {false};
+        if (!attr_set[dev_ & 63]) {
+            DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(Cfg::smem_bytes)));
+            attr_set[dev_ & 63] = true;
+        }
+        const int gx = (g_.C + TX - 1) / TX, gy = (g_.R + TY - 1) / TY;
+        // z chunks: enough CTAs for ~4 waves at 2 CTAs/SM, but chunks no shorter than 4 halos (<= 50% re-staging)
+        const long long nxy = static_cast<long long>(gx) * gy * 3;
+        const long long target = static_cast<long long>(sms_) * 8;
+        int nz = static_cast<int>(std::max<long long>(1, (target + nxy - 1) / nxy));
+        const int min_chunk = std::max(8 * R, 16);
+        nz = std::min(nz, std::max(1, g_.S / min_chunk));
+        int zchunk = (g_.S + nz - 1) / nz;
+        nz = (g_.S + zchunk - 1) / zchunk;
+        if (3LL * nz > 65535 || gy > 65535) throw std::invalid_argument("volume exceeds the smoothing kernel's grid limits");
+        kern<<<dim3(gx, gy, 3 * nz), NT, Cfg::smem_bytes, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2],
+                                                                     zchunk, nz, d_ctrl_, it);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+
+    template <int R>
+    void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+        constexpr int TX = 64, NT = 256;
+        constexpr int TY = (sizeof(T) == 4) ? 32 : 16;
+        const bool vec = (g_.C % 4 == 0);
+        if (vec)
+            launch_smooth3d_cfg<R, TX, TY, NT, true>(in, out, pl, it);
+        else
+            launch_smooth3d_cfg<R, TX, TY, NT, false>(in, out, pl, it);
+    }
+
+    void launch_smooth3d(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+        switch (pl.r[0]) {
+            case 1: launch_smooth3d_r<1>(in, out, pl, it); break;
+            case 2: launch_smooth3d_r<2>(in, out, pl, it); break;
+            case 3: launch_smooth3d_r<3>(in, out, pl, it); break;
+            case 4: launch_smooth3d_r<4>(in, out, pl, it); break;
+            case 5: launch_smooth3d_r<5>(in, out, pl, it); break;
+            case 6: launch_smooth3d_r<6>(in, out, pl, it); break;
+            default: throw std::logic_error("fast smoothing radius out of range");
+        }
+    }
+
+    Geo g_;
+    dcma_b200_demons_params p_;
+    int dev_ = 0, sms_ = 148;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    bool loaded_ = false;
+    int ntx_ = 0, nty_ = 0, grid_vox_ = 1, grid_lin_ = 1;
+    long long ntiles_ = 0;
+    float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
+    T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;
+    double *d_part_sum_ = nullptr;
+    long long *d_part_cnt_ = nullptr;
+    Ctrl *d_ctrl_ = nullptr, *h_ctrl_ = nullptr;
+    SmoothPlan<T> plan_u_, plan_d_;
+    std::map<double, SmoothPlan<T>> extra_plans_;
+    int w_src_ = 0;
+    std::vector<void *> allocs_;
+    int64_t bytes_ = 0;
+    int64_t launches_ = 0, prof_launch_mark_ = 0;
+    bool profiling_ = false;
+    std::vector<ProfRec> prof_;
+};
+
+}  // namespace DCMA_NS

@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's Demons interface, driving the CUDA library through its C ABI.
+
+Reference names kept on purpose (src/Alignment_Demons.h): `AlignViaDemonsParams` (:20-61), `demons_volume` (:64-74),
+`AlignViaDemons` (:233-236).  The C++ drop-in for the dispatcher lives in `dicomautomaton_b200/host/`; this module is
+what the Python tests and bench.py call.  Nothing here computes: every array operation happens in
+`lib/libdcma_b200.so` on the GPU, and a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import sys
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+
+
+@dataclasses.dataclass
+class AlignViaDemonsParams:
+    """Same fields and defaults as the reference struct (src/Alignment_Demons.h:20-61) + additive extensions."""
+    max_iterations: int = 100
+    convergence_threshold: float = 0.001
+    deformation_field_smoothing_sigma: float = 1.0
+    update_field_smoothing_sigma: float = 0.5
+    use_diffeomorphic: bool = False
+    use_histogram_matching: bool = False
+    histogram_bins: int = 256
+    histogram_outlier_fraction: float = 0.01
+    normalization_factor: float = 1.0
+    max_update_magnitude: float = 2.0
+    verbosity: int = 1
+    # extensions (defaults keep reference behaviour)
+    field_mode: str = "fp64"  # "fp64" | "fp64_strict" | "fp32"
+    device: int = -1
+    check_every: int = 0
+    pyramid_levels: int = 1
+    use_symmetric_force: bool = False
+    fused: bool = True
+
+    def to_c(self) -> capi.Params:
+        p = capi.default_params()
+        p.max_iterations = int(self.max_iterations)
+        p.convergence_threshold = float(self.convergence_threshold)
+        p.deformation_field_smoothing_sigma = float(self.deformation_field_smoothing_sigma)
+        p.update_field_smoothing_sigma = float(self.update_field_smoothing_sigma)
+        p.use_diffeomorphic = 1 if self.use_diffeomorphic else 0
+        p.use_histogram_matching = 1 if self.use_histogram_matching else 0
+        p.histogram_bins = int(self.histogram_bins)
+        p.histogram_outlier_fraction = float(self.histogram_outlier_fraction)
+        p.normalization_factor = float(self.normalization_factor)
+        p.max_update_magnitude = float(self.max_update_magnitude)
+        p.verbosity = int(self.verbosity)
+        p.field_mode = capi.FIELD_MODES[self.field_mode]
+        p.device = int(self.device)
+        p.check_every = int(self.check_every)
+        p.pyramid_levels = int(self.pyramid_levels)
+        p.use_symmetric_force = 1 if self.use_symmetric_force else 0
+        p.fused = 1 if self.fused else 0
+        return p
+
+
+@dataclasses.dataclass
+class demons_volume:
+    """Dense proxy of an image stack: reference `demons_volume<T>` (src/Alignment_Demons.h:64-74).
+
+    data has shape (slices, rows, cols, channels): idx = ((z*rows + y)*cols + x)*channels + c (:77-79)."""
+    data: np.ndarray
+    pxl_dx: float = 1.0
+    pxl_dy: float = 1.0
+    pxl_dz: float = 1.0
+
+    def __post_init__(self):
+        if self.data.ndim == 3:
+            self.data = self.data[..., None]
+        if self.data.ndim != 4:
+            raise ValueError("demons_volume data must be (slices, rows, cols[, channels])")
+
+    @property
+    def slices(self): return self.data.shape[0]
+    @property
+    def rows(self): return self.data.shape[1]
+    @property
+    def cols(self): return self.data.shape[2]
+    @property
+    def channels(self): return self.data.shape[3]
+
+    def geom(self) -> capi.Geom:
+        return capi.Geom(self.slices, self.rows, self.cols, self.channels, float(self.pxl_dx), float(self.pxl_dy),
+                         float(self.pxl_dz))
+
+
+def _as_f32(vol: demons_volume) -> np.ndarray:
+    return np.ascontiguousarray(vol.data, dtype=np.float32)
+
+
+class DemonsEngine:
+    """Device-resident engine: the replacement of the reference's `sycl_demons_engine` (src/Alignment_Demons.cc:52-704).
+
+    Method names follow the reference engine's methods so stage-level parity tests read like the reference."""
+
+    def __init__(self, fixed: demons_volume, moving: demons_volume, params: AlignViaDemonsParams, stream: int = 0,
+                 load: bool = True):
+        if fixed.data.shape != moving.data.shape:
+            raise ValueError("fixed and moving volumes must have the same shape (resample first)")
+        self._lib = capi.lib()
+        self.params = params
+        self.shape = fixed.data.shape[:3]
+        self.channels = fixed.channels
+        self.n_voxels = int(np.prod(self.shape))
+        self._geom = fixed.geom()
+        self._cparams = params.to_c()
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        capi.check(self._lib.dcma_b200_engine_create(C.byref(self._h), C.byref(self._geom), C.byref(self._cparams),
+                                                     C.c_void_p(stream), err, len(err)), err)
+        if load:
+            self.load(_as_f32(fixed), _as_f32(moving))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dcma_b200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- data movement ------------------------------------------------------------------------------------------
+    def load(self, fixed: np.ndarray, moving: np.ndarray):
+        """Host float32 arrays -> HBM (reference: allocate_device_memory's copies, cc:181-186)."""
+        fixed = np.ascontiguousarray(fixed, dtype=np.float32)
+        moving = np.ascontiguousarray(moving, dtype=np.float32)
+        assert fixed.size == self.n_voxels * self.channels == moving.size
+        capi.check(self._lib.dcma_b200_engine_load(self._h, fixed.ctypes.data, moving.ctypes.data, 0))
+
+    def load_device(self, fixed_ptr: int, moving_ptr: int):
+        """Device pointers (e.g. torch tensors' data_ptr()) of float32 volumes on the engine's device."""
+        capi.check(self._lib.dcma_b200_engine_load(self._h, C.c_void_p(fixed_ptr), C.c_void_p(moving_ptr), 1))
+
+    def get(self, name: str) -> np.ndarray:
+        which = {"fixed": 0, "moving": 1, "warped": 2, "gradient": 3, "update": 4, "deformation": 5}[name]
+        if which <= 2:
+            out = np.empty(self.shape + (self.channels,), dtype=np.float32)
+        else:
+            out = np.empty(self.shape + (3,), dtype=np.float64)
+        capi.check(self._lib.dcma_b200_engine_get(self._h, which, out.ctypes.data))
+        return out
+
+    def set(self, name: str, arr: np.ndarray):
+        which = {"fixed": 0, "moving": 1, "warped": 2, "update": 4, "deformation": 5}[name]
+        if which <= 2:
+            arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(self.shape + (self.channels,))
+        else:
+            arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(self.shape + (3,))
+        capi.check(self._lib.dcma_b200_engine_set(self._h, which, arr.ctypes.data))
+
+    def export_deformation_device(self, device_ptr: int):
+        capi.check(self._lib.dcma_b200_engine_export_deformation_device(self._h, C.c_void_p(device_ptr)))
+
+    def sync(self):
+        capi.check(self._lib.dcma_b200_engine_sync(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.dcma_b200_engine_device_bytes(self._h))
+
+    # -- the loop -----------------------------------------------------------------------------------------------
+    def run(self, max_iterations: Optional[int] = None, profile: bool = False):
+        """AlignViaDemons' iteration loop (cc:980-995). Returns (mse_history, stats)."""
+        n = int(self.params.max_iterations if max_iterations is None else max_iterations)
+        hist = np.full(max(n, 1), np.nan, dtype=np.float64)
+        stats = capi.RunStats()
+        capi.check(self._lib.dcma_b200_engine_run(self._h, n, 1 if profile else 0, hist.ctypes.data, C.byref(stats)))
+        return hist[:stats.iterations_done].copy(), stats
+
+    # -- reference engine methods, one at a time ------------------------------------------------------------------
+    def _stage(self, stage, sigma=0.0):
+        mse, n = C.c_double(0.0), C.c_int64(0)
+        capi.check(self._lib.dcma_b200_engine_stage(self._h, stage, float(sigma), C.byref(mse), C.byref(n)))
+        return mse.value, n.value
+
+    def compute_update_and_mse(self):
+        return self._stage(capi.STAGE_FORCE)
+
+    def smooth_update(self, sigma_mm):
+        self._stage(capi.STAGE_SMOOTH_U, sigma_mm)
+
+    def smooth_deformation(self, sigma_mm):
+        self._stage(capi.STAGE_SMOOTH_D, sigma_mm)
+
+    def add_update(self):
+        self._stage(capi.STAGE_ADD)
+
+    def add_update_diffeomorphic(self):
+        self._stage(capi.STAGE_COMPOSE)
+
+    def warp_moving(self):
+        self._stage(capi.STAGE_WARP)
+
+
+def AlignViaDemons(params: AlignViaDemonsParams, moving: demons_volume, stationary: demons_volume,
+                   return_stats: bool = False):
+    """Drop-in for the reference's AlignViaDemons (src/Alignment_Demons.h:233-236) at the `demons_volume` level.
+
+    `moving` must already be on the stationary grid (the reference's step 1, cc:964; identity when grids coincide).
+    Returns the deformation volume (slices, rows, cols, 3) float64 in mm, or None on failure -- the reference returns
+    std::nullopt after logging a warning (cc:953-956, 1001-1004)."""
+    if moving.data.size == 0 or stationary.data.size == 0:
+        print("Unable to perform demons alignment: an image array is empty", file=sys.stderr)
+        return (None, None, None) if return_stats else None
+    try:
+        lib = capi.lib()
+        if moving.data.shape != stationary.data.shape:
+            raise ValueError("moving image is not on the stationary grid")
+        f, m = _as_f32(stationary), _as_f32(moving)
+        geom = stationary.geom()
+        cp = params.to_c()
+        D = np.empty(stationary.data.shape[:3] + (3,), dtype=np.float64)
+        hist = np.full(max(int(params.max_iterations), 1), np.nan, dtype=np.float64)
+        stats = capi.RunStats()
+        err = C.create_string_buffer(512)
+        capi.check(lib.dcma_b200_demons_register(C.byref(geom), f.ctypes.data, m.ctypes.data, C.byref(cp),
+                                                 D.ctypes.data, hist.ctypes.data, C.byref(stats), err, len(err)), err)
+        out = demons_volume(D, stationary.pxl_dx, stationary.pxl_dy, stationary.pxl_dz)
+        if return_stats:
+            return out, hist[:stats.iterations_done].copy(), stats
+        return out
+    except (capi.DcmaError, ValueError) as e:
+        print(f"Demons registration failed: {e}", file=sys.stderr)
+    return (None, None, None) if return_stats else None
+
+
+def warp_image_with_field(image: demons_volume, deformation: np.ndarray, oob_value: Optional[float] = None,
+                          device: int = -1) -> np.ndarray:
+    """warp_moving semantics (cc:467-550) for an image on the field's grid: out(p) = image(p + D(p)).
+
+    oob_value=None keeps NaN where the reference writes NaN; WarpImages uses 0.0 (src/Operations/WarpImages.cc:197)."""
+    lib = capi.lib()
+    img = _as_f32(image)
+    D = np.ascontiguousarray(deformation, dtype=np.float64).reshape(image.data.shape[:3] + (3,))
+    out = np.empty_like(img)
+    geom = image.geom()
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_warp_image(C.byref(geom), img.ctypes.data, D.ctypes.data,
+                                        0.0 if oob_value is None else float(oob_value),
+                                        0 if oob_value is None else 1, out.ctypes.data, device, err, len(err)), err)
+    return out

@@ -1,0 +1,97 @@
+"""Deterministic synthetic CT-like phantom pair with a known smooth sinusoidal warp.
+
+The pair is generated analytically on the fixed grid, so the reference's pre-step
+`resample_image_to_reference_grid` (src/Alignment_Demons.cc:709-755) is the identity and no NaNs exist at t=0.
+The warp is modelled on the reference's own generator (src/Operations/GenerateVirtualDataSinusoidalFieldV1.cc:77-134).
+
+Fixed  F(p)  = phantom(p)            HU: -1000 air, soft-tissue ellipsoid with sigmoid edge, +300 / -700 HU Gaussian
+                                      blobs, +900 HU rod, and a 20 HU sinusoidal texture EVERYWHERE (so |grad F| is
+                                      never tiny-but-nonzero over large regions).
+Moving M(p)  = phantom(p + w(p)/pxl)  with w = A_w * ( sin(2pi y/ly) cos(2pi z/lz),
+                                                       sin(2pi x/lx) cos(2pi z/lz),
+                                                       sin(2pi x/lx) sin(2pi y/ly) ),  l = extent / (2, 3, 1.5).
+Pull convention warped(p) = moving(p + D(p)): the ideal recovered field satisfies D(p) = -w(p + D(p)) ~ -w(p).
+
+Pure torch so the same code fills 128^3 on the CPU and 1024^3 directly in HBM.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def _phantom_hu(x, y, z, shape, case: int = 0):
+    """x, y, z: float64 tensors of voxel-index coordinates (x=col, y=row, z=slice). shape = (slices, rows, cols)."""
+    nz, ny, nx = (float(v) for v in shape)
+    cx, cy, cz = (nx - 1.0) / 2.0, (ny - 1.0) / 2.0, (nz - 1.0) / 2.0
+    ph = 0.37 * float(case)  # per-case variation (batch mode, BASELINE config 5)
+    small = min(nx, ny, nz)
+
+    e = torch.sqrt(((x - cx) / (0.40 * nx)) ** 2 + ((y - cy) / (0.32 * ny)) ** 2 + ((z - cz) / (0.45 * nz)) ** 2)
+    body = torch.sigmoid((1.0 - e) / 0.03)
+    hu = -1000.0 + 1000.0 * body
+
+    def blob(amp, fx, fy, fz, s):
+        bx, by, bz = cx + fx * nx, cy + fy * ny, cz + fz * nz
+        r2 = (x - bx) ** 2 + (y - by) ** 2 + (z - bz) ** 2
+        return amp * torch.exp(-0.5 * r2 / (s * small) ** 2)
+
+    hu = hu + body * blob(300.0, 0.15 * math.cos(ph), -0.05 + 0.10 * math.sin(ph), 0.10, 0.08)
+    hu = hu + body * blob(-700.0, -0.15 * math.cos(ph), 0.08, -0.12 + 0.05 * math.sin(ph), 0.07)
+    rho2 = (x - cx) ** 2 + (y - (cy + 0.18 * ny)) ** 2
+    hu = hu + body * 900.0 * torch.exp(-0.5 * rho2 / (0.03 * small) ** 2)
+    hu = hu + 20.0 * (torch.sin(0.9 * x + 0.3 * y + ph) + torch.sin(0.7 * y + 0.4 * z) + torch.sin(0.8 * z + 0.5 * x))
+    return hu
+
+
+def known_warp_mm(x, y, z, shape, amplitude_mm: float = 2.0, case: int = 0):
+    """The known warp w(p) in mm at voxel-index coordinates (x, y, z). Returns (wx, wy, wz)."""
+    nz, ny, nx = (float(v) for v in shape)
+    lx, ly, lz = nx / 2.0, ny / 3.0, max(nz / 1.5, 1.0)
+    ph = 0.37 * float(case)
+    two_pi = 2.0 * math.pi
+    sx, sy = torch.sin(two_pi * x / lx + ph), torch.sin(two_pi * y / ly)
+    czs = torch.cos(two_pi * z / lz)
+    return amplitude_mm * sy * czs, amplitude_mm * sx * czs, amplitude_mm * sx * sy
+
+
+def make_pair(shape, spacing=(1.0, 1.0, 1.0), amplitude_mm: float = 2.0, case: int = 0, device="cpu",
+              z_range=None, chunk: int = 16):
+    """Returns (fixed, moving) float32 tensors of shape (slices, rows, cols) [or the z_range sub-slab of it].
+
+    spacing = (pxl_dx, pxl_dy, pxl_dz) mm. For a single-slice volume the z component of the warp is dropped."""
+    nz, ny, nx = (int(v) for v in shape)
+    z0, z1 = (0, nz) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    dev = torch.device(device)
+    fixed = torch.empty((z1 - z0, ny, nx), dtype=torch.float32, device=dev)
+    moving = torch.empty_like(fixed)
+    ys = torch.arange(ny, dtype=torch.float64, device=dev).view(1, ny, 1)
+    xs = torch.arange(nx, dtype=torch.float64, device=dev).view(1, 1, nx)
+    for a in range(z0, z1, chunk):
+        b = min(a + chunk, z1)
+        zs = torch.arange(a, b, dtype=torch.float64, device=dev).view(b - a, 1, 1)
+        x, y, z = torch.broadcast_tensors(xs, ys, zs)
+        fixed[a - z0:b - z0] = _phantom_hu(x, y, z, shape, case).to(torch.float32)
+        wx, wy, wz = known_warp_mm(x, y, z, shape, amplitude_mm, case)
+        if nz == 1:
+            wz = torch.zeros_like(wz)
+        moving[a - z0:b - z0] = _phantom_hu(x + wx / spacing[0], y + wy / spacing[1], z + wz / spacing[2],
+                                            shape, case).to(torch.float32)
+    return fixed, moving
+
+
+def make_dose_grid(shape, device="cpu", chunk: int = 16):
+    """Smooth 0-70 Gy blob on the same grid (BASELINE config 3: 'warp of a co-registered RT dose grid')."""
+    nz, ny, nx = (int(v) for v in shape)
+    dev = torch.device(device)
+    out = torch.empty((nz, ny, nx), dtype=torch.float32, device=dev)
+    ys = torch.arange(ny, dtype=torch.float64, device=dev).view(1, ny, 1)
+    xs = torch.arange(nx, dtype=torch.float64, device=dev).view(1, 1, nx)
+    for a in range(0, nz, chunk):
+        b = min(a + chunk, nz)
+        zs = torch.arange(a, b, dtype=torch.float64, device=dev).view(b - a, 1, 1)
+        r2 = ((xs - 0.55 * nx) / (0.18 * nx)) ** 2 + ((ys - 0.45 * ny) / (0.15 * ny)) ** 2 \
+            + ((zs - 0.5 * nz) / (0.2 * nz)) ** 2
+        out[a:b] = (70.0 * torch.exp(-0.5 * r2)).to(torch.float32)
+    return out

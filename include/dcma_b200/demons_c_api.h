@@ -1,0 +1,171 @@
+/* dcma_b200 -- C ABI of the B200-native Demons registration path (drop-in for DICOMautomaton's Alignment_Demons).
+ *
+ * The reference has no FFI for this path: `AlignViaDemons` (src/Alignment_Demons.h:233-236) constructs a file-local
+ * SYCL engine (src/Alignment_Demons.cc:52-704) in-process.  This header is the boundary a maintainer binds instead;
+ * every entry point names the reference interface it replaces.  Plain C, plain pointers and sizes, no C++/torch types,
+ * nothing throws across it: every call returns 0 on success or a negative dcma_b200_status and leaves a message in
+ * the caller's error buffer (and in dcma_b200_last_error()).
+ *
+ * There is NO CPU fallback: without a CUDA device (sm_100a) every compute entry point fails with DCMA_B200_ENODEVICE.
+ *
+ * Layouts (identical to the reference): images are dense row-major  idx = ((z*rows + y)*cols + x)*channels + c
+ * (src/Alignment_Demons.h:77-79), float; vector fields handed across this boundary are double, 3 interleaved
+ * components per voxel in mm along the index axes (x=column, y=row, z=slice), pull convention
+ * warped(p) = moving(p + D(p)) (src/Alignment_Demons.h:217-220).
+ */
+#ifndef DCMA_B200_DEMONS_C_API_H
+#define DCMA_B200_DEMONS_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCMA_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DCMA_B200_API __attribute__((visibility("default")))
+#else
+#define DCMA_B200_API
+#endif
+
+typedef enum {
+    DCMA_B200_OK = 0,
+    DCMA_B200_EINVAL = -1,    /* bad argument (reference: std::invalid_argument) */
+    DCMA_B200_ENODEVICE = -2, /* no usable CUDA device / wrong architecture */
+    DCMA_B200_ECUDA = -3,     /* CUDA runtime error (reference: SYCL async exception, cc:140-150) */
+    DCMA_B200_ENOMEM = -4,
+    DCMA_B200_ESTATE = -5     /* call made in the wrong engine state */
+} dcma_b200_status;
+
+/* Header of `demons_volume<T>` (src/Alignment_Demons.h:64-74). */
+typedef struct {
+    int64_t slices, rows, cols, channels;
+    double pxl_dx, pxl_dy, pxl_dz; /* mm: x=column spacing, y=row spacing, z=slice spacing */
+} dcma_b200_geom;
+
+/* How the gradient/update/deformation fields are held in HBM. */
+typedef enum {
+    DCMA_B200_FIELD_FP64 = 0,        /* double storage + double arithmetic with FMA contraction (default) */
+    DCMA_B200_FIELD_FP64_STRICT = 1, /* double storage, no contraction, IEEE division: bit-identical deformation field
+                                        to the reference's x86-64 build */
+    DCMA_B200_FIELD_FP32 = 2         /* float storage, fp32 smoothing; coordinates/interpolation/force stay fp64 */
+} dcma_b200_field_mode;
+
+/* POD mirror of `AlignViaDemonsParams` (src/Alignment_Demons.h:20-61), same names, same defaults
+ * (dcma_b200_demons_params_default), followed by additive extension fields whose defaults keep reference behaviour. */
+typedef struct {
+    int64_t max_iterations;                   /* 100 */
+    double convergence_threshold;             /* 0.001 */
+    double deformation_field_smoothing_sigma; /* 1.0 mm */
+    double update_field_smoothing_sigma;      /* 0.5 mm; only used when use_diffeomorphic (cc:86) */
+    int32_t use_diffeomorphic;                /* 0 */
+    int32_t use_histogram_matching;           /* 0; host-side pre-step, ignored by this library (cc:967-972) */
+    int64_t histogram_bins;                   /* 256; ditto */
+    double histogram_outlier_fraction;        /* 0.01; ditto */
+    double normalization_factor;              /* 1.0 */
+    double max_update_magnitude;              /* 2.0 */
+    int64_t verbosity;                        /* 1; >=1 prints one line per iteration to stderr (cc:983-985) */
+    /* ---- extensions (absent in the reference) ---- */
+    int32_t field_mode;          /* dcma_b200_field_mode; default DCMA_B200_FIELD_FP64 */
+    int32_t device;              /* CUDA device ordinal; -1 = current device */
+    int32_t check_every;         /* iterations between host polls of the device-side convergence flag; 0 = auto */
+    int32_t pyramid_levels;      /* 1 = reference behaviour (single resolution) */
+    int32_t use_symmetric_force; /* 0 = reference behaviour (fixed-image gradient only) */
+    int32_t fused;               /* 1 (default) = fused loop kernels; 0 = one kernel per reference stage */
+    int32_t reserved[6];
+} dcma_b200_demons_params;
+
+/* Timing/launch statistics of one run (all device-timed with CUDA events on the engine's stream). */
+typedef struct {
+    int64_t iterations_done; /* number of compute_single_iteration equivalents executed (cc:981-995) */
+    int64_t kernel_launches; /* kernels launched by this library inside the loop */
+    double loop_ms;          /* iteration loop only */
+    double h2d_ms, d2h_ms;   /* host<->device copies of the one-shot call (0 for engine-level runs) */
+    double stage_ms[8];      /* per-stage totals when profiling is on: see dcma_b200_stage */
+    int64_t stage_launches[8];
+    int64_t h2d_bytes, d2h_bytes;
+} dcma_b200_run_stats;
+
+typedef enum {
+    DCMA_B200_STAGE_FORCE = 0,     /* compute_update_and_mse            cc:274-343 (fused: warp+force+MSE) */
+    DCMA_B200_STAGE_SMOOTH_U = 1,  /* smooth_on_device(update)          cc:563-702 */
+    DCMA_B200_STAGE_ADD = 2,       /* add_update                        cc:345-369 */
+    DCMA_B200_STAGE_COMPOSE = 3,   /* add_update_diffeomorphic          cc:371-465 */
+    DCMA_B200_STAGE_SMOOTH_D = 4,  /* smooth_on_device(deformation)     cc:563-702 */
+    DCMA_B200_STAGE_WARP = 5,      /* warp_moving                       cc:467-550 */
+    DCMA_B200_STAGE_REDUCE = 6,    /* host MSE loop + convergence test  cc:334-342, 987-993 */
+    DCMA_B200_STAGE_GRADIENT = 7   /* compute_gradient                  cc:208-272 (stage API only) */
+} dcma_b200_stage;
+
+typedef enum { /* buffers addressable through engine_get/engine_set (same numbering as the oracle harness) */
+    DCMA_B200_BUF_FIXED = 0,
+    DCMA_B200_BUF_MOVING = 1,
+    DCMA_B200_BUF_WARPED = 2,   /* float[N*channels] */
+    DCMA_B200_BUF_GRADIENT = 3, /* double[N*3], computed on demand */
+    DCMA_B200_BUF_UPDATE = 4,   /* double[N*3] */
+    DCMA_B200_BUF_DEFORMATION = 5
+} dcma_b200_buffer;
+
+typedef struct dcma_b200_engine dcma_b200_engine; /* opaque; replaces `sycl_demons_engine` (cc:52-704) */
+
+/* ---- library ----------------------------------------------------------------------------------------------- */
+DCMA_B200_API int dcma_b200_abi_version(void);
+DCMA_B200_API const char *dcma_b200_last_error(void); /* thread-local message of the last failing call */
+DCMA_B200_API int dcma_b200_device_count(void);       /* number of CUDA devices visible, 0 if none (never fails) */
+DCMA_B200_API void dcma_b200_demons_params_default(dcma_b200_demons_params *p); /* defaults of Alignment_Demons.h:20-61 */
+
+/* ---- one-shot registration on HOST buffers ----------------------------------------------------------------- */
+/* Replaces, inside AlignViaDemons, the block  `sycl_demons_engine engine(fixed_vol, moving_vol, params); for(iter...)
+ * { engine.compute_single_iteration(); ... } engine.export_deformation_volume()`  (src/Alignment_Demons.cc:977-997).
+ * `moving_on_fixed_grid` is the moving image after resample_image_to_reference_grid / histogram_match (cc:964-972).
+ * deformation_out: N*3 doubles (AoS z,y,x,c).  mse_history: max_iterations doubles or NULL.  stats may be NULL.
+ * Blocking; H2D and D2H copies happen inside the call. */
+DCMA_B200_API int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, const float *moving_on_fixed_grid,
+                              const dcma_b200_demons_params *params, double *deformation_out, double *mse_history,
+                              dcma_b200_run_stats *stats, char *errbuf, size_t errbuf_len);
+
+/* ---- engine API (device-resident; used by the benchmark, the parity tests and the slab/batch drivers) ------- */
+/* Constructor of sycl_demons_engine (cc:54-75): allocates device buffers for `geom`. `stream` is a cudaStream_t
+ * (NULL = the library creates its own non-blocking stream). */
+DCMA_B200_API int dcma_b200_engine_create(dcma_b200_engine **out, const dcma_b200_geom *geom, const dcma_b200_demons_params *params,
+                            void *stream, char *errbuf, size_t errbuf_len);
+DCMA_B200_API void dcma_b200_engine_destroy(dcma_b200_engine *e); /* cc:77-79 */
+
+/* allocate_device_memory's copies (cc:181-186): F, M uploaded, W := M, D := 0, U := 0, iteration counter := 0.
+ * `on_device` != 0 means the pointers are device pointers on the engine's device (no PCIe traffic). */
+DCMA_B200_API int dcma_b200_engine_load(dcma_b200_engine *e, const float *fixed, const float *moving_on_fixed_grid, int on_device);
+
+/* The loop of AlignViaDemons (cc:980-995) for at most `max_iterations` further iterations (continues from the
+ * current state; convergence is evaluated on the device with the reference's rule). `profile` != 0 brackets every
+ * kernel with CUDA events and fills stats->stage_ms. mse_history: HOST array of max_iterations doubles or NULL. */
+DCMA_B200_API int dcma_b200_engine_run(dcma_b200_engine *e, int64_t max_iterations, int profile, double *mse_history,
+                         dcma_b200_run_stats *stats);
+
+/* One reference engine method at a time (stage-level parity; same order of buffers as the reference):
+ * FORCE reads `warped` and writes `update` and returns (mse, n_valid) through the two pointers. */
+DCMA_B200_API int dcma_b200_engine_stage(dcma_b200_engine *e, int stage, double sigma_mm, double *mse_out, int64_t *n_valid_out);
+
+/* export_deformation_volume (cc:110-113) and friends; `host` is a host pointer sized as in dcma_b200_buffer. */
+DCMA_B200_API int dcma_b200_engine_get(dcma_b200_engine *e, int buffer, void *host);
+DCMA_B200_API int dcma_b200_engine_set(dcma_b200_engine *e, int buffer, const void *host);
+/* Same as get(DEFORMATION) but into a DEVICE pointer (double[N*3], AoS) -- for device-resident consumers. */
+DCMA_B200_API int dcma_b200_engine_export_deformation_device(dcma_b200_engine *e, double *device_out);
+
+/* Synchronise the engine's stream (cudaStreamSynchronize). */
+DCMA_B200_API int dcma_b200_engine_sync(dcma_b200_engine *e);
+/* Bytes of HBM the engine holds. */
+DCMA_B200_API int64_t dcma_b200_engine_device_bytes(const dcma_b200_engine *e);
+
+/* ---- warp an image with a deformation field on the same grid (warp_moving semantics, cc:467-550) ------------ */
+/* out[p] = image(p + D(p)) with the reference's strict validity rule; `oob_value` replaces NaN when finite
+ * (WarpImages uses 0.0, src/Operations/WarpImages.cc:197,452).  All pointers HOST. */
+DCMA_B200_API int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
+                         int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCMA_B200_DEMONS_C_API_H */
