@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""Benchmark of the B200-native Demons registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-mode fp64|fp64_strict|fp32]
+
+A "step" is one pass of the hot path over one batch of synthetic input: one Demons registration of `--iters`
+iterations (default 200) on the BASELINE config-2 workload -- synthetic CT pair 512x512x256, diffeomorphic,
+sigma_d = sigma_u = 1.5 mm, convergence threshold 0 (exactly `iters` iterations run).  The metric is voxel-updates/s
+(voxels x iterations executed / time).
+
+  value     : loop-only throughput, inputs resident in HBM, device-timed (CUDA events on the engine's stream),
+              max over ranks.  N > 1: one independent registration per GPU (BASELINE config 5 style, weak scaling,
+              no data-path collective).
+  e2e       : the same metric through the C-ABI one-shot call `dcma_b200_demons_register` with HOST (pinned) buffers:
+              H2D of fixed+moving, the loop, and D2H of the fp64 deformation field are all inside the timed region.
+  roofline  : dominant kernel (k_smooth3d): algorithmic bytes per launch / mean launch time from CUDA events.
+  cpu_baseline : the reference's own engine (oracle/_ref, built from /root/reference sources) on the host cores.
+
+`--impl reference` times the reference CPU engine itself on a bounded sample of the same workload.
+Only the cpu_baseline / --impl reference legs touch `oracle/`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {"shape": (256, 512, 512), "spacing": (1.0, 1.0, 1.0), "sigma_d": 1.5, "sigma_u": 1.5,
+            "diffeomorphic": True}
+# algorithmic bytes per voxel-update, SURVEY.md section 8(d): diffeomorphic, C=1
+B_ALG = {"fp32": 136.0, "fp64": 256.0, "fp64_strict": 256.0}
+FIELD_BYTES = {"fp32": 4, "fp64": 8, "fp64_strict": 8}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_baseline(budget_s: float = 25.0, iters_timed: int = 3):
+    """Times the reference engine (oracle/_ref) on the host cores on a bounded sample of the workload.
+
+    Returns dict(value, unit, cores, kind, sample, ms_per_iter).  Test infrastructure used as a reported baseline."""
+    import numpy as np
+    import oracle
+    from dicomautomaton_b200 import phantom
+    kind = "reference" if oracle.available("reference") else "port"
+    okind = "reference" if kind == "reference" else "port"
+    cores = oracle.worker_threads(okind)
+    par = oracle.make_params(max_iterations=1, convergence_threshold=0.0,
+                             deformation_field_smoothing_sigma=WORKLOAD["sigma_d"],
+                             update_field_smoothing_sigma=WORKLOAD["sigma_u"],
+                             use_diffeomorphic=WORKLOAD["diffeomorphic"])
+    # calibrate on 64x128x128 (1/64 of the workload), then pick the largest sample that fits the budget
+    f, m = phantom.make_pair((64, 128, 128))
+    eng = oracle.OracleEngine(f.numpy(), m.numpy(), par, kind=okind)
+    eng.iterate()
+    t = time.perf_counter()
+    eng.iterate()
+    per_vox = (time.perf_counter() - t) / (64 * 128 * 128)
+    eng.close()
+    full = WORKLOAD["shape"]
+    shape = None
+    for div in (1, 2, 4):
+        cand = (full[0] // div, full[1] // div, full[2] // div)
+        est = per_vox * cand[0] * cand[1] * cand[2] * (iters_timed + 1.5)
+        mem_gb = cand[0] * cand[1] * cand[2] * 220 / 1e9
+        try:
+            avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 1e9
+        except Exception:
+            avail_gb = 16.0
+        if est <= budget_s and mem_gb < 0.6 * avail_gb:
+            shape = cand
+            break
+    if shape is None:
+        shape = (full[0] // 4, full[1] // 4, full[2] // 4)
+    dev = "cpu"
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = "cuda"
+    except Exception:
+        pass
+    f, m = phantom.make_pair(shape, device=dev)
+    f, m = f.cpu().numpy(), m.cpu().numpy()
+    eng = oracle.OracleEngine(f, m, par, kind=okind)
+    eng.iterate()  # warm-up (first iteration also has W = M)
+    t = time.perf_counter()
+    for _ in range(iters_timed):
+        eng.iterate()
+    dt = time.perf_counter() - t
+    eng.close()
+    nvox = shape[0] * shape[1] * shape[2]
+    return {"value": nvox * iters_timed / dt, "unit": "voxel-updates/s", "cores": cores, "kind": kind,
+            "sample": f"{shape[2]}x{shape[1]}x{shape[0]} sub-volume of the workload phantom, same parameters, "
+                      f"1 warm-up + {iters_timed} timed iterations of compute_single_iteration",
+            "ms_per_iter": 1e3 * dt / iters_timed}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU engine on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, ms = [], []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_baseline(budget_s=max(8.0, 150.0 / max(1, args.warmup + args.steps)), iters_timed=2)
+        if i >= args.warmup:
+            vals.append(base["value"])
+            ms.append(base["ms_per_iter"])
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "demons_voxel_updates_per_s", "value": v, "unit": "voxel-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms) * 2,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, "fp64"),
+            "cpu_baseline": {"value": v, "unit": "voxel-updates/s", "cores": base["cores"], "kind": base["kind"],
+                             "sample": base["sample"]},
+            "e2e": {"value": v, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, mode):
+    s = WORKLOAD["shape"]
+    return {"workload": f"BASELINE config 2: synthetic CT pair {s[2]}x{s[1]}x{s[0]} (textured phantom + known sinusoidal "
+                        f"warp), diffeomorphic Demons, sigma_d=sigma_u={WORKLOAD['sigma_d']} mm (r=4, 9 taps), "
+                        f"{args.iters} iterations per step, threshold 0",
+            "iterations_per_step": args.iters, "field_mode": mode,
+            "parallelism": "single GPU" if args.gpus == 1 else f"{args.gpus} independent registrations, one per GPU",
+            "l2": "working set (>= 3 GB of fields) is far larger than the 126 MB L2; no flush needed"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from dicomautomaton_b200 import capi, phantom
+    from dicomautomaton_b200.demons import AlignViaDemonsParams, DemonsEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    mode = args.field_mode
+    shape, spacing = WORKLOAD["shape"], WORKLOAD["spacing"]
+    nvox = shape[0] * shape[1] * shape[2]
+
+    fixed, moving = phantom.make_pair(shape, spacing=spacing, case=rank, device=dev)
+    torch.cuda.synchronize()
+    par = AlignViaDemonsParams(max_iterations=args.iters, convergence_threshold=0.0,
+                               deformation_field_smoothing_sigma=WORKLOAD["sigma_d"],
+                               update_field_smoothing_sigma=WORKLOAD["sigma_u"],
+                               use_diffeomorphic=WORKLOAD["diffeomorphic"], verbosity=0, field_mode=mode,
+                               device=local)
+    stream = torch.cuda.current_stream()
+    # engine on torch's current stream so torch.cuda.Event brackets exactly its kernels
+    eng = DemonsEngine.empty(shape, spacing, par, stream=stream.cuda_stream)
+
+    def step():
+        eng.load_device(fixed.data_ptr(), moving.data_ptr())
+        hist, st = eng.run(args.iters, profile=False)
+        return hist, st
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    iters_done = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        hist, st = step()
+        launches += st.kernel_launches
+        iters_done += st.iterations_done
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    final_mse = float(hist[-1]) if len(hist) else float("nan")
+    t = torch.tensor([ms, float(iters_done), float(launches)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        iters_all, launches_all = float(tsum[1]), int(tsum[2])
+    else:
+        iters_all, launches_all = float(iters_done), int(launches)
+    value = nvox * iters_all / (ms * 1e-3)
+
+    # ---- per-stage profile (one extra step, events around every kernel) -> roofline of the dominant kernel
+    eng.load_device(fixed.data_ptr(), moving.data_ptr())
+    _, pst = eng.run(args.iters, profile=True)
+    stage = {capi.STAGE_NAMES[i]: {"ms": pst.stage_ms[i], "launches": int(pst.stage_launches[i])} for i in range(8)
+             if pst.stage_launches[i] > 0}
+    sm_ms = pst.stage_ms[capi.STAGE_SMOOTH_U] + pst.stage_ms[capi.STAGE_SMOOTH_D]
+    sm_n = pst.stage_launches[capi.STAGE_SMOOTH_U] + pst.stage_launches[capi.STAGE_SMOOTH_D]
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes_per_launch = 2.0 * 3.0 * nvox * FIELD_BYTES[mode]  # one read + one write of a 3-component field
+    achieved = alg_bytes_per_launch / (sm_ms / max(sm_n, 1) * 1e-3) / 1e9 if sm_n else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get(mode, {}).get("k_smooth3d_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_smooth3d (separable 3-D Gaussian, one launch per field smooth)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "ms_per_launch": sm_ms / max(sm_n, 1), "share_of_step": sm_ms / max(pst.loop_ms, 1e-9),
+                "whole_iteration": {"algorithmic_bytes_per_voxel_update": B_ALG[mode],
+                                    "achieved_GBs": value / max(world, 1) * B_ALG[mode] / 1e9,
+                                    "frac_of_peak": value / max(world, 1) * B_ALG[mode] / 1e9 / peak},
+                "stages": stage}
+    eng.close()
+
+    # ---- end to end through the C-ABI one-shot call with pinned HOST buffers
+    lib = capi.lib()
+    import ctypes as C
+    hf = fixed.cpu().pin_memory()
+    hm = moving.cpu().pin_memory()
+    hD = torch.empty((nvox, 3), dtype=torch.float64).pin_memory()
+    geom = capi.Geom(shape[0], shape[1], shape[2], 1, *spacing)
+    cp = par.to_c()
+    err = C.create_string_buffer(512)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    stats = capi.RunStats()
+
+    def e2e_step():
+        capi.check(lib.dcma_b200_demons_register(C.byref(geom), hf.data_ptr(), hm.data_ptr(), C.byref(cp),
+                                                 hD.data_ptr(), None, C.byref(stats), err, len(err)), err)
+    e2e_step()  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        e2e_step()
+        e2e_iters += stats.iterations_done
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(e2e_iters)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        a = te.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = te.clone()
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_iters = float(a[0]), float(b[1])
+    e2e = {"value": nvox * e2e_iters / e2e_s, "unit": "voxel-updates/s",
+           "h2d_bytes_per_step": int(stats.h2d_bytes), "d2h_bytes_per_step": int(stats.d2h_bytes),
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "h2d_ms": stats.h2d_ms, "d2h_ms": stats.d2h_ms, "loop_ms": stats.loop_ms,
+           "api": "dcma_b200_demons_register (C ABI, host pinned buffers, fp64 AoS deformation out)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_baseline()
+        except Exception as ex:  # the baseline is reported context, never the product path
+            cpu = {"value": None, "unit": "voxel-updates/s", "cores": None, "kind": "unavailable", "sample": str(ex)}
+
+    if rank == 0:
+        line = {"metric": "demons_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64" if mode != "fp32" else "f32 fields / f64 coordinates+force",
+                "data": "synthetic", "config": workload_config(args, mode),
+                "ms_per_iteration": ms / max(iters_done, 1), "final_mse": final_mse,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters", type=int, default=200, help="Demons iterations per step (BASELINE config 2: 200)")
+    ap.add_argument("--field-mode", default=os.environ.get("DCMA_B200_FIELD_MODE", "fp64"),
+                    choices=["fp64", "fp64_strict", "fp32"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -167,7 +167,7 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
 //   w_src = 0: W := M (first iteration: the engine copies M into warped, cc:183 -- NOT a zero-field warp)
 //   w_src = 1: W := warp(M, D) computed in registers, never written to HBM
 //   w_src = 2: W read from `Wbuf` (stage API: the unfused compute_update_and_mse)
-// Tile = 32 x 8 voxels of one slice per 256-thread block, grid-stride over tiles; the fixed-image gradient is
+// Tile = 32 x 8 voxels of one slice per 256-thread block, 3-D grid striding over slices; the fixed-image gradient is
 // recomputed from F (7-point stencil served by L1/L2) instead of being read back as 3 field components.
 // MSE terms are reduced warp-shuffle -> block -> one (sum, count) partial per block (deterministic for a fixed grid).
 // ------------------------------------------------------------------------------------------------------------------
@@ -177,21 +177,17 @@ template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
                  const T *__restrict__ D, T *__restrict__ U, const Geo g, const int w_src, const double norm_eps,
-                 const double inv_norm_eps, const double max_update, const int ntx, const int nty,
-                 const long long ntiles, double *__restrict__ part_sum, long long *__restrict__ part_cnt,
+                 const double inv_norm_eps, const double max_update, double *__restrict__ part_sum, long long *__restrict__ part_cnt,
                  const Ctrl *__restrict__ ctrl, const long long it) {
     if (it > ctrl->converged_at) return;
     double acc = 0.0;
     long long cnt = 0;
     const long long N = g.N;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx_i = static_cast<int>(tile % ntx);
-        const long long rest = tile / ntx;
-        const int ty_i = static_cast<int>(rest % nty);
-        const int z = static_cast<int>(rest / nty);
-        const int x = tx_i * kTileX + threadIdx.x;
-        const int y = ty_i * kTileY + threadIdx.y;
-        if (x >= g.C || y >= g.R) continue;
+    const int x = blockIdx.x * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    const bool in_tile = (x < g.C) && (y < g.R);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
+        if (!in_tile) break;
         const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
         const float fixed_val = __ldg(F + v * g.CH);
         float moving_val;
@@ -240,8 +236,9 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             a += s_acc[i];
             c += s_cnt[i];
         }
-        part_sum[blockIdx.x] = a;
-        part_cnt[blockIdx.x] = c;
+        const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        part_sum[b] = a;
+        part_cnt[b] = c;
     }
 }
 
@@ -295,17 +292,14 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_warp(const float *__restrict__ M, const T *__restrict__ D, float *__restrict__ W, const Geo g, const int ntx,
-           const int nty, const long long ntiles, const int use_oob, const float oob_value) {
+    k_warp(const float *__restrict__ M, const T *__restrict__ D, float *__restrict__ W, const Geo g, const int use_oob,
+           const float oob_value) {
     const long long N = g.N;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx_i = static_cast<int>(tile % ntx);
-        const long long rest = tile / ntx;
-        const int ty_i = static_cast<int>(rest % nty);
-        const int z = static_cast<int>(rest / nty);
-        const int x = tx_i * kTileX + threadIdx.x;
-        const int y = ty_i * kTileY + threadIdx.y;
-        if (x >= g.C || y >= g.R) continue;
+    const int x = blockIdx.x * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    const bool in_tile = (x < g.C) && (y < g.R);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
+        if (!in_tile) break;
         const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
         const double dx = static_cast<double>(D[v]), dy = static_cast<double>(D[v + N]),
                      dz = static_cast<double>(D[v + 2 * N]);
@@ -322,16 +316,12 @@ __global__ void __launch_bounds__(kTileX *kTileY)
 
 // k_gradient: compute_gradient as its own kernel, AoS double output (stage API / inspection only).
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_gradient(const float *__restrict__ F, double *__restrict__ G_aos, const Geo g, const int ntx, const int nty,
-               const long long ntiles) {
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx_i = static_cast<int>(tile % ntx);
-        const long long rest = tile / ntx;
-        const int ty_i = static_cast<int>(rest % nty);
-        const int z = static_cast<int>(rest / nty);
-        const int x = tx_i * kTileX + threadIdx.x;
-        const int y = ty_i * kTileY + threadIdx.y;
-        if (x >= g.C || y >= g.R) continue;
+    k_gradient(const float *__restrict__ F, double *__restrict__ G_aos, const Geo g) {
+    const int x = blockIdx.x * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    const bool in_tile = (x < g.C) && (y < g.R);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
+        if (!in_tile) break;
         const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
         double gx, gy, gz;
         grad_fixed(F, g, x, y, z, gx, gy, gz);
@@ -369,18 +359,14 @@ __device__ __forceinline__ double fetch_u(const T *__restrict__ Uc, const Geo &g
 
 template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int ntx, const int nty,
-              const long long ntiles, const Ctrl *__restrict__ ctrl, const long long it) {
+    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const Ctrl *__restrict__ ctrl, const long long it) {
     if (it > ctrl->converged_at) return;
     const long long N = g.N;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tx_i = static_cast<int>(tile % ntx);
-        const long long rest = tile / ntx;
-        const int ty_i = static_cast<int>(rest % nty);
-        const int z = static_cast<int>(rest / nty);
-        const int x = tx_i * kTileX + threadIdx.x;
-        const int y = ty_i * kTileY + threadIdx.y;
-        if (x >= g.C || y >= g.R) continue;
+    const int x = blockIdx.x * kTileX + threadIdx.x;
+    const int y = blockIdx.y * kTileY + threadIdx.y;
+    const bool in_tile = (x < g.C) && (y < g.R);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
+        if (!in_tile) break;
         const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
         const double dx = static_cast<double>(D[v]), dy = static_cast<double>(D[v + N]),
                      dz = static_cast<double>(D[v + 2 * N]);

@@ -82,10 +82,14 @@ class Engine final : public EngineBase {
             own_stream_ = true;
         }
 
-        ntx_ = (g_.C + kTileX - 1) / kTileX;
-        nty_ = (g_.R + kTileY - 1) / kTileY;
-        ntiles_ = static_cast<long long>(ntx_) * nty_ * g_.S;
-        grid_vox_ = static_cast<int>(std::min<long long>(ntiles_, static_cast<long long>(sms_) * 8));
+        // per-voxel kernels: 3-D grid of 32x8 tiles, striding over slices; ~16 resident-CTA waves worth of blocks
+        const int ntx = (g_.C + kTileX - 1) / kTileX, nty = (g_.R + kTileY - 1) / kTileY;
+        if (nty > 65535) throw std::invalid_argument("too many rows");
+        const long long per_plane = static_cast<long long>(ntx) * nty;
+        const long long want = static_cast<long long>(sms_) * 8 * 16;
+        const int gz = static_cast<int>(std::max<long long>(1, std::min<long long>(g_.S, (want + per_plane - 1) / per_plane)));
+        grid3_ = dim3(ntx, nty, std::min(gz, 65535));
+        grid_vox_ = static_cast<int>(per_plane * grid3_.z);  // number of MSE partials
         grid_lin_ = static_cast<int>(std::min<long long>((3 * N + 255) / 256, static_cast<long long>(sms_) * 16));
 
         dF_ = alloc<float>(N * g_.CH);
@@ -255,7 +259,7 @@ class Engine final : public EngineBase {
             case DCMA_B200_BUF_GRADIENT: {
                 double *tmp = nullptr;
                 DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
-                k_gradient<<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dF_, tmp, g_, ntx_, nty_, ntiles_);
+                k_gradient<<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dF_, tmp, g_);
                 DCMA_CUDA(cudaGetLastError());
                 DCMA_CUDA(cudaMemcpyAsync(host, tmp, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream_));
                 DCMA_CUDA(cudaStreamSynchronize(stream_));
@@ -468,9 +472,9 @@ class Engine final : public EngineBase {
     void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true) {
         if (w_src == 2) ensure_warped_buffer();
         const double norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
-        k_warp_force<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(
-            dF_, dM_, dW_, dD_, dU_, g_, w_src, norm_eps, 1.0 / norm_eps, p_.max_update_magnitude, ntx_, nty_, ntiles_,
-            d_part_sum_, d_part_cnt_, d_ctrl_, it);
+        k_warp_force<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(
+            dF_, dM_, dW_, dD_, dU_, g_, w_src, norm_eps, 1.0 / norm_eps, p_.max_update_magnitude, d_part_sum_,
+            d_part_cnt_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
         if (reduce) launch_reduce(it, d_hist, hist_idx, count_iter && d_hist != nullptr ? 1 : 0);
@@ -487,7 +491,7 @@ class Engine final : public EngineBase {
         ++launches_;
     }
     void launch_compose(long long it) {
-        k_compose<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, ntx_, nty_, ntiles_, d_ctrl_, it);
+        k_compose<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -500,7 +504,7 @@ class Engine final : public EngineBase {
     void launch_warp_to_buffer(long long it = 0) {
         (void)it;
         ensure_warped_buffer();
-        k_warp<T, STRICT><<<grid_vox_, dim3(kTileX, kTileY), 0, stream_>>>(dM_, dD_, dW_, g_, ntx_, nty_, ntiles_, 0, 0.f);
+        k_warp<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -589,8 +593,8 @@ class Engine final : public EngineBase {
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     bool loaded_ = false;
-    int ntx_ = 0, nty_ = 0, grid_vox_ = 1, grid_lin_ = 1;
-    long long ntiles_ = 0;
+    dim3 grid3_;
+    int grid_vox_ = 1, grid_lin_ = 1;
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
     T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;
     double *d_part_sum_ = nullptr;

@@ -100,23 +100,33 @@ class DemonsEngine:
 
     Method names follow the reference engine's methods so stage-level parity tests read like the reference."""
 
-    def __init__(self, fixed: demons_volume, moving: demons_volume, params: AlignViaDemonsParams, stream: int = 0,
-                 load: bool = True):
+    def __init__(self, fixed: demons_volume, moving: demons_volume, params: AlignViaDemonsParams, stream: int = 0):
         if fixed.data.shape != moving.data.shape:
             raise ValueError("fixed and moving volumes must have the same shape (resample first)")
+        self._create(fixed.data.shape[:3], (fixed.pxl_dx, fixed.pxl_dy, fixed.pxl_dz), fixed.channels, params, stream)
+        self.load(_as_f32(fixed), _as_f32(moving))
+
+    @classmethod
+    def empty(cls, shape, spacing, params: AlignViaDemonsParams, channels: int = 1, stream: int = 0):
+        """Engine with allocated but unfilled buffers; fill with load()/load_device().  `stream` is a cudaStream_t
+        handle (e.g. torch.cuda.current_stream().cuda_stream); 0 lets the library create its own stream."""
+        self = cls.__new__(cls)
+        self._create(tuple(int(v) for v in shape), spacing, channels, params, stream)
+        return self
+
+    def _create(self, shape, spacing, channels, params, stream):
         self._lib = capi.lib()
         self.params = params
-        self.shape = fixed.data.shape[:3]
-        self.channels = fixed.channels
+        self.shape = tuple(shape)
+        self.channels = int(channels)
         self.n_voxels = int(np.prod(self.shape))
-        self._geom = fixed.geom()
+        self._geom = capi.Geom(self.shape[0], self.shape[1], self.shape[2], self.channels, float(spacing[0]),
+                               float(spacing[1]), float(spacing[2]))
         self._cparams = params.to_c()
         self._h = C.c_void_p()
         err = C.create_string_buffer(512)
         capi.check(self._lib.dcma_b200_engine_create(C.byref(self._h), C.byref(self._geom), C.byref(self._cparams),
                                                      C.c_void_p(stream), err, len(err)), err)
-        if load:
-            self.load(_as_f32(fixed), _as_f32(moving))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
