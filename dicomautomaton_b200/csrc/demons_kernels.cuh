@@ -26,109 +26,263 @@
 namespace DCMA_NS {
 using namespace ::dcma;
 
+constexpr int kTileX = 32, kTileY = 8;  // per-voxel kernels: 32 x 8 voxels of one slice per 256-thread block
+
 // ------------------------------------------------------------------------------------------------------------------
-// small helpers
+// scalar helpers.  B200 runs F2F/F2I/I2F/FRND/MUFU at 16 lanes/clk/SM (measured with ncu: the "xu" pipe), four times
+// slower than the fp64 pipe, so floor() and int<->double conversions are done with fp64/fp32 adds instead.
 // ------------------------------------------------------------------------------------------------------------------
-template <bool STRICT>
-__device__ __forceinline__ double mm_to_index(double d, double p, double ip) {
-    if (STRICT) return (p == 1.0) ? d : d / p;  // reference: dx / pxl_dx (cc:403, cc:501)
-    return d * ip;
+__device__ __forceinline__ bool finite_f(float v) { return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u; }
+__device__ __forceinline__ bool finite_d(double v) { return (static_cast<unsigned>(__double2hiint(v)) & 0x7ff00000u) != 0x7ff00000u; }
+
+// floor of |s| < 2^31 as (double f, int i), exactly: s + 1.5*2^52 rounds to the nearest integer, whose two's complement
+// sits in the low word; one compare fixes round-to-nearest into round-down.
+__device__ __forceinline__ void floor_split(double s, double &f, int &i) {
+    constexpr double kMagic = 6755399441055744.0;
+    const double t = __dadd_rn(s, kMagic);
+    double r = __dadd_rn(t, -kMagic);
+    int n = __double2loint(t);
+    if (r > s) {
+        r = __dadd_rn(r, -1.0);
+        n -= 1;
+    }
+    f = r;
+    i = n;
+}
+// same for |s| < 2^22 in fp32 (magic 1.5*2^23)
+__device__ __forceinline__ void floor_split(float s, float &f, int &i) {
+    constexpr float kMagic = 12582912.0f;
+    const float t = __fadd_rn(s, kMagic);
+    float r = __fadd_rn(t, -kMagic);
+    int n = static_cast<int>(__float_as_uint(t) & 0x7fffffu) - 0x400000;
+    if (r > s) {
+        r = __fadd_rn(r, -1.0f);
+        n -= 1;
+    }
+    f = r;
+    i = n;
 }
 
-struct Tri {
-    int x0, y0, z0;
-    double tx, ty, tz;
+// x rounded to float precision and widened again (the reference narrows four corners to float, cc:439-442).
+//   STRICT: the real conversions.  Otherwise Veltkamp's split (3 fp64 ops, no conversion pipe): identical except on
+//   exact ties and outside the float exponent range, neither of which matters below 1e-12 mm.
+template <bool STRICT>
+__device__ __forceinline__ double narrow_to_float(double x) {
+    if (STRICT) return static_cast<double>(static_cast<float>(x));
+    const double c = __dmul_rn(x, 536870913.0);  // 2^29 + 1
+    return __dsub_rn(c, __dsub_rn(c, x));
+}
+template <bool STRICT>
+__device__ __forceinline__ float narrow_to_float(float x) {
+    return x;
+}
+
+// (double)a - (double)b with one conversion instead of two whenever the fp32 subtraction is exact (TwoSum error == 0);
+// 0 if either value is non-finite (cc:238, 249, 260).  Exact in every case.
+__device__ __forceinline__ double diff_exact(float a, float b) {
+    const float s = __fsub_rn(a, b);
+    if (finite_f(s)) {
+        const float bb = __fsub_rn(s, a);
+        const float e = __fadd_rn(__fsub_rn(a, __fsub_rn(s, bb)), __fsub_rn(-b, bb));
+        if (e == 0.0f) return static_cast<double>(s);
+    }
+    if (finite_f(a) && finite_f(b)) return static_cast<double>(a) - static_cast<double>(b);
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sample position of a voxel displaced by d mm along one axis (cc:401-421, cc:501-513): integer corner i0 and
+// fraction t.  Clamped to [-4, extent+4]: a clamped coordinate has both corners outside the grid either way, and the
+// reference's int64 cast of an absurd coordinate would be undefined.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool STRICT>
+__device__ __forceinline__ void axis_coord(int xi, double xd, double d, double p, double ip, double lim, int &i0,
+                                           double &t) {
+    (void)xi;
+    double s = xd + (STRICT ? ((p == 1.0) ? d : d / p) : d * ip);  // reference: x + dx / pxl_dx
+    s = fmin(fmax(s, -4.0), lim);
+    double f;
+    floor_split(s, f, i0);
+    t = s - f;
+}
+template <bool STRICT>
+__device__ __forceinline__ void axis_coord(int xi, float xd, float d, float p, float ip, float lim, int &i0, float &t) {
+    (void)xd;
+    (void)p;
+    // fp32 mode: never add the voxel index to the displacement (that would cost 10 bits of the fraction)
+    float s = fminf(fmaxf(d * ip, -lim), lim);
+    float f;
+    int n;
+    floor_split(s, f, n);
+    i0 = xi + n;
+    t = s - f;
+}
+
+// per-kernel constants of the compute type
+template <typename CT>
+struct AxisK {
+    CT px, py, pz, ipx, ipy, ipz, limx, limy, limz;
+    __device__ __forceinline__ explicit AxisK(const Geo &g)
+        : px(static_cast<CT>(g.px)), py(static_cast<CT>(g.py)), pz(static_cast<CT>(g.pz)),
+          ipx(static_cast<CT>(g.ipx)), ipy(static_cast<CT>(g.ipy)), ipz(static_cast<CT>(g.ipz)),
+          limx(static_cast<CT>(g.C + 4)), limy(static_cast<CT>(g.R + 4)), limz(static_cast<CT>(g.S + 4)) {}
 };
 
-// Sample coordinates of voxel (x,y,z) displaced by (dx,dy,dz) mm: cc:401-421 and cc:501-513.
-template <bool STRICT>
-__device__ __forceinline__ Tri tri_coords(const Geo &g, int x, int y, int z, double dx, double dy, double dz) {
-    const double sx = static_cast<double>(x) + mm_to_index<STRICT>(dx, g.px, g.ipx);
-    const double sy = static_cast<double>(y) + mm_to_index<STRICT>(dy, g.py, g.ipy);
-    const double sz = g.is2d ? static_cast<double>(z) : (static_cast<double>(z) + mm_to_index<STRICT>(dz, g.pz, g.ipz));
-    // floor() then clamp into [-2, extent]: both corners of a clamped coordinate are outside the grid either way, and
-    // the int conversion stays defined for absurd displacements (the reference's int64 cast would be UB there).
-    double fx = floor(sx), fy = floor(sy), fz = floor(sz);
-    fx = fmin(fmax(fx, -2.0), static_cast<double>(g.C));
-    fy = fmin(fmax(fy, -2.0), static_cast<double>(g.R));
-    fz = fmin(fmax(fz, -2.0), static_cast<double>(g.S));
-    Tri t;
-    t.x0 = static_cast<int>(fx);
-    t.y0 = static_cast<int>(fy);
-    t.z0 = static_cast<int>(fz);
-    t.tx = sx - fx;
-    t.ty = sy - fy;
-    t.tz = g.is2d ? 0.0 : (sz - fz);
+template <typename CT>
+struct Tri {
+    int x0, y0, z0;
+    CT tx, ty, tz;
+};
+
+template <typename CT, bool STRICT>
+__device__ __forceinline__ Tri<CT> tri_coords(const Geo &g, const AxisK<CT> &k, int x, int y, int z, CT xd, CT yd, CT zd,
+                                              CT dx, CT dy, CT dz) {
+    Tri<CT> t;
+    axis_coord<STRICT>(x, xd, dx, k.px, k.ipx, k.limx, t.x0, t.tx);
+    axis_coord<STRICT>(y, yd, dy, k.py, k.ipy, k.limy, t.y0, t.ty);
+    if (g.is2d) {  // cc:405, 413, 421 / cc:503, 510, 513
+        t.z0 = z;
+        t.tz = CT(0);
+    } else {
+        axis_coord<STRICT>(z, zd, dz, k.pz, k.ipz, k.limz, t.z0, t.tz);
+    }
     return t;
 }
 
-__device__ __forceinline__ bool finite_f(float v) { return isfinite(v); }
-
-// warp_moving for one channel of one voxel, cc:515-546.  NaN if any corner is outside the grid or non-finite.
-__device__ __forceinline__ float warp_one(const float *__restrict__ M, const Geo &g, const Tri &t, int c) {
-    const float oob = CUDART_NAN_F;
-    const int x1 = t.x0 + 1, y1 = t.y0 + 1, z1 = g.is2d ? t.z0 : (t.z0 + 1);
-    if (t.x0 < 0 || x1 >= g.C || t.y0 < 0 || y1 >= g.R || t.z0 < 0 || z1 >= g.S) return oob;
-    const long long CH = g.CH;
-    const long long row0 = (static_cast<long long>(t.z0) * g.R + t.y0) * g.C;
-    const long long row1 = row0 + g.C;  // y1 = y0+1
-    const float c000 = __ldg(M + (row0 + t.x0) * CH + c), c100 = __ldg(M + (row0 + x1) * CH + c);
-    const float c010 = __ldg(M + (row1 + t.x0) * CH + c), c110 = __ldg(M + (row1 + x1) * CH + c);
-    float c001 = c000, c101 = c100, c011 = c010, c111 = c110;  // 2-D: reuse the z0 plane (cc:530-533)
-    if (!g.is2d) {
-        const long long dz = static_cast<long long>(g.R) * g.C;
-        c001 = __ldg(M + (row0 + dz + t.x0) * CH + c);
-        c101 = __ldg(M + (row0 + dz + x1) * CH + c);
-        c011 = __ldg(M + (row1 + dz + t.x0) * CH + c);
-        c111 = __ldg(M + (row1 + dz + x1) * CH + c);
+// ------------------------------------------------------------------------------------------------------------------
+// warp_moving for one channel of one voxel (cc:515-546): NaN if any corner is outside the grid or non-finite.
+// Interpolating first and testing the RESULT is equivalent to the reference's eight isfinite tests: with weights in
+// [0,1] finite corners give a finite value inside the float range, and a non-finite corner always yields NaN/Inf.
+//   double path: the reference's fp64 arithmetic, rounded to float once (cc:546).
+//   float  path: fp32 on differences to the first corner (error ~1e-6 HU instead of ~1e-4 HU for plain fp32).
+// Returns diff = fixed - warped through `diff` when WANT_DIFF, and the warped value itself.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename IX, bool CH1>
+__device__ __forceinline__ bool load_corners(const float *__restrict__ M, const Geo &g, int x0, int y0, int z0, int c,
+                                             float (&v)[8]) {
+    const int x1 = x0 + 1, y1 = y0 + 1, z1 = g.is2d ? z0 : (z0 + 1);
+    if (x0 < 0 || x1 >= g.C || y0 < 0 || y1 >= g.R || z0 < 0 || z1 >= g.S) return false;  // cc:516-519
+    const IX row = (static_cast<IX>(z0) * g.R + y0) * g.C + x0;
+    const IX dy = g.C, dz = g.is2d ? IX(0) : static_cast<IX>(g.R) * g.C;
+    if (CH1) {
+        const float *p = M + row;
+        v[0] = __ldg(p);
+        v[1] = __ldg(p + 1);
+        v[2] = __ldg(p + dy);
+        v[3] = __ldg(p + dy + 1);
+        v[4] = __ldg(p + dz);
+        v[5] = __ldg(p + dz + 1);
+        v[6] = __ldg(p + dz + dy);
+        v[7] = __ldg(p + dz + dy + 1);
+    } else {
+        const IX ch = g.CH;
+        const float *p = M + row * ch + c;
+        v[0] = __ldg(p);
+        v[1] = __ldg(p + ch);
+        v[2] = __ldg(p + dy * ch);
+        v[3] = __ldg(p + (dy + 1) * ch);
+        v[4] = __ldg(p + dz * ch);
+        v[5] = __ldg(p + (dz + 1) * ch);
+        v[6] = __ldg(p + (dz + dy) * ch);
+        v[7] = __ldg(p + (dz + dy + 1) * ch);
     }
-    if (!(finite_f(c000) && finite_f(c100) && finite_f(c010) && finite_f(c110) && finite_f(c001) && finite_f(c101) &&
-          finite_f(c011) && finite_f(c111)))
-        return oob;
+    return true;
+}
+
+// v = {c000, c100, c010, c110, c001, c101, c011, c111}
+__device__ __forceinline__ float warp_interp(const float (&v)[8], const Tri<double> &t) {
     const double tx = t.tx, ty = t.ty, tz = t.tz;
-    const double c00 = static_cast<double>(c000) * (1.0 - tx) + static_cast<double>(c100) * tx;
-    const double c10 = static_cast<double>(c010) * (1.0 - tx) + static_cast<double>(c110) * tx;
-    const double c01 = static_cast<double>(c001) * (1.0 - tx) + static_cast<double>(c101) * tx;
-    const double c11 = static_cast<double>(c011) * (1.0 - tx) + static_cast<double>(c111) * tx;
+    const double c00 = static_cast<double>(v[0]) * (1.0 - tx) + static_cast<double>(v[1]) * tx;
+    const double c10 = static_cast<double>(v[2]) * (1.0 - tx) + static_cast<double>(v[3]) * tx;
+    const double c01 = static_cast<double>(v[4]) * (1.0 - tx) + static_cast<double>(v[5]) * tx;
+    const double c11 = static_cast<double>(v[6]) * (1.0 - tx) + static_cast<double>(v[7]) * tx;
     const double c0 = c00 * (1.0 - ty) + c10 * ty;
     const double c1 = c01 * (1.0 - ty) + c11 * ty;
-    return static_cast<float>(c0 * (1.0 - tz) + c1 * tz);
+    const float w = static_cast<float>(c0 * (1.0 - tz) + c1 * tz);
+    return finite_f(w) ? w : CUDART_NAN_F;
+}
+__device__ __forceinline__ float warp_interp(const float (&v)[8], const Tri<float> &t) {
+    const float b = v[0];
+    const float tx = t.tx, ty = t.ty, tz = t.tz;
+    const float e00 = tx * (v[1] - b);  // c000 - b == 0
+    const float e10 = fmaf(tx, v[3] - v[2], v[2] - b);
+    const float e01 = fmaf(tx, v[5] - v[4], v[4] - b);
+    const float e11 = fmaf(tx, v[7] - v[6], v[6] - b);
+    const float e0 = fmaf(ty, e10 - e00, e00);
+    const float e1 = fmaf(ty, e11 - e01, e01);
+    const float w = b + fmaf(tz, e1 - e0, e0);
+    return finite_f(w) ? w : CUDART_NAN_F;
 }
 
+template <typename CT, typename IX, bool CH1>
+__device__ __forceinline__ float warp_one(const float *__restrict__ M, const Geo &g, const Tri<CT> &t, int c) {
+    float v[8];
+    if (!load_corners<IX, CH1>(M, g, t.x0, t.y0, t.z0, c, v)) return CUDART_NAN_F;
+    return warp_interp(v, t);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // compute_gradient for one voxel (channel 0 of the fixed image), cc:232-265: central difference in index units,
-// one-sided (/1) at the borders, zero if a neighbour is non-finite or the extent is 1.
-__device__ __forceinline__ void grad_fixed(const float *__restrict__ F, const Geo &g, int x, int y, int z, double &gx,
-                                           double &gy, double &gz) {
-    const long long CH = g.CH;
-    const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
-    gx = gy = gz = 0.0;
-    if (g.C > 1) {
-        const int xl = (x > 0) ? -1 : 0, xr = (x + 1 < g.C) ? 1 : 0;
-        const float vl = __ldg(F + (v + xl) * CH), vr = __ldg(F + (v + xr) * CH);
-        if (finite_f(vl) && finite_f(vr) && xr != xl)
-            gx = (static_cast<double>(vr) - static_cast<double>(vl)) * ((xr - xl == 2) ? 0.5 : 1.0);  // == /(xr-xl), exact
+// one-sided (/1) at the borders, zero if a neighbour is non-finite or the extent is 1.  The per-thread neighbour
+// offsets/scales along x and y are loop invariants of the caller.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename IX>
+struct GradK {
+    IX xl, xr, yu, yd;      // element offsets of the in-plane neighbours (0 at the borders)
+    float sx, sy;           // 1/(index distance): 0.5, 1 or 0 (extent 1)
+    __device__ __forceinline__ GradK(const Geo &g, int x, int y, IX ch) {
+        const int ixl = (x > 0) ? -1 : 0, ixr = (x + 1 < g.C) ? 1 : 0;
+        const int iyu = (y > 0) ? -1 : 0, iyd = (y + 1 < g.R) ? 1 : 0;
+        xl = ixl * ch;
+        xr = ixr * ch;
+        yu = static_cast<IX>(iyu) * g.C * ch;
+        yd = static_cast<IX>(iyd) * g.C * ch;
+        sx = (g.C > 1 && ixr != ixl) ? ((ixr - ixl == 2) ? 0.5f : 1.0f) : 0.0f;
+        sy = (g.R > 1 && iyd != iyu) ? ((iyd - iyu == 2) ? 0.5f : 1.0f) : 0.0f;
     }
-    if (g.R > 1) {
-        const int yu = (y > 0) ? -1 : 0, yd = (y + 1 < g.R) ? 1 : 0;
-        const float vu = __ldg(F + (v + static_cast<long long>(yu) * g.C) * CH);
-        const float vd = __ldg(F + (v + static_cast<long long>(yd) * g.C) * CH);
-        if (finite_f(vu) && finite_f(vd) && yd != yu)
-            gy = (static_cast<double>(vd) - static_cast<double>(vu)) * ((yd - yu == 2) ? 0.5 : 1.0);
-    }
+};
+
+template <typename IX>
+__device__ __forceinline__ void grad_fixed(const float *__restrict__ Fv, const Geo &g, const GradK<IX> &k, int z,
+                                           IX plane_ch, double &gx, double &gy, double &gz) {
+    // (vr - vl) / (xr - xl) with xr - xl in {1, 2}: multiplying by 1 or 0.5 is the same operation bit for bit
+    gx = (k.sx != 0.0f) ? diff_exact(__ldg(Fv + k.xr), __ldg(Fv + k.xl)) * static_cast<double>(k.sx) : 0.0;
+    gy = (k.sy != 0.0f) ? diff_exact(__ldg(Fv + k.yd), __ldg(Fv + k.yu)) * static_cast<double>(k.sy) : 0.0;
+    gz = 0.0;
     if (g.S > 1) {
-        const long long plane = static_cast<long long>(g.R) * g.C;
         const int zp = (z > 0) ? -1 : 0, zn = (z + 1 < g.S) ? 1 : 0;
-        const float vp = __ldg(F + (v + zp * plane) * CH), vn = __ldg(F + (v + zn * plane) * CH);
-        if (finite_f(vp) && finite_f(vn) && zn != zp)
-            gz = (static_cast<double>(vn) - static_cast<double>(vp)) * ((zn - zp == 2) ? 0.5 : 1.0);
+        gz = diff_exact(__ldg(Fv + zn * plane_ch), __ldg(Fv + zp * plane_ch)) * ((zn - zp == 2) ? 0.5 : 1.0);
+    }
+}
+template <typename IX>
+__device__ __forceinline__ void grad_fixed(const float *__restrict__ Fv, const Geo &g, const GradK<IX> &k, int z,
+                                           IX plane_ch, float &gx, float &gy, float &gz) {
+    const float dx = __ldg(Fv + k.xr) - __ldg(Fv + k.xl);
+    const float dy = __ldg(Fv + k.yd) - __ldg(Fv + k.yu);
+    gx = finite_f(dx) ? dx * k.sx : 0.0f;
+    gy = finite_f(dy) ? dy * k.sy : 0.0f;
+    gz = 0.0f;
+    if (g.S > 1) {
+        const int zp = (z > 0) ? -1 : 0, zn = (z + 1 < g.S) ? 1 : 0;
+        const float dz = __ldg(Fv + zn * plane_ch) - __ldg(Fv + zp * plane_ch);
+        gz = finite_f(dz) ? dz * ((zn - zp == 2) ? 0.5f : 1.0f) : 0.0f;
     }
 }
 
-// Demons force of one voxel, cc:297-330.  norm_eps = normalization_factor + 1e-10 (same double add as cc:315).
+// ------------------------------------------------------------------------------------------------------------------
+// Demons force of one voxel, cc:297-330.
+// ------------------------------------------------------------------------------------------------------------------
+struct ForceK {
+    double norm_eps;      // normalization_factor + 1e-10 (the same double add as cc:315)
+    double inv_norm_eps;  // 1 / norm_eps
+    double max_update;    // cc:281
+    double mu2_lo;        // max_update^2 * (1 - 2^-50): below it sqrt(|u|^2) <= max_update for certain
+};
+
 template <bool STRICT>
 __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, double gx, double gy, double gz,
-                                             double norm_eps, double inv_norm_eps, double max_update, double &ux,
-                                             double &uy, double &uz, double &term, int &valid) {
+                                             const ForceK &k, double &ux, double &uy, double &uz, double &term,
+                                             int &valid) {
     constexpr double epsilon = 1.0e-10;
     ux = uy = uz = 0.0;
     if (!(finite_f(fixed_val) && finite_f(moving_val))) {
@@ -136,11 +290,11 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
         valid = 0;
         return;
     }
-    const double diff = static_cast<double>(fixed_val) - static_cast<double>(moving_val);
+    const double diff = diff_exact(fixed_val, moving_val);  // == (double)fixed - (double)moving
     term = diff * diff;
     valid = 1;
     const double gmag_sq = gx * gx + gy * gy + gz * gz;
-    const double denom = gmag_sq + (STRICT ? (diff * diff) / norm_eps : (diff * diff) * inv_norm_eps);
+    const double denom = gmag_sq + (STRICT ? (diff * diff) / k.norm_eps : (diff * diff) * k.inv_norm_eps);
     if (denom > epsilon) {
         if (STRICT) {
             ux = diff * gx / denom;
@@ -152,9 +306,41 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
             uy = s * gy;
             uz = s * gz;
         }
-        const double mag = sqrt(ux * ux + uy * uy + uz * uz);
-        if (mag > max_update) {
-            const double scale = max_update / mag;
+        const double m2 = ux * ux + uy * uy + uz * uz;
+        if (m2 > k.mu2_lo) {  // only then can sqrt(m2) exceed max_update (cc:320-326)
+            const double mag = sqrt(m2);
+            if (mag > k.max_update) {
+                const double scale = k.max_update / mag;
+                ux *= scale;
+                uy *= scale;
+                uz *= scale;
+            }
+        }
+    }
+}
+template <bool STRICT>
+__device__ __forceinline__ void demons_force(float fixed_val, float moving_val, float gx, float gy, float gz,
+                                             const ForceK &k, float &ux, float &uy, float &uz, float &term,
+                                             int &valid) {
+    ux = uy = uz = 0.0f;
+    if (!(finite_f(fixed_val) && finite_f(moving_val))) {
+        term = 0.0f;
+        valid = 0;
+        return;
+    }
+    const float diff = fixed_val - moving_val;
+    term = diff * diff;
+    valid = 1;
+    const float denom = fmaf(gx, gx, fmaf(gy, gy, gz * gz)) + term * static_cast<float>(k.inv_norm_eps);
+    if (denom > 1.0e-10f) {
+        const float s = diff / denom;
+        ux = s * gx;
+        uy = s * gy;
+        uz = s * gz;
+        const float m2 = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
+        const float mu = static_cast<float>(k.max_update);
+        if (m2 > mu * mu) {
+            const float scale = mu * rsqrtf(m2);
             ux *= scale;
             uy *= scale;
             uz *= scale;
@@ -167,77 +353,88 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
 //   w_src = 0: W := M (first iteration: the engine copies M into warped, cc:183 -- NOT a zero-field warp)
 //   w_src = 1: W := warp(M, D) computed in registers, never written to HBM
 //   w_src = 2: W read from `Wbuf` (stage API: the unfused compute_update_and_mse)
-// Tile = 32 x 8 voxels of one slice per 256-thread block, 3-D grid striding over slices; the fixed-image gradient is
-// recomputed from F (7-point stencil served by L1/L2) instead of being read back as 3 field components.
-// MSE terms are reduced warp-shuffle -> block -> one (sum, count) partial per block (deterministic for a fixed grid).
+// 3-D grid striding over slices (no div/mod); 32-bit element offsets (IX = int) whenever N*channels < 2^31; the fixed
+// gradient is recomputed from F (7-point stencil served by L1/L2) instead of being read back as 3 field components.
+// MSE terms: per-thread sum -> warp shuffle -> block -> one (sum, count) partial per block (deterministic).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kTileX = 32, kTileY = 8;
-
-template <typename T, bool STRICT>
+template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
-                 const T *__restrict__ D, T *__restrict__ U, const Geo g, const int w_src, const double norm_eps,
-                 const double inv_norm_eps, const double max_update, double *__restrict__ part_sum, long long *__restrict__ part_cnt,
-                 const Ctrl *__restrict__ ctrl, const long long it) {
+                 const T *__restrict__ D, T *__restrict__ U, const Geo g, const int w_src, const ForceK fk,
+                 double *__restrict__ part_sum, long long *__restrict__ part_cnt, const Ctrl *__restrict__ ctrl,
+                 const long long it) {
+    using CT = T;  // compute type of coordinates / interpolation / force == field storage type
     if (it > ctrl->converged_at) return;
-    double acc = 0.0;
-    long long cnt = 0;
-    const long long N = g.N;
+    CT acc = 0;
+    int cnt = 0;
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
-    const bool in_tile = (x < g.C) && (y < g.R);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
-        if (!in_tile) break;
-        const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
-        const float fixed_val = __ldg(F + v * g.CH);
-        float moving_val;
-        if (w_src == 0) {
-            moving_val = __ldg(M + v * g.CH);
-        } else if (w_src == 2) {
-            moving_val = __ldg(Wbuf + v * g.CH);
-        } else {
-            const double dx = static_cast<double>(D[v]), dy = static_cast<double>(D[v + N]),
-                         dz = static_cast<double>(D[v + 2 * N]);
-            if (!(isfinite(dx) && isfinite(dy) && isfinite(dz))) {  // cc:494-500
-                moving_val = CUDART_NAN_F;
+    if (x < g.C && y < g.R) {
+        const IX ch = CH1 ? IX(1) : static_cast<IX>(g.CH);
+        const IX plane = static_cast<IX>(g.R) * g.C;
+        const IX vxy = static_cast<IX>(y) * g.C + x;
+        const T *D1 = D + g.N, *D2 = D + 2 * g.N;
+        T *U1 = U + g.N, *U2 = U + 2 * g.N;
+        const AxisK<CT> ak(g);
+        const GradK<IX> gk(g, x, y, ch);
+        const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
+        CT zd = static_cast<CT>(static_cast<int>(blockIdx.z));
+        const CT zstep = static_cast<CT>(static_cast<int>(gridDim.z));
+        for (int z = blockIdx.z; z < g.S; z += gridDim.z, zd += zstep) {
+            const IX v = static_cast<IX>(z) * plane + vxy;
+            const float *Fv = F + v * ch;
+            const float fixed_val = __ldg(Fv);
+            float moving_val;
+            if (w_src == 1) {
+                const CT dx = D[v], dy = D1[v], dz = D2[v];
+                bool ok;
+                if (sizeof(CT) == 8)
+                    ok = finite_d(dx) && finite_d(dy) && finite_d(dz);  // cc:494-500
+                else
+                    ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
+                if (ok) {
+                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, dx, dy, dz);
+                    moving_val = warp_one<CT, IX, CH1>(M, g, t, 0);  // only channel 0 drives the force (cc:294-295)
+                } else {
+                    moving_val = CUDART_NAN_F;
+                }
             } else {
-                const Tri t = tri_coords<STRICT>(g, x, y, z, dx, dy, dz);
-                moving_val = warp_one(M, g, t, 0);  // only channel 0 drives the force (cc:294-295)
+                moving_val = __ldg((w_src == 0 ? M : Wbuf) + v * ch);
             }
+            CT gx, gy, gz;
+            grad_fixed<IX>(Fv, g, gk, z, plane * ch, gx, gy, gz);
+            CT ux, uy, uz, term;
+            int valid;
+            demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
+            U[v] = ux;
+            U1[v] = uy;
+            U2[v] = uz;
+            acc += term;
+            cnt += valid;
         }
-        double gx, gy, gz;
-        grad_fixed(F, g, x, y, z, gx, gy, gz);
-        double ux, uy, uz, term;
-        int valid;
-        demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, norm_eps, inv_norm_eps, max_update, ux, uy, uz, term,
-                             valid);
-        U[v] = static_cast<T>(ux);
-        U[v + N] = static_cast<T>(uy);
-        U[v + 2 * N] = static_cast<T>(uz);
-        acc += term;
-        cnt += valid;
     }
     // warp-shuffle + block reduction of (sum of squared differences, valid count): cc:334-339 done on the device
+    double a = static_cast<double>(acc);
     for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_down_sync(0xffffffffu, acc, o);
+        a += __shfl_down_sync(0xffffffffu, a, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     }
     __shared__ double s_acc[kTileY];
-    __shared__ long long s_cnt[kTileY];
+    __shared__ int s_cnt[kTileY];
     if (threadIdx.x == 0) {
-        s_acc[threadIdx.y] = acc;
+        s_acc[threadIdx.y] = a;
         s_cnt[threadIdx.y] = cnt;
     }
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        double a = 0.0;
+        double aa = 0.0;
         long long c = 0;
         for (int i = 0; i < kTileY; ++i) {
-            a += s_acc[i];
+            aa += s_acc[i];
             c += s_cnt[i];
         }
         const int b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        part_sum[b] = a;
+        part_sum[b] = aa;
         part_cnt[b] = c;
     }
 }
@@ -288,28 +485,36 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_warp: warp_moving as its own kernel (stage API, KeepDeformedImages, dcma_b200_warp_image): all channels.
-// D may be SoA T (engine) -- AoS double input goes through k_import_aos first.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T, bool STRICT>
+template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp(const float *__restrict__ M, const T *__restrict__ D, float *__restrict__ W, const Geo g, const int use_oob,
            const float oob_value) {
-    const long long N = g.N;
+    using CT = T;
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
-    const bool in_tile = (x < g.C) && (y < g.R);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
-        if (!in_tile) break;
-        const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
-        const double dx = static_cast<double>(D[v]), dy = static_cast<double>(D[v + N]),
-                     dz = static_cast<double>(D[v + 2 * N]);
-        const bool ok = isfinite(dx) && isfinite(dy) && isfinite(dz);
-        Tri t;
-        if (ok) t = tri_coords<STRICT>(g, x, y, z, dx, dy, dz);
-        for (int c = 0; c < g.CH; ++c) {
-            float w = ok ? warp_one(M, g, t, c) : CUDART_NAN_F;
+    if (x >= g.C || y >= g.R) return;
+    const IX ch = CH1 ? IX(1) : static_cast<IX>(g.CH);
+    const IX plane = static_cast<IX>(g.R) * g.C;
+    const IX vxy = static_cast<IX>(y) * g.C + x;
+    const T *D1 = D + g.N, *D2 = D + 2 * g.N;
+    const AxisK<CT> ak(g);
+    const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {
+        const IX v = static_cast<IX>(z) * plane + vxy;
+        const CT dx = D[v], dy = D1[v], dz = D2[v];
+        bool ok;
+        if (sizeof(CT) == 8)
+            ok = finite_d(dx) && finite_d(dy) && finite_d(dz);
+        else
+            ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
+        Tri<CT> t;
+        if (ok) t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, static_cast<CT>(z), dx, dy, dz);
+        const int nch = CH1 ? 1 : g.CH;
+        for (int c = 0; c < nch; ++c) {
+            float w = ok ? warp_one<CT, IX, CH1>(M, g, t, c) : CUDART_NAN_F;
             if (use_oob && !finite_f(w)) w = oob_value;
-            W[v * g.CH + c] = w;
+            W[v * ch + c] = w;
         }
     }
 }
@@ -319,12 +524,14 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     k_gradient(const float *__restrict__ F, double *__restrict__ G_aos, const Geo g) {
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
-    const bool in_tile = (x < g.C) && (y < g.R);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
-        if (!in_tile) break;
-        const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
+    if (x >= g.C || y >= g.R) return;
+    const long long ch = g.CH;
+    const long long plane = static_cast<long long>(g.R) * g.C;
+    const GradK<long long> gk(g, x, y, ch);
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {
+        const long long v = static_cast<long long>(z) * plane + static_cast<long long>(y) * g.C + x;
         double gx, gy, gz;
-        grad_fixed(F, g, x, y, z, gx, gy, gz);
+        grad_fixed<long long>(F + v * ch, g, gk, z, plane * ch, gx, gy, gz);
         G_aos[v * 3 + 0] = gx;
         G_aos[v * 3 + 1] = gy;
         G_aos[v * 3 + 2] = gz;
@@ -348,60 +555,70 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_compose: add_update_diffeomorphic (cc:371-465):  D(p) += U(p + D(p)/pxl) * pxl, trilinear, ZERO outside the grid,
-// no NaN checks; the four upper-z corners are narrowed to float exactly as the reference does (cc:439-442).
-// Reads D only at self (in place is race-free), gathers U at 8 corners x 3 components.
+// no NaN checks; the four upper-z corners are narrowed to float as the reference does (cc:439-442).
+// Reads D only at self (in place is race-free), gathers U at 8 corners x 3 components; the corner offsets and the
+// in-grid predicates are computed once and shared by the three components.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ double fetch_u(const T *__restrict__ Uc, const Geo &g, int zz, int yy, int xx) {
-    if (xx < 0 || xx >= g.C || yy < 0 || yy >= g.R || zz < 0 || zz >= g.S) return 0.0;
-    return static_cast<double>(Uc[(static_cast<long long>(zz) * g.R + yy) * g.C + xx]);
-}
-
-template <typename T, bool STRICT>
+template <typename T, bool STRICT, typename IX>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const Ctrl *__restrict__ ctrl, const long long it) {
+    using CT = T;
     if (it > ctrl->converged_at) return;
-    const long long N = g.N;
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
-    const bool in_tile = (x < g.C) && (y < g.R);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {  // no div/mod: 3-D grid, stride over slices
-        if (!in_tile) break;
-        const long long v = (static_cast<long long>(z) * g.R + y) * g.C + x;
-        const double dx = static_cast<double>(D[v]), dy = static_cast<double>(D[v + N]),
-                     dz = static_cast<double>(D[v + 2 * N]);
-        const Tri t = tri_coords<STRICT>(g, x, y, z, dx, dy, dz);
+    if (x >= g.C || y >= g.R) return;
+    const IX plane = static_cast<IX>(g.R) * g.C;
+    const IX vxy = static_cast<IX>(y) * g.C + x;
+    const AxisK<CT> ak(g);
+    const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
+    CT zd = static_cast<CT>(static_cast<int>(blockIdx.z));
+    const CT zstep = static_cast<CT>(static_cast<int>(gridDim.z));
+    for (int z = blockIdx.z; z < g.S; z += gridDim.z, zd += zstep) {
+        const IX v = static_cast<IX>(z) * plane + vxy;
+        CT d[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = D[v + c * g.N];
+        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
         const int x1 = t.x0 + 1, y1 = t.y0 + 1, z1 = g.is2d ? t.z0 : (t.z0 + 1);
-        const double tx = t.tx, ty = t.ty, tz = t.tz;
-        double u[3];
+        const bool vx0 = static_cast<unsigned>(t.x0) < static_cast<unsigned>(g.C);
+        const bool vx1 = static_cast<unsigned>(x1) < static_cast<unsigned>(g.C);
+        const bool vy0 = static_cast<unsigned>(t.y0) < static_cast<unsigned>(g.R);
+        const bool vy1 = static_cast<unsigned>(y1) < static_cast<unsigned>(g.R);
+        const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.S);
+        const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.S);
+        const IX o00 = (static_cast<IX>(t.z0) * g.R + t.y0) * g.C + t.x0;  // only dereferenced where in-grid
+        const IX oy = g.C, oz = g.is2d ? IX(0) : plane;
+        const CT tx = t.tx, ty = t.ty, tz = t.tz;
+        const CT pxl[3] = {ak.px, ak.py, ak.pz};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const T *Uc = U + c * N;
-            const double c000 = fetch_u(Uc, g, t.z0, t.y0, t.x0), c100 = fetch_u(Uc, g, t.z0, t.y0, x1);
-            const double c010 = fetch_u(Uc, g, t.z0, y1, t.x0), c110 = fetch_u(Uc, g, t.z0, y1, x1);
-            float c001, c101, c011, c111;
-            if (g.is2d) {
-                c001 = static_cast<float>(c000);
-                c101 = static_cast<float>(c100);
-                c011 = static_cast<float>(c010);
-                c111 = static_cast<float>(c110);
+            const T *Uc = U + c * g.N + o00;
+            // zero outside the grid (cc:424-427)
+            const CT c000 = (vz0 && vy0 && vx0) ? Uc[0] : CT(0);
+            const CT c100 = (vz0 && vy0 && vx1) ? Uc[1] : CT(0);
+            const CT c010 = (vz0 && vy1 && vx0) ? Uc[oy] : CT(0);
+            const CT c110 = (vz0 && vy1 && vx1) ? Uc[oy + 1] : CT(0);
+            CT c001, c101, c011, c111;
+            if (g.is2d) {  // cc:436-442: the z0 plane is reused (and still narrowed)
+                c001 = narrow_to_float<STRICT>(c000);
+                c101 = narrow_to_float<STRICT>(c100);
+                c011 = narrow_to_float<STRICT>(c010);
+                c111 = narrow_to_float<STRICT>(c110);
             } else {
-                c001 = static_cast<float>(fetch_u(Uc, g, z1, t.y0, t.x0));
-                c101 = static_cast<float>(fetch_u(Uc, g, z1, t.y0, x1));
-                c011 = static_cast<float>(fetch_u(Uc, g, z1, y1, t.x0));
-                c111 = static_cast<float>(fetch_u(Uc, g, z1, y1, x1));
+                c001 = narrow_to_float<STRICT>((vz1 && vy0 && vx0) ? Uc[oz] : CT(0));
+                c101 = narrow_to_float<STRICT>((vz1 && vy0 && vx1) ? Uc[oz + 1] : CT(0));
+                c011 = narrow_to_float<STRICT>((vz1 && vy1 && vx0) ? Uc[oz + oy] : CT(0));
+                c111 = narrow_to_float<STRICT>((vz1 && vy1 && vx1) ? Uc[oz + oy + 1] : CT(0));
             }
-            const double c00 = c000 * (1.0 - tx) + c100 * tx;
-            const double c10 = c010 * (1.0 - tx) + c110 * tx;
-            const double c01 = static_cast<double>(c001) * (1.0 - tx) + static_cast<double>(c101) * tx;
-            const double c11 = static_cast<double>(c011) * (1.0 - tx) + static_cast<double>(c111) * tx;
-            const double c0 = c00 * (1.0 - ty) + c10 * ty;
-            const double c1 = c01 * (1.0 - ty) + c11 * ty;
-            u[c] = c0 * (1.0 - tz) + c1 * tz;
+            const CT c00 = c000 * (CT(1) - tx) + c100 * tx;  // cc:445-451
+            const CT c10 = c010 * (CT(1) - tx) + c110 * tx;
+            const CT c01 = c001 * (CT(1) - tx) + c101 * tx;
+            const CT c11 = c011 * (CT(1) - tx) + c111 * tx;
+            const CT c0 = c00 * (CT(1) - ty) + c10 * ty;
+            const CT c1 = c01 * (CT(1) - ty) + c11 * ty;
+            const CT u = c0 * (CT(1) - tz) + c1 * tz;
+            D[v + c * g.N] = d[c] + u * pxl[c];  // cc:460-462
         }
-        D[v] = static_cast<T>(dx + u[0] * g.px);
-        D[v + N] = static_cast<T>(dy + u[1] * g.py);
-        D[v + 2 * N] = static_cast<T>(dz + u[2] * g.pz);
     }
 }
 

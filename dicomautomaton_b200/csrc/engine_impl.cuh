@@ -42,7 +42,7 @@ class Engine final : public EngineBase {
             throw std::invalid_argument("volume extents and channel count must be >= 1");
         if (!(geom.pxl_dx > 0.0) || !(geom.pxl_dy > 0.0) || !(geom.pxl_dz > 0.0))
             throw std::invalid_argument("voxel spacing must be > 0");
-        if (geom.slices > 32767 * 64LL || geom.rows > (1 << 22) || geom.cols > (1 << 22))
+        if (geom.slices > (1 << 21) || geom.rows > (1 << 21) || geom.cols > (1 << 21))
             throw std::invalid_argument("volume extent too large");
         const long long N = geom.slices * geom.rows * geom.cols;
         if (N * 3 >= (1LL << 40)) throw std::invalid_argument("volume too large");
@@ -58,6 +58,7 @@ class Engine final : public EngineBase {
         g_.ipy = 1.0 / geom.pxl_dy;
         g_.ipz = 1.0 / geom.pxl_dz;
         g_.is2d = (geom.slices == 1) ? 1 : 0;
+        small_index_ = (N * geom.channels < 2000000000LL);  // 32-bit element offsets inside the per-voxel kernels
 
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -382,7 +383,8 @@ class Engine final : public EngineBase {
             for (int a = 0; a < 3; ++a) {
                 const int rad = pl.r[a];
                 for (int k = 0; k < 2 * rad + 1; ++k) pl.W.w[a][k] = static_cast<T>(pl.w[a][k]);
-                std::vector<T> tab(extent[a]);
+                const int padded = ((extent[a] + 127) / 128) * 128 + 128;  // whole tiles: the kernel never tests bounds
+                std::vector<T> tab(padded, T(1));
                 for (int pos = 0; pos < extent[a]; ++pos) {
                     // in-order accumulation over the in-grid taps, in the kernel's own type (cc:620-631)
                     T wsum = 0;
@@ -392,7 +394,7 @@ class Engine final : public EngineBase {
                     }
                     tab[pos] = STRICT ? wsum : static_cast<T>(1.0 / static_cast<double>(wsum));
                 }
-                pl.tab[a] = alloc<T>(extent[a]);
+                pl.tab[a] = alloc<T>(padded);
                 DCMA_CUDA(cudaMemcpy(pl.tab[a], tab.data(), sizeof(T) * tab.size(), cudaMemcpyHostToDevice));
             }
         }
@@ -471,10 +473,21 @@ class Engine final : public EngineBase {
 
     void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true) {
         if (w_src == 2) ensure_warped_buffer();
-        const double norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
-        k_warp_force<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(
-            dF_, dM_, dW_, dD_, dU_, g_, w_src, norm_eps, 1.0 / norm_eps, p_.max_update_magnitude, d_part_sum_,
-            d_part_cnt_, d_ctrl_, it);
+        ForceK fk;
+        fk.norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
+        fk.inv_norm_eps = 1.0 / fk.norm_eps;
+        fk.max_update = p_.max_update_magnitude;
+        fk.mu2_lo = (fk.max_update >= 0.0) ? fk.max_update * fk.max_update * (1.0 - 8.881784197001252e-16) : -1.0;
+        const dim3 blk(kTileX, kTileY);
+#define DCMA_LAUNCH_FORCE(IX, CH1)                                                                                   \
+    k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, w_src, fk, d_part_sum_, \
+                                                                  d_part_cnt_, d_ctrl_, it)
+        if (small_index_) {
+            if (g_.CH == 1) DCMA_LAUNCH_FORCE(int, true); else DCMA_LAUNCH_FORCE(int, false);
+        } else {
+            if (g_.CH == 1) DCMA_LAUNCH_FORCE(long long, true); else DCMA_LAUNCH_FORCE(long long, false);
+        }
+#undef DCMA_LAUNCH_FORCE
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
         if (reduce) launch_reduce(it, d_hist, hist_idx, count_iter && d_hist != nullptr ? 1 : 0);
@@ -491,7 +504,10 @@ class Engine final : public EngineBase {
         ++launches_;
     }
     void launch_compose(long long it) {
-        k_compose<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
+        if (small_index_)
+            k_compose<T, STRICT, int><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
+        else
+            k_compose<T, STRICT, long long><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -504,7 +520,18 @@ class Engine final : public EngineBase {
     void launch_warp_to_buffer(long long it = 0) {
         (void)it;
         ensure_warped_buffer();
-        k_warp<T, STRICT><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+        const dim3 blk(kTileX, kTileY);
+        if (small_index_) {
+            if (g_.CH == 1)
+                k_warp<T, STRICT, int, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+            else
+                k_warp<T, STRICT, int, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+        } else {
+            if (g_.CH == 1)
+                k_warp<T, STRICT, long long, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+            else
+                k_warp<T, STRICT, long long, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+        }
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -549,17 +576,30 @@ class Engine final : public EngineBase {
             attr_set[dev_ & 63] = true;
         }
         const int gx = (g_.C + TX - 1) / TX, gy = (g_.R + TY - 1) / TY;
-        // z chunks: enough CTAs for ~4 waves at 2 CTAs/SM, but chunks no shorter than 4 halos (<= 50% re-staging)
+        // z chunks: score = (fraction of slice steps that produce output) x (wave efficiency); every chunk re-stages
+        // 2R slices of warm-up, and a partially filled last wave idles SMs.
+        int blocks_per_sm = 1;
+        DCMA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NT, Cfg::smem_bytes));
+        const double slots = static_cast<double>(std::max(1, blocks_per_sm)) * sms_;
         const long long nxy = static_cast<long long>(gx) * gy * 3;
-        const long long target = static_cast<long long>(sms_) * 8;
-        int nz = static_cast<int>(std::max<long long>(1, (target + nxy - 1) / nxy));
-        const int min_chunk = std::max(8 * R, 16);
-        nz = std::min(nz, std::max(1, g_.S / min_chunk));
-        int zchunk = (g_.S + nz - 1) / nz;
-        nz = (g_.S + zchunk - 1) / zchunk;
+        int best_nz = 1;
+        double best_score = -1.0;
+        const int nz_max = std::max(1, std::min(g_.S / std::max(2 * R, 1), static_cast<int>(65535 / 3)));
+        for (int nzc = 1; nzc <= nz_max; ++nzc) {
+            const int zc = (g_.S + nzc - 1) / nzc;
+            const int nz_eff = (g_.S + zc - 1) / zc;
+            const double waves = static_cast<double>(nxy) * nz_eff / slots;
+            const double score = (static_cast<double>(zc) / (zc + 2 * R)) * (waves / std::ceil(waves));
+            if (score > best_score + 1e-9) {
+                best_score = score;
+                best_nz = nz_eff;
+            }
+        }
+        const int zchunk = (g_.S + best_nz - 1) / best_nz;
+        const int nz = (g_.S + zchunk - 1) / zchunk;
         if (3LL * nz > 65535 || gy > 65535) throw std::invalid_argument("volume exceeds the smoothing kernel's grid limits");
         kern<<<dim3(gx, gy, 3 * nz), NT, Cfg::smem_bytes, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2],
-                                                                     zchunk, nz, d_ctrl_, it);
+                                                                     pl.dw[0], pl.dw[1], pl.dw[2], zchunk, nz, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -568,7 +608,7 @@ class Engine final : public EngineBase {
     void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
         constexpr int TX = 64, NT = 256;
         constexpr int TY = (sizeof(T) == 4) ? 32 : 16;
-        const bool vec = (g_.C % 4 == 0);
+        const bool vec = (g_.C % static_cast<int>(16 / sizeof(T)) == 0);
         if (vec)
             launch_smooth3d_cfg<R, TX, TY, NT, true>(in, out, pl, it);
         else
@@ -594,6 +634,7 @@ class Engine final : public EngineBase {
     bool own_stream_ = false;
     bool loaded_ = false;
     dim3 grid3_;
+    bool small_index_ = true;
     int grid_vox_ = 1, grid_lin_ = 1;
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
     T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;

@@ -79,67 +79,105 @@ __global__ void __launch_bounds__(256)
 // fused three-pass kernel
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
-struct alignas(4 * sizeof(T)) Vec4 {
-    T v[4];
+struct alignas(16) VecT {  // one 16-byte shared/global access: 4 floats or 2 doubles
+    static constexpr int W = 16 / sizeof(T);
+    T v[W];
 };
 
-__device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gmem_src, int bytes, int src_bytes) {
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, int src_bytes) {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    if (bytes == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
-    else if (bytes == 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_src, int src_bytes) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(s), "l"(gmem_src), "n"(BYTES), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
 template <typename T, int R, int TX, int TY, int NT>
 struct Smooth3dCfg {
-    static constexpr int HX = ((R + 3) / 4) * 4;       // x halo rounded up so rows stay 16-byte aligned
-    static constexpr int PW = TX + 2 * HX;             // staged row width
-    static constexpr int PH = TY + 2 * R;              // staged rows
-    static constexpr int QX = TX / 4;                  // quads (4 consecutive x) per tile row
-    static constexpr int RG = NT / QX;                 // row groups
-    static constexpr int OY = TY / RG;                 // rows owned per thread
+    static constexpr int VW = 16 / sizeof(T);             // elements per 16-byte vector
+    static constexpr int HX = ((R + VW - 1) / VW) * VW;   // x halo rounded up so staged rows stay 16-byte aligned
+    static constexpr int PW = TX + 2 * HX;                // staged row width
+    static constexpr int PH = TY + 2 * R;                 // staged rows
+    static constexpr int QX = TX / VW;                    // vectors per tile row (thread column index = tid % QX)
+    static constexpr int RG = NT / QX;                    // thread rows
+    static constexpr int OY = TY / RG;                    // ADJACENT output rows owned by a thread
     static constexpr int TAPS = 2 * R + 1;
+    static constexpr int XT = PH * QX;                    // x-pass tasks (one vector of outputs each)
+    static constexpr int XN = (XT + NT - 1) / NT;
+    static constexpr int NV = (VW + 2 * HX) / VW;         // vectors read per x-pass task
+    static constexpr int CPR = PW / VW;                   // 16-byte copies per staged row
+    static constexpr int NCP = (PH * CPR + NT - 1) / NT;  // 16-byte copies per thread per slice
     static constexpr size_t smem_bytes = (size_t(2) * PH * PW + size_t(PH) * TX) * sizeof(T);
-    static_assert(TX % 4 == 0 && NT % QX == 0 && TY % RG == 0, "tile/thread shape");
+    static_assert(TX % VW == 0 && NT % QX == 0 && TY % RG == 0 && (QX & (QX - 1)) == 0, "tile/thread shape");
 };
 
-// One output through the literal per-tap path (non-finite data only).  `tap(k)` returns the k-th tap value,
-// `inb(k)` whether it lies inside the grid, `centre` the input value kept when no tap qualifies.
-// Force-inlined and fully unrolled so the tap arrays stay in registers (a real call would force them to local memory).
-template <typename T, int R, typename TapF, typename InbF>
-__device__ __forceinline__ T smooth_slow(const T *w, TapF tap, InbF inb, T centre) {
-    T sum = 0, wsum = 0;
-#pragma unroll
-    for (int k = 0; k < 2 * R + 1; ++k) {
-        if (inb(k)) {
-            const T val = tap(k);
-            if (isfinite(val)) {
-                sum += w[k] * val;
-                wsum += w[k];
+// The literal definition for ONE output voxel, straight from global memory (cc:609-693): used only when the fast path
+// produced a non-finite value, i.e. when some tap in the (2r+1)^3 support is non-finite.  Deliberately not inlined.
+template <typename T, int R>
+__device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g, const double *__restrict__ dwx,
+                                         const double *__restrict__ dwy, const double *__restrict__ dwz, int x, int y,
+                                         int z) {
+    const long long plane = static_cast<long long>(g.R) * g.C;
+    T zs = 0, zw = 0, z_centre = 0;
+    for (int kz = -R; kz <= R; ++kz) {
+        const int zz = z + kz;
+        if (zz < 0 || zz >= g.S) continue;
+        T ys = 0, yw = 0, y_centre = 0;
+        for (int ky = -R; ky <= R; ++ky) {
+            const int yy = y + ky;
+            if (yy < 0 || yy >= g.R) continue;
+            const T *row = src + zz * plane + static_cast<long long>(yy) * g.C;
+            T xs = 0, xw = 0;
+            for (int kx = -R; kx <= R; ++kx) {
+                const int xx = x + kx;
+                if (xx < 0 || xx >= g.C) continue;
+                const T val = row[xx];
+                if (isfinite(val)) {
+                    const T wk = static_cast<T>(dwx[kx + R]);
+                    xs += wk * val;
+                    xw += wk;
+                }
+            }
+            const T xv = (xw > T(0)) ? (xs / xw) : row[x];
+            if (ky == 0) y_centre = xv;
+            if (isfinite(xv)) {
+                const T wk = static_cast<T>(dwy[ky + R]);
+                ys += wk * xv;
+                yw += wk;
             }
         }
+        const T yv = (yw > T(0)) ? (ys / yw) : y_centre;
+        if (kz == 0) z_centre = yv;
+        if (isfinite(yv)) {
+            const T wk = static_cast<T>(dwz[kz + R]);
+            zs += wk * yv;
+            zw += wk;
+        }
     }
-    return (wsum > T(0)) ? (sum / wsum) : centre;
+    return (zw > T(0)) ? (zs / zw) : z_centre;
 }
 
-// grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks
+// grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks.
+// tab_x / tab_y / tab_z are padded by the host to whole tiles (no bounds tests here).
 template <typename T, bool STRICT, int R, int TX, int TY, int NT, bool VEC>
 __global__ void __launch_bounds__(NT)
     k_smooth3d(const T *__restrict__ in, T *__restrict__ out, const Geo g, const SmoothWeights<T> W,
-               const T *__restrict__ tab_x, const T *__restrict__ tab_y, const T *__restrict__ tab_z, const int zchunk,
-               const int nzchunks, const Ctrl *__restrict__ ctrl, const long long it) {
+               const T *__restrict__ tab_x, const T *__restrict__ tab_y, const T *__restrict__ tab_z,
+               const double *__restrict__ dwx, const double *__restrict__ dwy, const double *__restrict__ dwz,
+               const int zchunk, const int nzchunks, const Ctrl *__restrict__ ctrl, const long long it) {
     using Cfg = Smooth3dCfg<T, R, TX, TY, NT>;
-    constexpr int HX = Cfg::HX, PW = Cfg::PW, PH = Cfg::PH, QX = Cfg::QX, RG = Cfg::RG, OY = Cfg::OY, TAPS = Cfg::TAPS;
+    constexpr int VW = Cfg::VW, HX = Cfg::HX, PW = Cfg::PW, PH = Cfg::PH, QX = Cfg::QX, OY = Cfg::OY, TAPS = Cfg::TAPS;
+    constexpr int XT = Cfg::XT, XN = Cfg::XN, NV = Cfg::NV, CPR = Cfg::CPR, NCP = Cfg::NCP;
+    using Vec = VecT<T>;
     if (it > ctrl->converged_at) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *s_in = reinterpret_cast<T *>(smem_raw);   // [2][PH][PW]
-    T *s_x = s_in + 2 * PH * PW;                 // [PH][TX]
+    T *s_in = reinterpret_cast<T *>(smem_raw);  // [2][PH][PW]
+    T *s_x = s_in + 2 * PH * PW;                // [PH][TX]
 
     const int tid = threadIdx.x;
     const int comp = blockIdx.z / nzchunks;
@@ -151,43 +189,69 @@ __global__ void __launch_bounds__(NT)
     const T *src = in + comp * g.N;
     T *dst = out + comp * g.N;
 
-    // stage one input slice tile (+halo) with cp.async; out-of-grid elements are zero-filled (src-size 0)
+    // weights in registers; the host builds them symmetric bit for bit (w[k] == w[2R-k]), so R+1 per axis suffice
+    T wxh[R + 1], wyh[R + 1], wzh[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; ++k) {
+        wxh[k] = W.w[0][k];
+        wyh[k] = W.w[1][k];
+        wzh[k] = W.w[2][k];
+    }
+#define DCMA_WX(k) wxh[((k) <= R) ? (k) : (2 * R - (k))]
+#define DCMA_WY(k) wyh[((k) <= R) ? (k) : (2 * R - (k))]
+#define DCMA_WZ(k) wzh[((k) <= R) ? (k) : (2 * R - (k))]
+
+    // ---- per-thread staging plan, fixed across slices: source offset inside a slice (-1: outside the grid -> zeros)
+    int cp_src[NCP], cp_dst[NCP];
+    if (VEC) {
+#pragma unroll
+        for (int n = 0; n < NCP; ++n) {
+            const int e = tid + n * NT;
+            const int row = e / CPR, cc = e - row * CPR;
+            const int gy = y0 - R + row, gx = x0 - HX + cc * VW;
+            const bool ok = (gy >= 0) && (gy < g.R) && (gx >= 0) && (gx + VW <= g.C);
+            cp_dst[n] = (e < PH * CPR) ? (row * PW + cc * VW) : -1;
+            cp_src[n] = ok ? (gy * g.C + gx) : -1;
+        }
+    }
     auto stage = [&](int zp, int buf) {
+        if (zp < 0 || zp >= g.S) return;  // slice outside the grid: contributes zeros, nothing to load
         T *sb = s_in + buf * PH * PW;
-        if (zp < 0 || zp >= g.S) return;  // nothing to load: the whole slice is outside (handled by the caller)
         const T *sp = src + zp * plane;
         if (VEC) {
-            constexpr int E = 16 / sizeof(T);  // elements per 16-byte copy
-            constexpr int CPR = PW / E;        // copies per staged row
-            for (int e = tid; e < PH * CPR; e += NT) {
-                const int row = e / CPR, cc = e - row * CPR;
-                const int gy = y0 - R + row, gx = x0 - HX + cc * E;
-                const bool ok = (gy >= 0) && (gy < g.R) && (gx >= 0) && (gx + E <= g.C);
-                const T *p = ok ? (sp + static_cast<long long>(gy) * g.C + gx) : src;
-                cp_async_zfill(sb + row * PW + cc * E, p, 16, ok ? 16 : 0);
+#pragma unroll
+            for (int n = 0; n < NCP; ++n) {
+                if (cp_dst[n] >= 0) cp_async_16(sb + cp_dst[n], (cp_src[n] >= 0) ? (sp + cp_src[n]) : src, (cp_src[n] >= 0) ? 16 : 0);
             }
         } else {
             for (int e = tid; e < PH * PW; e += NT) {
                 const int row = e / PW, col = e - row * PW;
                 const int gy = y0 - R + row, gx = x0 - HX + col;
                 const bool ok = (gy >= 0) && (gy < g.R) && (gx >= 0) && (gx < g.C);
-                const T *p = ok ? (sp + static_cast<long long>(gy) * g.C + gx) : src;
-                cp_async_zfill(sb + row * PW + col, p, static_cast<int>(sizeof(T)), ok ? static_cast<int>(sizeof(T)) : 0);
+                cp_async_small<sizeof(T)>(sb + row * PW + col, ok ? (sp + static_cast<long long>(gy) * g.C + gx) : src,
+                                          ok ? static_cast<int>(sizeof(T)) : 0);
             }
         }
     };
 
+    // ---- thread geometry: column vector qx (x-pass, y-pass and outputs all use the same one), thread row ry
+    const int qx = tid & (QX - 1), ry = tid / QX;
+    const int gx_out = x0 + qx * VW;
+    const int yl0 = ry * OY;  // first owned (local) output row; owned rows are adjacent
+    T nx[VW], ny[OY];          // per-position normalisers (wsum or 1/wsum), fixed across slices
+#pragma unroll
+    for (int i = 0; i < VW; ++i) nx[i] = tab_x[gx_out + i];
+#pragma unroll
+    for (int j = 0; j < OY; ++j) ny[j] = tab_y[y0 + yl0 + j];
+
     // z window: the last TAPS xy-smoothed values of each owned output, in registers
-    T win[OY][4][TAPS];
+    T win[OY][VW][TAPS];
 #pragma unroll
     for (int j = 0; j < OY; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < VW; ++i)
 #pragma unroll
             for (int k = 0; k < TAPS; ++k) win[j][i][k] = T(0);
-
-    const int qx = tid % QX, ry = tid / QX;
-    const int gx_out = x0 + 4 * qx;
 
     const int zp_first = z_begin - R, zp_last = z_end - 1 + R;
     stage(zp_first, 0);
@@ -201,107 +265,105 @@ __global__ void __launch_bounds__(NT)
         cp_async_commit();
 
         const bool slice_in = (zp >= 0 && zp < g.S);
-        T vxy[OY][4];
+        T vxy[OY][VW];
         if (slice_in) {
             const T *sb = s_in + buf * PH * PW;
-            // ---- x pass: s_in -> s_x, 4 consecutive outputs per task from HX/2+1 aligned 4-vectors
-            for (int task = tid; task < PH * QX; task += NT) {
-                const int row = task / QX, q = task - row * QX;
-                constexpr int NV = (4 + 2 * HX) / 4;
-                T a[4 * NV];
+            // ---- x pass: s_in -> s_x.  Task = one vector of VW outputs; q == qx for every task of this thread.
 #pragma unroll
-                for (int n = 0; n < NV; ++n) {
-                    const Vec4<T> t4 = *reinterpret_cast<const Vec4<T> *>(sb + row * PW + 4 * q + 4 * n);
+            for (int n = 0; n < XN; ++n) {
+                const int row = ry + n * (NT / QX);
+                if ((XT % NT != 0) && row >= PH) break;
+                T a[VW * NV];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) a[4 * n + i] = t4.v[i];
+                for (int m = 0; m < NV; ++m) {
+                    const Vec t = *reinterpret_cast<const Vec *>(sb + row * PW + (qx + m) * VW);
+#pragma unroll
+                    for (int i = 0; i < VW; ++i) a[m * VW + i] = t.v[i];
                 }
-                Vec4<T> o;
+                Vec o;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    T sum = 0;
+                for (int i = 0; i < VW; ++i) {
+                    T sum = DCMA_WX(0) * a[HX - R + i];
 #pragma unroll
-                    for (int k = 0; k < TAPS; ++k) sum += W.w[0][k] * a[HX - R + i + k];
-                    const int gx = x0 + 4 * q + i;
-                    T res = normalise<T, STRICT>(sum, tab_x[min(gx, g.C - 1)]);
-                    if (!isfinite(res)) {
-                        res = smooth_slow<T, R>(
-                            W.w[0], [&](int k) { return a[HX - R + i + k]; },
-                            [&](int k) { const int q2 = gx + k - R; return q2 >= 0 && q2 < g.C; }, a[HX + i]);
-                    }
-                    o.v[i] = res;
+                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WX(k) * a[HX - R + i + k];
+                    o.v[i] = normalise<T, STRICT>(sum, nx[i]);
                 }
-                *reinterpret_cast<Vec4<T> *>(s_x + row * TX + 4 * q) = o;
+                *reinterpret_cast<Vec *>(s_x + row * TX + qx * VW) = o;
             }
             __syncthreads();
-            // ---- y pass: s_x -> registers
+            // ---- y pass: s_x -> registers, OY adjacent rows share their taps
+            // rows are streamed once; output j takes row m as its tap k = m - j (ascending k: the reference's order)
+            T acc[OY][VW];
 #pragma unroll
-            for (int j = 0; j < OY; ++j) {
-                const int yl = ry + j * RG;  // local output row
-                const int gy = y0 + yl;
-                T col[TAPS][4];
+            for (int m = 0; m < OY + 2 * R; ++m) {
+                const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
 #pragma unroll
-                for (int k = 0; k < TAPS; ++k) {
-                    const Vec4<T> t4 = *reinterpret_cast<const Vec4<T> *>(s_x + (yl + k) * TX + 4 * qx);
+                for (int j = 0; j < OY; ++j) {
+                    const int k = m - j;
+                    if (k < 0 || k >= TAPS) continue;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) col[k][i] = t4.v[i];
-                }
-                const T ty = tab_y[min(gy, g.R - 1)];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    T sum = 0;
-#pragma unroll
-                    for (int k = 0; k < TAPS; ++k) sum += W.w[1][k] * col[k][i];
-                    T res = normalise<T, STRICT>(sum, ty);
-                    if (!isfinite(res)) {
-                        res = smooth_slow<T, R>(
-                            W.w[1], [&](int k) { return col[k][i]; },
-                            [&](int k) { const int q2 = gy + k - R; return q2 >= 0 && q2 < g.R; }, col[R][i]);
+                    for (int i = 0; i < VW; ++i) {
+                        if (k == 0)
+                            acc[j][i] = DCMA_WY(0) * t.v[i];
+                        else
+                            acc[j][i] += DCMA_WY(k) * t.v[i];
                     }
-                    vxy[j][i] = res;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < OY; ++j)
+#pragma unroll
+                for (int i = 0; i < VW; ++i) vxy[j][i] = normalise<T, STRICT>(acc[j][i], ny[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < OY; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) vxy[j][i] = T(0);
+                for (int i = 0; i < VW; ++i) vxy[j][i] = T(0);
         }
         // ---- z pass from the register window
         const int zo = zp - R;  // output slice completed by this step
-        const bool emit = (zo >= z_begin) && (zo < z_end);
-        const T tz = tab_z[min(max(zo, 0), g.S - 1)];
 #pragma unroll
-        for (int j = 0; j < OY; ++j) {
-            const int gy = y0 + ry + j * RG;
-            Vec4<T> o;
+        for (int j = 0; j < OY; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < VW; ++i) {
 #pragma unroll
                 for (int k = 0; k < TAPS - 1; ++k) win[j][i][k] = win[j][i][k + 1];
                 win[j][i][TAPS - 1] = vxy[j][i];
-                T sum = 0;
-#pragma unroll
-                for (int k = 0; k < TAPS; ++k) sum += W.w[2][k] * win[j][i][k];
-                T res = normalise<T, STRICT>(sum, tz);
-                if (!isfinite(res)) {
-                    res = smooth_slow<T, R>(
-                        W.w[2], [&](int k) { return win[j][i][k]; },
-                        [&](int k) { const int q2 = zo + k - R; return q2 >= 0 && q2 < g.S; }, win[j][i][R]);
-                }
-                o.v[i] = res;
             }
-            if (emit && gy < g.R) {
-                T *p = dst + zo * plane + static_cast<long long>(gy) * g.C + gx_out;
-                if (VEC) {
-                    if (gx_out < g.C) *reinterpret_cast<Vec4<T> *>(p) = o;  // C % 4 == 0 in the VEC variant
-                } else {
+        if (zo >= z_begin) {  // zo < z_end holds by construction of zp_last
+            const T nz = tab_z[zo];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (gx_out + i < g.C) p[i] = o.v[i];
+            for (int j = 0; j < OY; ++j) {
+                const int gy = y0 + yl0 + j;
+                Vec o;
+#pragma unroll
+                for (int i = 0; i < VW; ++i) {
+                    T sum = DCMA_WZ(0) * win[j][i][0];
+#pragma unroll
+                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WZ(k) * win[j][i][k];
+                    T res = normalise<T, STRICT>(sum, nz);
+                    // a non-finite result <=> a non-finite tap somewhere in the (2r+1)^3 support: redo it literally
+                    if (!isfinite(res) && gy < g.R && gx_out + i < g.C)
+                        res = smooth_literal<T, R>(src, g, dwx, dwy, dwz, gx_out + i, gy, zo);
+                    o.v[i] = res;
+                }
+                if (gy < g.R) {
+                    T *p = dst + zo * plane + static_cast<long long>(gy) * g.C + gx_out;
+                    if (VEC) {
+                        if (gx_out < g.C) *reinterpret_cast<Vec *>(p) = o;  // C % VW == 0 in the VEC variant
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VW; ++i)
+                            if (gx_out + i < g.C) p[i] = o.v[i];
+                    }
                 }
             }
         }
     }
 }
+
+#undef DCMA_WX
+#undef DCMA_WY
+#undef DCMA_WZ
 
 }  // namespace DCMA_NS
