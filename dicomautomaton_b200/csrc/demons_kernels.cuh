@@ -157,36 +157,39 @@ __device__ __forceinline__ Tri<CT> tri_coords(const Geo &g, const AxisK<CT> &k, 
 //   float  path: fp32 on differences to the first corner (error ~1e-6 HU instead of ~1e-4 HU for plain fp32).
 // Returns diff = fixed - warped through `diff` when WANT_DIFF, and the warped value itself.
 // ------------------------------------------------------------------------------------------------------------------
+// Loads are issued UNCONDITIONALLY from coordinates clamped into the grid (so the 8 gathers of a voxel, and those of
+// the other voxels of the warp, are all in flight together); the return value says whether every corner was inside.
 template <typename IX, bool CH1>
 __device__ __forceinline__ bool load_corners(const float *__restrict__ M, const Geo &g, int x0, int y0, int z0, int c,
                                              float (&v)[8]) {
     const int x1 = x0 + 1, y1 = y0 + 1, z1 = g.is2d ? z0 : (z0 + 1);
-    if (x0 < 0 || x1 >= g.C || y0 < 0 || y1 >= g.R || z0 < 0 || z1 >= g.S) return false;  // cc:516-519
-    const IX row = (static_cast<IX>(z0) * g.R + y0) * g.C + x0;
-    const IX dy = g.C, dz = g.is2d ? IX(0) : static_cast<IX>(g.R) * g.C;
+    const bool inside = !(x0 < 0 || x1 >= g.C || y0 < 0 || y1 >= g.R || z0 < 0 || z1 >= g.S);  // cc:516-519
+    const int cx0 = min(max(x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
+    const int cy0 = min(max(y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
+    const int cz0 = min(max(z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
+    const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
+    const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
     if (CH1) {
-        const float *p = M + row;
-        v[0] = __ldg(p);
-        v[1] = __ldg(p + 1);
-        v[2] = __ldg(p + dy);
-        v[3] = __ldg(p + dy + 1);
-        v[4] = __ldg(p + dz);
-        v[5] = __ldg(p + dz + 1);
-        v[6] = __ldg(p + dz + dy);
-        v[7] = __ldg(p + dz + dy + 1);
+        v[0] = __ldg(M + (r00 + cx0));
+        v[1] = __ldg(M + (r00 + cx1));
+        v[2] = __ldg(M + (r10 + cx0));
+        v[3] = __ldg(M + (r10 + cx1));
+        v[4] = __ldg(M + (r01 + cx0));
+        v[5] = __ldg(M + (r01 + cx1));
+        v[6] = __ldg(M + (r11 + cx0));
+        v[7] = __ldg(M + (r11 + cx1));
     } else {
         const IX ch = g.CH;
-        const float *p = M + row * ch + c;
-        v[0] = __ldg(p);
-        v[1] = __ldg(p + ch);
-        v[2] = __ldg(p + dy * ch);
-        v[3] = __ldg(p + (dy + 1) * ch);
-        v[4] = __ldg(p + dz * ch);
-        v[5] = __ldg(p + (dz + 1) * ch);
-        v[6] = __ldg(p + (dz + dy) * ch);
-        v[7] = __ldg(p + (dz + dy + 1) * ch);
+        v[0] = __ldg(M + (r00 + cx0) * ch + c);
+        v[1] = __ldg(M + (r00 + cx1) * ch + c);
+        v[2] = __ldg(M + (r10 + cx0) * ch + c);
+        v[3] = __ldg(M + (r10 + cx1) * ch + c);
+        v[4] = __ldg(M + (r01 + cx0) * ch + c);
+        v[5] = __ldg(M + (r01 + cx1) * ch + c);
+        v[6] = __ldg(M + (r11 + cx0) * ch + c);
+        v[7] = __ldg(M + (r11 + cx1) * ch + c);
     }
-    return true;
+    return inside;
 }
 
 // v = {c000, c100, c010, c110, c001, c101, c011, c111}
@@ -217,8 +220,9 @@ __device__ __forceinline__ float warp_interp(const float (&v)[8], const Tri<floa
 template <typename CT, typename IX, bool CH1>
 __device__ __forceinline__ float warp_one(const float *__restrict__ M, const Geo &g, const Tri<CT> &t, int c) {
     float v[8];
-    if (!load_corners<IX, CH1>(M, g, t.x0, t.y0, t.z0, c, v)) return CUDART_NAN_F;
-    return warp_interp(v, t);
+    const bool inside = load_corners<IX, CH1>(M, g, t.x0, t.y0, t.z0, c, v);
+    const float w = warp_interp(v, t);
+    return inside ? w : CUDART_NAN_F;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -242,31 +246,35 @@ struct GradK {
     }
 };
 
+struct Stencil {  // the six neighbours of the fixed image, channel 0
+    float xl, xr, yu, yd, zp, zn;
+    float sz;  // 1/(index distance) along z: 0.5, 1 or 0
+};
+// in-plane neighbours (L1/L2 hits); the z neighbours are supplied by the caller, which marches along z and keeps the
+// previous / next slice values of its voxel column in registers
 template <typename IX>
-__device__ __forceinline__ void grad_fixed(const float *__restrict__ Fv, const Geo &g, const GradK<IX> &k, int z,
-                                           IX plane_ch, double &gx, double &gy, double &gz) {
-    // (vr - vl) / (xr - xl) with xr - xl in {1, 2}: multiplying by 1 or 0.5 is the same operation bit for bit
-    gx = (k.sx != 0.0f) ? diff_exact(__ldg(Fv + k.xr), __ldg(Fv + k.xl)) * static_cast<double>(k.sx) : 0.0;
-    gy = (k.sy != 0.0f) ? diff_exact(__ldg(Fv + k.yd), __ldg(Fv + k.yu)) * static_cast<double>(k.sy) : 0.0;
-    gz = 0.0;
-    if (g.S > 1) {
-        const int zp = (z > 0) ? -1 : 0, zn = (z + 1 < g.S) ? 1 : 0;
-        gz = diff_exact(__ldg(Fv + zn * plane_ch), __ldg(Fv + zp * plane_ch)) * ((zn - zp == 2) ? 0.5 : 1.0);
-    }
+__device__ __forceinline__ void load_stencil_xy(Stencil &s, const float *__restrict__ Fv, const GradK<IX> &k) {
+    s.xl = __ldg(Fv + k.xl);
+    s.xr = __ldg(Fv + k.xr);
+    s.yu = __ldg(Fv + k.yu);
+    s.yd = __ldg(Fv + k.yd);
 }
-template <typename IX>
-__device__ __forceinline__ void grad_fixed(const float *__restrict__ Fv, const Geo &g, const GradK<IX> &k, int z,
-                                           IX plane_ch, float &gx, float &gy, float &gz) {
-    const float dx = __ldg(Fv + k.xr) - __ldg(Fv + k.xl);
-    const float dy = __ldg(Fv + k.yd) - __ldg(Fv + k.yu);
-    gx = finite_f(dx) ? dx * k.sx : 0.0f;
-    gy = finite_f(dy) ? dy * k.sy : 0.0f;
-    gz = 0.0f;
-    if (g.S > 1) {
-        const int zp = (z > 0) ? -1 : 0, zn = (z + 1 < g.S) ? 1 : 0;
-        const float dz = __ldg(Fv + zn * plane_ch) - __ldg(Fv + zp * plane_ch);
-        gz = finite_f(dz) ? dz * ((zn - zp == 2) ? 0.5f : 1.0f) : 0.0f;
-    }
+__device__ __forceinline__ float z_scale(const Geo &g, int z) {
+    if (g.S <= 1) return 0.0f;
+    return (z > 0 && z + 1 < g.S) ? 0.5f : 1.0f;  // S > 1: at a border the one-sided difference has distance 1
+}
+__device__ __forceinline__ void grad_fixed(const Stencil &s, float sx, float sy, double &gx, double &gy, double &gz) {
+    // (vr - vl) / (xr - xl) with xr - xl in {1, 2}: multiplying by 1 or 0.5 is the same operation bit for bit;
+    // scale 0 encodes "extent 1" (cc:233, 244, 255)
+    gx = (sx != 0.0f) ? diff_exact(s.xr, s.xl) * static_cast<double>(sx) : 0.0;
+    gy = (sy != 0.0f) ? diff_exact(s.yd, s.yu) * static_cast<double>(sy) : 0.0;
+    gz = (s.sz != 0.0f) ? diff_exact(s.zn, s.zp) * static_cast<double>(s.sz) : 0.0;
+}
+__device__ __forceinline__ void grad_fixed(const Stencil &s, float sx, float sy, float &gx, float &gy, float &gz) {
+    const float dx = s.xr - s.xl, dy = s.yd - s.yu, dz = s.zn - s.zp;
+    gx = finite_f(dx) ? dx * sx : 0.0f;
+    gy = finite_f(dy) ? dy * sy : 0.0f;
+    gz = finite_f(dz) ? dz * s.sz : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -360,8 +368,8 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
 template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
-                 const T *__restrict__ D, T *__restrict__ U, const Geo g, const int w_src, const ForceK fk,
-                 double *__restrict__ part_sum, long long *__restrict__ part_cnt, const Ctrl *__restrict__ ctrl,
+                 const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
+                 const ForceK fk, double *__restrict__ part_sum, long long *__restrict__ part_cnt, const Ctrl *__restrict__ ctrl,
                  const long long it) {
     using CT = T;  // compute type of coordinates / interpolation / force == field storage type
     if (it > ctrl->converged_at) return;
@@ -378,39 +386,63 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         const AxisK<CT> ak(g);
         const GradK<IX> gk(g, x, y, ch);
         const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
-        CT zd = static_cast<CT>(static_cast<int>(blockIdx.z));
-        const CT zstep = static_cast<CT>(static_cast<int>(gridDim.z));
-        for (int z = blockIdx.z; z < g.S; z += gridDim.z, zd += zstep) {
-            const IX v = static_cast<IX>(z) * plane + vxy;
-            const float *Fv = F + v * ch;
-            const float fixed_val = __ldg(Fv);
-            float moving_val;
+        // Each block marches through a run of CONSECUTIVE slices [z_begin, z_end): the z neighbours of the gradient
+        // stencil roll through registers (one new F load per voxel instead of three), the moving-image gathers of
+        // consecutive slices overlap in L1/L2, and the displacement of the next slice is requested one step ahead.
+        const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+        if (z_begin < z_end) {
+            IX v = static_cast<IX>(z_begin) * plane + vxy;
+            const IX pch = plane * ch;
+            CT zd = static_cast<CT>(z_begin);
+            CT dx = 0, dy = 0, dz = 0;
             if (w_src == 1) {
-                const CT dx = D[v], dy = D1[v], dz = D2[v];
-                bool ok;
-                if (sizeof(CT) == 8)
-                    ok = finite_d(dx) && finite_d(dy) && finite_d(dz);  // cc:494-500
-                else
-                    ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
-                if (ok) {
-                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, dx, dy, dz);
-                    moving_val = warp_one<CT, IX, CH1>(M, g, t, 0);  // only channel 0 drives the force (cc:294-295)
-                } else {
-                    moving_val = CUDART_NAN_F;
-                }
-            } else {
-                moving_val = __ldg((w_src == 0 ? M : Wbuf) + v * ch);
+                dx = D[v];
+                dy = D1[v];
+                dz = D2[v];
             }
-            CT gx, gy, gz;
-            grad_fixed<IX>(Fv, g, gk, z, plane * ch, gx, gy, gz);
-            CT ux, uy, uz, term;
-            int valid;
-            demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
-            U[v] = ux;
-            U1[v] = uy;
-            U2[v] = uz;
-            acc += term;
-            cnt += valid;
+            float f_prev = __ldg(F + (z_begin > 0 ? v - plane : v) * ch);
+            float f_cur = __ldg(F + v * ch);
+            for (int z = z_begin; z < z_end; ++z, v += plane, zd += CT(1)) {
+                const float *Fv = F + v * ch;
+                Stencil st;
+                load_stencil_xy<IX>(st, Fv, gk);
+                const float f_next = (z + 1 < g.S) ? __ldg(Fv + pch) : f_cur;
+                st.zp = f_prev;
+                st.zn = f_next;
+                st.sz = z_scale(g, z);
+                const float fixed_val = f_cur;
+                float moving_val;
+                if (w_src == 1) {
+                    bool ok;
+                    if (sizeof(CT) == 8)
+                        ok = finite_d(dx) && finite_d(dy) && finite_d(dz);  // cc:494-500
+                    else
+                        ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
+                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, ok ? dx : CT(0),
+                                                             ok ? dy : CT(0), ok ? dz : CT(0));
+                    const float w = warp_one<CT, IX, CH1>(M, g, t, 0);  // only channel 0 drives the force (cc:294-295)
+                    moving_val = ok ? w : CUDART_NAN_F;
+                    if (z + 1 < z_end) {
+                        dx = D[v + plane];
+                        dy = D1[v + plane];
+                        dz = D2[v + plane];
+                    }
+                } else {
+                    moving_val = __ldg((w_src == 0 ? M : Wbuf) + v * ch);
+                }
+                CT gx, gy, gz;
+                grad_fixed(st, gk.sx, gk.sy, gx, gy, gz);
+                CT ux, uy, uz, term;
+                int valid;
+                demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
+                U[v] = ux;
+                U1[v] = uy;
+                U2[v] = uz;
+                acc += term;
+                cnt += valid;
+                f_prev = f_cur;
+                f_cur = f_next;
+            }
         }
     }
     // warp-shuffle + block reduction of (sum of squared differences, valid count): cc:334-339 done on the device
@@ -488,8 +520,8 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_warp(const float *__restrict__ M, const T *__restrict__ D, float *__restrict__ W, const Geo g, const int use_oob,
-           const float oob_value) {
+    k_warp(const float *__restrict__ M, const T *__restrict__ D, float *__restrict__ W, const Geo g, const int zlen,
+           const int use_oob, const float oob_value) {
     using CT = T;
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
@@ -500,7 +532,8 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const T *D1 = D + g.N, *D2 = D + 2 * g.N;
     const AxisK<CT> ak(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {
+    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+    for (int z = z_begin; z < z_end; ++z) {
         const IX v = static_cast<IX>(z) * plane + vxy;
         const CT dx = D[v], dy = D1[v], dz = D2[v];
         bool ok;
@@ -521,17 +554,24 @@ __global__ void __launch_bounds__(kTileX *kTileY)
 
 // k_gradient: compute_gradient as its own kernel, AoS double output (stage API / inspection only).
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_gradient(const float *__restrict__ F, double *__restrict__ G_aos, const Geo g) {
+    k_gradient(const float *__restrict__ F, double *__restrict__ G_aos, const Geo g, const int zlen) {
     const int x = blockIdx.x * kTileX + threadIdx.x;
     const int y = blockIdx.y * kTileY + threadIdx.y;
     if (x >= g.C || y >= g.R) return;
     const long long ch = g.CH;
     const long long plane = static_cast<long long>(g.R) * g.C;
     const GradK<long long> gk(g, x, y, ch);
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z) {
+    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+    for (int z = z_begin; z < z_end; ++z) {
         const long long v = static_cast<long long>(z) * plane + static_cast<long long>(y) * g.C + x;
+        const float *Fv = F + v * ch;
+        Stencil st;
+        load_stencil_xy<long long>(st, Fv, gk);
+        st.zp = __ldg(Fv - ((z > 0) ? plane * ch : 0));
+        st.zn = __ldg(Fv + ((z + 1 < g.S) ? plane * ch : 0));
+        st.sz = z_scale(g, z);
         double gx, gy, gz;
-        grad_fixed<long long>(F + v * ch, g, gk, z, plane * ch, gx, gy, gz);
+        grad_fixed(st, gk.sx, gk.sy, gx, gy, gz);
         G_aos[v * 3 + 0] = gx;
         G_aos[v * 3 + 1] = gy;
         G_aos[v * 3 + 2] = gz;
@@ -561,7 +601,8 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, bool STRICT, typename IX>
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const Ctrl *__restrict__ ctrl, const long long it) {
+    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int zlen, const Ctrl *__restrict__ ctrl,
+              const long long it) {
     using CT = T;
     if (it > ctrl->converged_at) return;
     const int x = blockIdx.x * kTileX + threadIdx.x;
@@ -571,13 +612,19 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const IX vxy = static_cast<IX>(y) * g.C + x;
     const AxisK<CT> ak(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
-    CT zd = static_cast<CT>(static_cast<int>(blockIdx.z));
-    const CT zstep = static_cast<CT>(static_cast<int>(gridDim.z));
-    for (int z = blockIdx.z; z < g.S; z += gridDim.z, zd += zstep) {
-        const IX v = static_cast<IX>(z) * plane + vxy;
-        CT d[3];
+    const long long N = g.N;
+    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);  // consecutive slices: gathers overlap
+    if (z_begin >= z_end) return;
+    CT zd = static_cast<CT>(z_begin);
+    CT d[3];
+    {
+        const IX v0 = static_cast<IX>(z_begin) * plane + vxy;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) d[c] = D[v + c * g.N];
+        for (int c = 0; c < 3; ++c) d[c] = D[v0 + c * N];
+    }
+    const CT pxl[3] = {ak.px, ak.py, ak.pz};
+    for (int z = z_begin; z < z_end; ++z, zd += CT(1)) {
+        const IX v = static_cast<IX>(z) * plane + vxy;
         const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
         const int x1 = t.x0 + 1, y1 = t.y0 + 1, z1 = g.is2d ? t.z0 : (t.z0 + 1);
         const bool vx0 = static_cast<unsigned>(t.x0) < static_cast<unsigned>(g.C);
@@ -586,18 +633,40 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         const bool vy1 = static_cast<unsigned>(y1) < static_cast<unsigned>(g.R);
         const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.S);
         const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.S);
-        const IX o00 = (static_cast<IX>(t.z0) * g.R + t.y0) * g.C + t.x0;  // only dereferenced where in-grid
-        const IX oy = g.C, oz = g.is2d ? IX(0) : plane;
-        const CT tx = t.tx, ty = t.ty, tz = t.tz;
-        const CT pxl[3] = {ak.px, ak.py, ak.pz};
+        // gathers are issued unconditionally from clamped coordinates (all 24 in flight together); corners outside
+        // the grid are then replaced by zero (cc:424-427)
+        const int cx0 = min(max(t.x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
+        const int cy0 = min(max(t.y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
+        const int cz0 = min(max(t.z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
+        const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
+        const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
+        CT q[3][8];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const T *Uc = U + c * g.N + o00;
-            // zero outside the grid (cc:424-427)
-            const CT c000 = (vz0 && vy0 && vx0) ? Uc[0] : CT(0);
-            const CT c100 = (vz0 && vy0 && vx1) ? Uc[1] : CT(0);
-            const CT c010 = (vz0 && vy1 && vx0) ? Uc[oy] : CT(0);
-            const CT c110 = (vz0 && vy1 && vx1) ? Uc[oy + 1] : CT(0);
+            const T *Uc = U + c * N;
+            q[c][0] = Uc[r00 + cx0];
+            q[c][1] = Uc[r00 + cx1];
+            q[c][2] = Uc[r10 + cx0];
+            q[c][3] = Uc[r10 + cx1];
+            q[c][4] = Uc[r01 + cx0];
+            q[c][5] = Uc[r01 + cx1];
+            q[c][6] = Uc[r11 + cx0];
+            q[c][7] = Uc[r11 + cx1];
+        }
+        // prefetch the next slice's displacement before consuming the gathers
+        CT dn[3] = {CT(0), CT(0), CT(0)};
+        if (z + 1 < z_end) {
+            const IX vn = v + plane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dn[c] = D[vn + c * N];
+        }
+        const CT tx = t.tx, ty = t.ty, tz = t.tz;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const CT c000 = (vz0 && vy0 && vx0) ? q[c][0] : CT(0);
+            const CT c100 = (vz0 && vy0 && vx1) ? q[c][1] : CT(0);
+            const CT c010 = (vz0 && vy1 && vx0) ? q[c][2] : CT(0);
+            const CT c110 = (vz0 && vy1 && vx1) ? q[c][3] : CT(0);
             CT c001, c101, c011, c111;
             if (g.is2d) {  // cc:436-442: the z0 plane is reused (and still narrowed)
                 c001 = narrow_to_float<STRICT>(c000);
@@ -605,10 +674,10 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                 c011 = narrow_to_float<STRICT>(c010);
                 c111 = narrow_to_float<STRICT>(c110);
             } else {
-                c001 = narrow_to_float<STRICT>((vz1 && vy0 && vx0) ? Uc[oz] : CT(0));
-                c101 = narrow_to_float<STRICT>((vz1 && vy0 && vx1) ? Uc[oz + 1] : CT(0));
-                c011 = narrow_to_float<STRICT>((vz1 && vy1 && vx0) ? Uc[oz + oy] : CT(0));
-                c111 = narrow_to_float<STRICT>((vz1 && vy1 && vx1) ? Uc[oz + oy + 1] : CT(0));
+                c001 = narrow_to_float<STRICT>((vz1 && vy0 && vx0) ? q[c][4] : CT(0));
+                c101 = narrow_to_float<STRICT>((vz1 && vy0 && vx1) ? q[c][5] : CT(0));
+                c011 = narrow_to_float<STRICT>((vz1 && vy1 && vx0) ? q[c][6] : CT(0));
+                c111 = narrow_to_float<STRICT>((vz1 && vy1 && vx1) ? q[c][7] : CT(0));
             }
             const CT c00 = c000 * (CT(1) - tx) + c100 * tx;  // cc:445-451
             const CT c10 = c010 * (CT(1) - tx) + c110 * tx;
@@ -617,8 +686,10 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             const CT c0 = c00 * (CT(1) - ty) + c10 * ty;
             const CT c1 = c01 * (CT(1) - ty) + c11 * ty;
             const CT u = c0 * (CT(1) - tz) + c1 * tz;
-            D[v + c * g.N] = d[c] + u * pxl[c];  // cc:460-462
+            D[v + c * N] = d[c] + u * pxl[c];  // cc:460-462
         }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = dn[c];
     }
 }
 

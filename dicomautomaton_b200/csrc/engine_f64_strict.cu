@@ -49,13 +49,14 @@ void warp_image_host(const dcma_b200_geom &geom, const float *image, const doubl
         DCMA_CUDA(cudaMemcpy(dA, deformation_aos, sizeof(double) * 3 * N, cudaMemcpyHostToDevice));
         const int ntx = (g.C + kTileX - 1) / kTileX, nty = (g.R + kTileY - 1) / kTileY;
         if (nty > 65535) throw std::invalid_argument("too many rows");
-        const dim3 grid(ntx, nty, std::min(g.S, 64));
+        const int zlen = 16;
+        const dim3 grid(ntx, nty, (g.S + zlen - 1) / zlen);
         const int grid_lin = static_cast<int>(std::min<long long>((3 * N + 255) / 256, 148LL * 16));
         k_import_aos<double><<<grid_lin, 256>>>(dA, dS, N);
         if (g.CH == 1)
-            k_warp<double, true, long long, true><<<grid, dim3(kTileX, kTileY)>>>(dM, dS, dW, g, use_oob ? 1 : 0, oob_value);
+            k_warp<double, true, long long, true><<<grid, dim3(kTileX, kTileY)>>>(dM, dS, dW, g, zlen, use_oob ? 1 : 0, oob_value);
         else
-            k_warp<double, true, long long, false><<<grid, dim3(kTileX, kTileY)>>>(dM, dS, dW, g, use_oob ? 1 : 0, oob_value);
+            k_warp<double, true, long long, false><<<grid, dim3(kTileX, kTileY)>>>(dM, dS, dW, g, zlen, use_oob ? 1 : 0, oob_value);
         DCMA_CUDA(cudaGetLastError());
         DCMA_CUDA(cudaMemcpy(out, dW, sizeof(float) * N * g.CH, cudaMemcpyDeviceToHost));
     } catch (...) {

@@ -87,9 +87,13 @@ class Engine final : public EngineBase {
         const int ntx = (g_.C + kTileX - 1) / kTileX, nty = (g_.R + kTileY - 1) / kTileY;
         if (nty > 65535) throw std::invalid_argument("too many rows");
         const long long per_plane = static_cast<long long>(ntx) * nty;
-        const long long want = static_cast<long long>(sms_) * 8 * 16;
-        const int gz = static_cast<int>(std::max<long long>(1, std::min<long long>(g_.S, (want + per_plane - 1) / per_plane)));
-        grid3_ = dim3(ntx, nty, std::min(gz, 65535));
+        // runs of ~16 consecutive slices per block (rolling z stencil, gather reuse), at least ~8 waves of blocks
+        const long long want = static_cast<long long>(sms_) * 8 * 8;
+        int gz = static_cast<int>(std::max<long long>((g_.S + 15) / 16, std::min<long long>(g_.S, (want + per_plane - 1) / per_plane)));
+        gz = std::max(1, std::min(gz, std::min(g_.S, 65535)));
+        zlen_ = (g_.S + gz - 1) / gz;
+        gz = (g_.S + zlen_ - 1) / zlen_;
+        grid3_ = dim3(ntx, nty, gz);
         grid_vox_ = static_cast<int>(per_plane * grid3_.z);  // number of MSE partials
         grid_lin_ = static_cast<int>(std::min<long long>((3 * N + 255) / 256, static_cast<long long>(sms_) * 16));
 
@@ -260,7 +264,7 @@ class Engine final : public EngineBase {
             case DCMA_B200_BUF_GRADIENT: {
                 double *tmp = nullptr;
                 DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
-                k_gradient<<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dF_, tmp, g_);
+                k_gradient<<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dF_, tmp, g_, zlen_);
                 DCMA_CUDA(cudaGetLastError());
                 DCMA_CUDA(cudaMemcpyAsync(host, tmp, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream_));
                 DCMA_CUDA(cudaStreamSynchronize(stream_));
@@ -480,7 +484,7 @@ class Engine final : public EngineBase {
         fk.mu2_lo = (fk.max_update >= 0.0) ? fk.max_update * fk.max_update * (1.0 - 8.881784197001252e-16) : -1.0;
         const dim3 blk(kTileX, kTileY);
 #define DCMA_LAUNCH_FORCE(IX, CH1)                                                                                   \
-    k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, w_src, fk, d_part_sum_, \
+    k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
                                                                   d_part_cnt_, d_ctrl_, it)
         if (small_index_) {
             if (g_.CH == 1) DCMA_LAUNCH_FORCE(int, true); else DCMA_LAUNCH_FORCE(int, false);
@@ -505,9 +509,9 @@ class Engine final : public EngineBase {
     }
     void launch_compose(long long it) {
         if (small_index_)
-            k_compose<T, STRICT, int><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
+            k_compose<T, STRICT, int><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, zlen_, d_ctrl_, it);
         else
-            k_compose<T, STRICT, long long><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, d_ctrl_, it);
+            k_compose<T, STRICT, long long><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, zlen_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -523,14 +527,14 @@ class Engine final : public EngineBase {
         const dim3 blk(kTileX, kTileY);
         if (small_index_) {
             if (g_.CH == 1)
-                k_warp<T, STRICT, int, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+                k_warp<T, STRICT, int, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
             else
-                k_warp<T, STRICT, int, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+                k_warp<T, STRICT, int, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
         } else {
             if (g_.CH == 1)
-                k_warp<T, STRICT, long long, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+                k_warp<T, STRICT, long long, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
             else
-                k_warp<T, STRICT, long long, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, 0, 0.f);
+                k_warp<T, STRICT, long long, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
         }
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
@@ -565,14 +569,17 @@ class Engine final : public EngineBase {
         }
     }
 
-    template <int R, int TX, int TY, int NT, bool VEC>
+    template <int R, int TX, int TY, int NT, int MINB, bool VEC>
     void launch_smooth3d_cfg(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
         using Cfg = Smooth3dCfg<T, R, TX, TY, NT>;
-        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, VEC>;
+        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, MINB, VEC>;
         static thread_local bool attr_set[64] = {false};
         if (!attr_set[dev_ & 63]) {
             DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(Cfg::smem_bytes)));
+            // without this the driver picks the smallest L1/shared split that fits ONE block (ncu: 1 block/SM)
+            DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
             attr_set[dev_ & 63] = true;
         }
         const int gx = (g_.C + TX - 1) / TX, gy = (g_.R + TY - 1) / TY;
@@ -606,13 +613,17 @@ class Engine final : public EngineBase {
 
     template <int R>
     void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
-        constexpr int TX = 64, NT = 256;
-        constexpr int TY = (sizeof(T) == 4) ? 32 : 16;
+        // 128-thread CTAs, 2 adjacent output rows x one 16-byte vector per thread; the register z window (72 regs)
+        // puts the kernel at ~165 registers, so 3 CTAs/SM.  float: 64x16 tile; double: 32x16 tile.
+        constexpr int TX = (sizeof(T) == 4) ? 64 : 32;
+        constexpr int TY = 16;
+        constexpr int NT = 128;
+        constexpr int MINB = 3;
         const bool vec = (g_.C % static_cast<int>(16 / sizeof(T)) == 0);
         if (vec)
-            launch_smooth3d_cfg<R, TX, TY, NT, true>(in, out, pl, it);
+            launch_smooth3d_cfg<R, TX, TY, NT, MINB, true>(in, out, pl, it);
         else
-            launch_smooth3d_cfg<R, TX, TY, NT, false>(in, out, pl, it);
+            launch_smooth3d_cfg<R, TX, TY, NT, MINB, false>(in, out, pl, it);
     }
 
     void launch_smooth3d(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
@@ -635,6 +646,7 @@ class Engine final : public EngineBase {
     bool loaded_ = false;
     dim3 grid3_;
     bool small_index_ = true;
+    int zlen_ = 1;
     int grid_vox_ = 1, grid_lin_ = 1;
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
     T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;

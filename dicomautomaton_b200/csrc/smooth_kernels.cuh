@@ -163,8 +163,8 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
 
 // grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks.
 // tab_x / tab_y / tab_z are padded by the host to whole tiles (no bounds tests here).
-template <typename T, bool STRICT, int R, int TX, int TY, int NT, bool VEC>
-__global__ void __launch_bounds__(NT)
+template <typename T, bool STRICT, int R, int TX, int TY, int NT, int MINB, bool VEC>
+__global__ void __launch_bounds__(NT, MINB)
     k_smooth3d(const T *__restrict__ in, T *__restrict__ out, const Geo g, const SmoothWeights<T> W,
                const T *__restrict__ tab_x, const T *__restrict__ tab_y, const T *__restrict__ tab_z,
                const double *__restrict__ dwx, const double *__restrict__ dwy, const double *__restrict__ dwz,
