@@ -77,17 +77,10 @@ __device__ __forceinline__ float narrow_to_float(float x) {
     return x;
 }
 
-// (double)a - (double)b with one conversion instead of two whenever the fp32 subtraction is exact (TwoSum error == 0);
-// 0 if either value is non-finite (cc:238, 249, 260).  Exact in every case.
+// (double)a - (double)b, or 0 if either value is non-finite (cc:238, 249, 260).
 __device__ __forceinline__ double diff_exact(float a, float b) {
-    const float s = __fsub_rn(a, b);
-    if (finite_f(s)) {
-        const float bb = __fsub_rn(s, a);
-        const float e = __fadd_rn(__fsub_rn(a, __fsub_rn(s, bb)), __fsub_rn(-b, bb));
-        if (e == 0.0f) return static_cast<double>(s);
-    }
-    if (finite_f(a) && finite_f(b)) return static_cast<double>(a) - static_cast<double>(b);
-    return 0.0;
+    const double d = static_cast<double>(a) - static_cast<double>(b);
+    return (finite_f(a) && finite_f(b)) ? d : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

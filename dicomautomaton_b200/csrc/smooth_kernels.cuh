@@ -17,6 +17,8 @@
 //    accumulation, so for finite fields the arithmetic (order included) equals the reference's; a non-finite result
 //    re-runs that output through the literal per-tap path, which makes the two implementations agree on any input.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 #ifndef DCMA_NS
@@ -161,6 +163,17 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
     return (zw > T(0)) ? (zs / zw) : z_centre;
 }
 
+// calls f(integral_constant<P>, zb + P) for P = 0..N-1 while zb + P <= last (compile-time ring phases)
+template <int N, int P, typename F>
+__device__ __forceinline__ void unroll_phases(F &f, const int zb, const int last) {
+    if constexpr (P < N) {
+        if (zb + P <= last) {
+            f(std::integral_constant<int, P>{}, zb + P);
+            unroll_phases<N, P + 1>(f, zb, last);
+        }
+    }
+}
+
 // grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks.
 // tab_x / tab_y / tab_z are padded by the host to whole tiles (no bounds tests here).
 template <typename T, bool STRICT, int R, int TX, int TY, int NT, int MINB, bool VEC>
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
     for (int j = 0; j < OY; ++j) ny[j] = tab_y[y0 + yl0 + j];
 
-    // z window: the last TAPS xy-smoothed values of each owned output, in registers
+    // z window: the last TAPS xy-smoothed values of each owned output, in registers, used as a RING: the slice loop
+    // is unrolled TAPS times so that every ring index is a compile-time constant (no register shuffling per slice).
     T win[OY][VW][TAPS];
 #pragma unroll
     for (int j = 0; j < OY; ++j)
@@ -257,7 +271,9 @@ __global__ void __launch_bounds__(NT, MINB)
     stage(zp_first, 0);
     cp_async_commit();
 
-    for (int zp = zp_first; zp <= zp_last; ++zp) {
+    // one slice step; P = (zp - zp_first) % TAPS is the ring slot that receives this slice's xy-smoothed values
+    auto step = [&](auto phase, const int zp) {
+        constexpr int P = decltype(phase)::value;
         const int buf = (zp - zp_first) & 1;
         cp_async_wait_all();
         __syncthreads();  // s_in[buf] complete; everyone is done with s_x and s_in[buf^1] of the previous step
@@ -265,7 +281,6 @@ __global__ void __launch_bounds__(NT, MINB)
         cp_async_commit();
 
         const bool slice_in = (zp >= 0 && zp < g.S);
-        T vxy[OY][VW];
         if (slice_in) {
             const T *sb = s_in + buf * PH * PW;
             // ---- x pass: s_in -> s_x.  Task = one vector of VW outputs; q == qx for every task of this thread.
@@ -291,8 +306,8 @@ __global__ void __launch_bounds__(NT, MINB)
                 *reinterpret_cast<Vec *>(s_x + row * TX + qx * VW) = o;
             }
             __syncthreads();
-            // ---- y pass: s_x -> registers, OY adjacent rows share their taps
-            // rows are streamed once; output j takes row m as its tap k = m - j (ascending k: the reference's order)
+            // ---- y pass: s_x -> ring slot P.  Rows are streamed once; output j takes row m as its tap k = m - j
+            // (ascending k: the reference's order); OY adjacent rows share their taps.
             T acc[OY][VW];
 #pragma unroll
             for (int m = 0; m < OY + 2 * R; ++m) {
@@ -313,39 +328,36 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
             for (int j = 0; j < OY; ++j)
 #pragma unroll
-                for (int i = 0; i < VW; ++i) vxy[j][i] = normalise<T, STRICT>(acc[j][i], ny[j]);
+                for (int i = 0; i < VW; ++i) win[j][i][P] = normalise<T, STRICT>(acc[j][i], ny[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < OY; ++j)
 #pragma unroll
-                for (int i = 0; i < VW; ++i) vxy[j][i] = T(0);
+                for (int i = 0; i < VW; ++i) win[j][i][P] = T(0);
         }
-        // ---- z pass from the register window
+        // ---- z pass from the register ring: tap k (oldest first) lives in slot (P + 1 + k) % TAPS
         const int zo = zp - R;  // output slice completed by this step
-#pragma unroll
-        for (int j = 0; j < OY; ++j)
-#pragma unroll
-            for (int i = 0; i < VW; ++i) {
-#pragma unroll
-                for (int k = 0; k < TAPS - 1; ++k) win[j][i][k] = win[j][i][k + 1];
-                win[j][i][TAPS - 1] = vxy[j][i];
-            }
-        if (zo >= z_begin) {  // zo < z_end holds by construction of zp_last
+        if (zo >= z_begin) {    // zo < z_end holds by construction of zp_last
             const T nz = tab_z[zo];
 #pragma unroll
             for (int j = 0; j < OY; ++j) {
                 const int gy = y0 + yl0 + j;
                 Vec o;
+                bool bad = false;
 #pragma unroll
                 for (int i = 0; i < VW; ++i) {
-                    T sum = DCMA_WZ(0) * win[j][i][0];
+                    T sum = DCMA_WZ(0) * win[j][i][(P + 1) % TAPS];
 #pragma unroll
-                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WZ(k) * win[j][i][k];
-                    T res = normalise<T, STRICT>(sum, nz);
+                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WZ(k) * win[j][i][(P + 1 + k) % TAPS];
+                    o.v[i] = normalise<T, STRICT>(sum, nz);
+                    bad = bad || !isfinite(o.v[i]);
+                }
+                if (bad) {
                     // a non-finite result <=> a non-finite tap somewhere in the (2r+1)^3 support: redo it literally
-                    if (!isfinite(res) && gy < g.R && gx_out + i < g.C)
-                        res = smooth_literal<T, R>(src, g, dwx, dwy, dwz, gx_out + i, gy, zo);
-                    o.v[i] = res;
+#pragma unroll
+                    for (int i = 0; i < VW; ++i)
+                        if (!isfinite(o.v[i]) && gy < g.R && gx_out + i < g.C)
+                            o.v[i] = smooth_literal<T, R>(src, g, dwx, dwy, dwz, gx_out + i, gy, zo);
                 }
                 if (gy < g.R) {
                     T *p = dst + zo * plane + static_cast<long long>(gy) * g.C + gx_out;
@@ -359,7 +371,9 @@ __global__ void __launch_bounds__(NT, MINB)
                 }
             }
         }
-    }
+    };
+
+    for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
 }
 
 #undef DCMA_WX
