@@ -1,0 +1,81 @@
+"""World-size-2 (and 3) gloo tests on CPU of the multi-GPU host logic: case sharding, z-slab partition, the
+neighbour halo exchange and the reductions the bench uses (max time, summed units, global MSE terms)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dicomautomaton_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, slices, halo, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows, cols = 5, 7
+        full = torch.arange(3 * slices * rows * cols, dtype=torch.float64).reshape(3, slices, rows, cols)
+        z0, z1 = parallel.slab_partition(slices, world)[rank]
+        ext = parallel.exchange_z_halos(full[:, z0:z1].contiguous(), halo, rank, world)
+        lo, hi = max(z0 - halo, 0), min(z1 + halo, slices)
+        ok_halo = torch.equal(ext, full[:, lo:hi])
+        # reductions
+        tmax, usum = parallel.reduce_timing(10.0 * (rank + 1), 100.0 + rank)
+        ssq, cnt = parallel.allreduce_mse(float(rank + 1), 10 * (rank + 1))
+        ret[rank] = (ok_halo, tmax, usum, ssq, cnt, parallel.shard_cases(7, world, rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,slices,halo", [(2, 16, 4), (2, 9, 3), (3, 20, 4)])
+def test_halo_exchange_and_reductions(world, slices, halo):
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, slices, halo, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        cases = []
+        for r in range(world):
+            ok_halo, tmax, usum, ssq, cnt, mine = ret[r]
+            assert ok_halo, f"rank {r}: extended slab differs from the whole volume"
+            assert tmax == 10.0 * world
+            assert usum == sum(100.0 + i for i in range(world))
+            assert ssq == sum(range(1, world + 1)) and cnt == 10 * sum(range(1, world + 1))
+            cases += mine
+        assert sorted(cases) == list(range(7))  # every registration runs exactly once
+
+
+def test_slab_partition_properties():
+    for slices in (1, 7, 256, 1024):
+        for world in (1, 2, 3, 4, 8):
+            parts = parallel.slab_partition(slices, world)
+            assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == slices
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_radius_rule_matches_reference():
+    # max(1, int(3 sigma / pxl)) -- src/Alignment_Demons.cc:574-576
+    assert parallel.smoothing_radius(1.5, 1.0) == 4
+    assert parallel.smoothing_radius(1.0, 1.0) == 3
+    assert parallel.smoothing_radius(0.5, 1.0) == 1
+    assert parallel.smoothing_radius(1.5, 2.5) == 1
+    assert parallel.smoothing_radius(0.1, 1.0) == 1
+    assert parallel.smoothing_radius(0.0, 1.0) == 0
