@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Build `host/_build/demons_host_tests`: the reference's OWN unit-test file for this path, compiled IN PLACE from
+/root/reference/src/Alignment_Demons_Tests.cc (read through stdin so that its quoted includes resolve to our drop-in
+header and the shims instead of the reference's Ygor-dependent headers), linked against our AlignViaDemons drop-in and
+libdcma_b200.so.  Nothing of the reference is copied into the repository; the binary is git-ignored and travels to the
+GPU box with the snapshot.  No-op when /root/reference is absent.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_SRC = os.environ.get("DCMA_REFERENCE_SRC", "/root/reference/src")
+OUT = os.path.join(HERE, "_build")
+EXE = os.path.join(OUT, "demons_host_tests")
+
+
+def build(verbose=True):
+    test_src = os.path.join(REF_SRC, "Alignment_Demons_Tests.cc")
+    if not os.path.isfile(test_src):
+        if verbose:
+            print(f"[host tests] {test_src} not found; {'using prebuilt ' + EXE if os.path.isfile(EXE) else 'nothing to do'}")
+        return EXE if os.path.isfile(EXE) else None
+    os.makedirs(OUT, exist_ok=True)
+    libdir = os.path.join(os.path.dirname(HERE), "lib")
+    inc = ["-I", os.path.join(HERE, "shim", "dcma_min"), "-I", os.path.join(HERE, "shim", "ygor_min"), "-I", HERE,
+           "-I", os.path.join(ROOT, "include"), "-I", REF_SRC]
+    cxx = ["g++", "-std=c++17", "-O2", "-Wno-unused-function", "-Wno-unused-variable"]
+    objs = []
+    # 1. the reference's test file, in place, via stdin (so "Structs.h" etc. resolve through -I, not its own directory)
+    o = os.path.join(OUT, "ref_tests.o")
+    cmd = cxx + inc + ["-x", "c++", "-c", "-", "-o", o]
+    if verbose:
+        print("[host tests]", " ".join(cmd), "<", test_src)
+    with open(test_src, "rb") as f:
+        subprocess.check_call(cmd, stdin=f, cwd=OUT)
+    objs.append(o)
+    # 2. doctest main (header used in place from the reference's vendored copy)
+    main_cc = os.path.join(OUT, "doctest_main.cc")
+    with open(main_cc, "w") as f:
+        f.write('#define DOCTEST_CONFIG_IMPLEMENT_WITH_MAIN\n#include "doctest20251212/doctest.h"\n')
+    o = os.path.join(OUT, "doctest_main.o")
+    subprocess.check_call(cxx + ["-I", REF_SRC, "-c", main_cc, "-o", o])
+    objs.append(o)
+    # 3. our drop-in
+    o = os.path.join(OUT, "Alignment_Demons.o")
+    subprocess.check_call(cxx + inc + ["-c", os.path.join(HERE, "Alignment_Demons.cc"), "-o", o])
+    objs.append(o)
+    cmd = ["g++", "-o", EXE, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    if verbose:
+        print("[host tests]", " ".join(cmd))
+    subprocess.check_call(cmd)
+    return EXE
+
+
+if __name__ == "__main__":
+    p = build()
+    print(p if p else "unavailable")
+    sys.exit(0 if p else 1)

@@ -1,0 +1,2 @@
+// Empty stand-in for the reference's Structs.h: the Demons unit tests include it but use nothing from it.
+#pragma once

@@ -1,0 +1,47 @@
+"""The C++ host drop-in (dicomautomaton_b200/host/Alignment_Demons.{h,cc}) under the REFERENCE'S OWN unit tests:
+/root/reference/src/Alignment_Demons_Tests.cc is compiled in place, unmodified, against our AlignViaDemons and a minimal
+Ygor stand-in (host/build_host_tests.py), and linked to libdcma_b200.so.  The binary is built in the container where
+/root/reference exists and travels to the GPU box."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "dicomautomaton_b200", "host"))
+
+
+@pytest.fixture(scope="module")
+def exe():
+    import build_host_tests
+    p = build_host_tests.build(verbose=False)
+    if not p:
+        pytest.skip("reference test source not available and no prebuilt binary")
+    return p
+
+
+def _run(exe, *args, mode=None):
+    env = dict(os.environ, YLOG_VERBOSITY="0")
+    if mode:
+        env["DCMA_B200_FIELD_MODE"] = mode
+    r = subprocess.run([exe, *args], capture_output=True, text=True, env=env, timeout=600)
+    m = re.search(r"test cases:\s+(\d+)\s+\|\s+(\d+) passed\s+\|\s+(\d+) failed", r.stdout)
+    assert m, r.stdout[-2000:]
+    return int(m.group(1)), int(m.group(2)), int(m.group(3)), r.stdout
+
+
+def test_reference_host_side_cases_pass_without_gpu(exe):
+    """resample / histogram_match (exact values 10, 17.5, 25, 32.5) / warp_image_with_field / empty input."""
+    total, passed, failed, out = _run(
+        exe, "-tc=resample_image_to_reference_grid*,histogram_match*,warp_image_with_field*,AlignViaDemons handles empty inputs")
+    assert total == 6 and failed == 0, out[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp64", "fp64_strict", "fp32"])
+def test_reference_unit_tests_pass_against_the_gpu_dropin(exe, mode):
+    """All 14 doctest cases of the reference (src/Alignment_Demons_Tests.cc) against the CUDA path."""
+    total, passed, failed, out = _run(exe, mode=mode)
+    assert total == 14 and failed == 0, out[-3000:]
