@@ -55,6 +55,32 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(tag: str, defines, verbose: bool = False) -> str:
+    """Kernel-tuning builds: the same library with extra -D flags, as lib/libdcma_b200_<tag>.so (selected at run time
+    with DCMA_B200_LIB=<path>).  Never used by the product path or the tests."""
+    nvcc = _nvcc()
+    objdir = os.path.join(OBJDIR, "variant_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, f"libdcma_b200_{tag}.so")
+
+    def one(item):
+        src, extra = item
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(one, UNITS.items()))
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", *objs, "-o", out])
+    if verbose:
+        print("[dcma_b200.build] variant", tag, defines, "->", out)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdcma_b200.so")
+# DCMA_B200_LIB selects another build of the SAME library (kernel-tuning experiments: tools/build_variant.py)
+LIB_PATH = os.environ.get("DCMA_B200_LIB") or os.path.join(HERE, "lib", "libdcma_b200.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 FIELD_FP64, FIELD_FP64_STRICT, FIELD_FP32 = 0, 1, 2

@@ -28,6 +28,25 @@ using namespace ::dcma;
 
 constexpr int kTileX = 32, kTileY = 8;  // per-voxel kernels: 32 x 8 voxels of one slice per 256-thread block
 
+// The per-voxel kernels march along z and every step ends in a chain  D -> sample position -> gathers -> arithmetic,
+// whose DRAM latency (~1000 SM cycles loaded) the resident warps cannot cover (ncu: >70 % long-scoreboard stalls).
+// Each step therefore asks for the lines it will need kPrefetchAhead slices later -- the voxel's own row of every
+// streamed array, which is where the gathers land for displacements of a few voxels -- so that they come from L2.
+#ifndef DCMA_PREFETCH_AHEAD
+#define DCMA_PREFETCH_AHEAD 3
+#endif
+constexpr int kPrefetchAhead = DCMA_PREFETCH_AHEAD;
+#ifndef DCMA_PREFETCH_L1
+#define DCMA_PREFETCH_L1 0
+#endif
+__device__ __forceinline__ void prefetch_line(const void *p) {
+#if DCMA_PREFETCH_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // scalar helpers.  B200 runs F2F/F2I/I2F/FRND/MUFU at 16 lanes/clk/SM (measured with ncu: the "xu" pipe), four times
 // slower than the fp64 pipe, so floor() and int<->double conversions are done with fp64/fp32 adds instead.
@@ -35,32 +54,20 @@ constexpr int kTileX = 32, kTileY = 8;  // per-voxel kernels: 32 x 8 voxels of o
 __device__ __forceinline__ bool finite_f(float v) { return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u; }
 __device__ __forceinline__ bool finite_d(double v) { return (static_cast<unsigned>(__double2hiint(v)) & 0x7ff00000u) != 0x7ff00000u; }
 
-// floor of |s| < 2^31 as (double f, int i), exactly: s + 1.5*2^52 rounds to the nearest integer, whose two's complement
-// sits in the low word; one compare fixes round-to-nearest into round-down.
+// floor of |s| < 2^31 as (double f, int i), exactly: the round-DOWN add  s + 1.5*2^52  is  1.5*2^52 + floor(s)  (ulp 1 there),
+// whose two's complement low word is floor(s); subtracting the magic back is exact.  No compare, no conversion pipe.
 __device__ __forceinline__ void floor_split(double s, double &f, int &i) {
     constexpr double kMagic = 6755399441055744.0;
-    const double t = __dadd_rn(s, kMagic);
-    double r = __dadd_rn(t, -kMagic);
-    int n = __double2loint(t);
-    if (r > s) {
-        r = __dadd_rn(r, -1.0);
-        n -= 1;
-    }
-    f = r;
-    i = n;
+    const double t = __dadd_rd(s, kMagic);
+    f = __dadd_rn(t, -kMagic);
+    i = __double2loint(t);
 }
-// same for |s| < 2^22 in fp32 (magic 1.5*2^23)
+// same for |s| < 2^22 in fp32 (magic 1.5*2^23 = 0x4B400000: consecutive integers are consecutive bit patterns)
 __device__ __forceinline__ void floor_split(float s, float &f, int &i) {
     constexpr float kMagic = 12582912.0f;
-    const float t = __fadd_rn(s, kMagic);
-    float r = __fadd_rn(t, -kMagic);
-    int n = static_cast<int>(__float_as_uint(t) & 0x7fffffu) - 0x400000;
-    if (r > s) {
-        r = __fadd_rn(r, -1.0f);
-        n -= 1;
-    }
-    f = r;
-    i = n;
+    const float t = __fadd_rd(s, kMagic);
+    f = __fadd_rn(t, -kMagic);
+    i = __float_as_int(t) - 0x4B400000;
 }
 
 // x rounded to float precision and widened again (the reference narrows four corners to float, cc:439-442).
@@ -84,61 +91,67 @@ __device__ __forceinline__ double diff_exact(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Sample position of a voxel displaced by d mm along one axis (cc:401-421, cc:501-513): integer corner i0 and
-// fraction t.  Clamped to [-4, extent+4]: a clamped coordinate has both corners outside the grid either way, and the
-// reference's int64 cast of an absurd coordinate would be undefined.
+// Sample position of a voxel displaced by d mm along one axis (cc:401-421, cc:501-513): integer corner i0, fraction t
+// and the coordinate magnitude |s| (for the range guard of tri_coords).  Nothing is clamped: a coordinate that is
+// NaN, infinite or beyond the exact range of floor_split makes Tri::ok false, and such a sample point has every
+// corner outside the grid anyway (extents are < 2^20 per axis; the reference's int64 cast would be undefined there).
 // ------------------------------------------------------------------------------------------------------------------
 template <bool STRICT>
-__device__ __forceinline__ void axis_coord(int xi, double xd, double d, double p, double ip, double lim, int &i0,
-                                           double &t) {
+__device__ __forceinline__ void axis_coord(int xi, double xd, double d, double p, double ip, int &i0, double &t,
+                                           double &mag) {
     (void)xi;
-    double s = xd + (STRICT ? ((p == 1.0) ? d : d / p) : d * ip);  // reference: x + dx / pxl_dx
-    s = fmin(fmax(s, -4.0), lim);
+    const double s = xd + (STRICT ? ((p == 1.0) ? d : d / p) : d * ip);  // reference: x + dx / pxl_dx
     double f;
     floor_split(s, f, i0);
     t = s - f;
+    mag = fabs(s);
 }
 template <bool STRICT>
-__device__ __forceinline__ void axis_coord(int xi, float xd, float d, float p, float ip, float lim, int &i0, float &t) {
+__device__ __forceinline__ void axis_coord(int xi, float xd, float d, float p, float ip, int &i0, float &t, float &mag) {
     (void)xd;
     (void)p;
     // fp32 mode: never add the voxel index to the displacement (that would cost 10 bits of the fraction)
-    float s = fminf(fmaxf(d * ip, -lim), lim);
+    const float s = d * ip;
     float f;
     int n;
     floor_split(s, f, n);
     i0 = xi + n;
     t = s - f;
+    mag = fabsf(s);
 }
 
 // per-kernel constants of the compute type
 template <typename CT>
 struct AxisK {
-    CT px, py, pz, ipx, ipy, ipz, limx, limy, limz;
+    CT px, py, pz, ipx, ipy, ipz;
     __device__ __forceinline__ explicit AxisK(const Geo &g)
         : px(static_cast<CT>(g.px)), py(static_cast<CT>(g.py)), pz(static_cast<CT>(g.pz)),
-          ipx(static_cast<CT>(g.ipx)), ipy(static_cast<CT>(g.ipy)), ipz(static_cast<CT>(g.ipz)),
-          limx(static_cast<CT>(g.C + 4)), limy(static_cast<CT>(g.R + 4)), limz(static_cast<CT>(g.S + 4)) {}
+          ipx(static_cast<CT>(g.ipx)), ipy(static_cast<CT>(g.ipy)), ipz(static_cast<CT>(g.ipz)) {}
 };
 
 template <typename CT>
 struct Tri {
     int x0, y0, z0;
     CT tx, ty, tz;
+    bool ok;  // coordinates finite and inside floor_split's exact range; false => every corner is outside the grid
 };
 
 template <typename CT, bool STRICT>
 __device__ __forceinline__ Tri<CT> tri_coords(const Geo &g, const AxisK<CT> &k, int x, int y, int z, CT xd, CT yd, CT zd,
                                               CT dx, CT dy, CT dz) {
     Tri<CT> t;
-    axis_coord<STRICT>(x, xd, dx, k.px, k.ipx, k.limx, t.x0, t.tx);
-    axis_coord<STRICT>(y, yd, dy, k.py, k.ipy, k.limy, t.y0, t.ty);
+    CT mx, my, mz;
+    axis_coord<STRICT>(x, xd, dx, k.px, k.ipx, t.x0, t.tx, mx);
+    axis_coord<STRICT>(y, yd, dy, k.py, k.ipy, t.y0, t.ty, my);
     if (g.is2d) {  // cc:405, 413, 421 / cc:503, 510, 513
         t.z0 = z;
         t.tz = CT(0);
+        mz = CT(0);
     } else {
-        axis_coord<STRICT>(z, zd, dz, k.pz, k.ipz, k.limz, t.z0, t.tz);
+        axis_coord<STRICT>(z, zd, dz, k.pz, k.ipz, t.z0, t.tz, mz);
     }
+    // one compare for all three axes; NaN compares false.  2^21 (float: |s| < 2^22 needed) / 2^30 (double: < 2^31)
+    t.ok = (mx + my + mz) < (sizeof(CT) == 4 ? CT(2097152.0) : CT(1073741824.0));
     return t;
 }
 
@@ -150,39 +163,54 @@ __device__ __forceinline__ Tri<CT> tri_coords(const Geo &g, const AxisK<CT> &k, 
 //   float  path: fp32 on differences to the first corner (error ~1e-6 HU instead of ~1e-4 HU for plain fp32).
 // Returns diff = fixed - warped through `diff` when WANT_DIFF, and the warped value itself.
 // ------------------------------------------------------------------------------------------------------------------
-// Loads are issued UNCONDITIONALLY from coordinates clamped into the grid (so the 8 gathers of a voxel, and those of
-// the other voxels of the warp, are all in flight together); the return value says whether every corner was inside.
+// Grid limits of the "all eight corners inside" test (cc:516-519) as three unsigned compares.
+struct InsideK {
+    unsigned cx, cy, cz;  // x0 < C-1, y0 < R-1, z0 < S-1 (or z0 < S when slices == 1: z1 = z0, cc:510-513)
+    __device__ __forceinline__ explicit InsideK(const Geo &g)
+        : cx(static_cast<unsigned>(g.C - 1)), cy(static_cast<unsigned>(g.R - 1)),
+          cz(static_cast<unsigned>(g.is2d ? g.S : g.S - 1)) {}
+    template <typename CT>
+    __device__ __forceinline__ bool operator()(const Tri<CT> &t) const {
+        return t.ok && static_cast<unsigned>(t.x0) < cx && static_cast<unsigned>(t.y0) < cy &&
+               static_cast<unsigned>(t.z0) < cz;
+    }
+};
+
+// The eight corners of a sample point whose corners are ALL inside the grid: one row offset, three adds, and the
+// x+1 neighbours as immediate offsets.  No clamps, no predicates.
 template <typename IX, bool CH1>
-__device__ __forceinline__ bool load_corners(const float *__restrict__ M, const Geo &g, int x0, int y0, int z0, int c,
+__device__ __forceinline__ void load_corners(const float *__restrict__ M, const Geo &g, int x0, int y0, int z0, int c,
                                              float (&v)[8]) {
-    const int x1 = x0 + 1, y1 = y0 + 1, z1 = g.is2d ? z0 : (z0 + 1);
-    const bool inside = !(x0 < 0 || x1 >= g.C || y0 < 0 || y1 >= g.R || z0 < 0 || z1 >= g.S);  // cc:516-519
-    const int cx0 = min(max(x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
-    const int cy0 = min(max(y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
-    const int cz0 = min(max(z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
-    const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
-    const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
+    const IX o00 = (static_cast<IX>(z0) * g.R + y0) * g.C + x0;
+    const IX zstep = g.is2d ? IX(0) : static_cast<IX>(g.R) * g.C;
     if (CH1) {
-        v[0] = __ldg(M + (r00 + cx0));
-        v[1] = __ldg(M + (r00 + cx1));
-        v[2] = __ldg(M + (r10 + cx0));
-        v[3] = __ldg(M + (r10 + cx1));
-        v[4] = __ldg(M + (r01 + cx0));
-        v[5] = __ldg(M + (r01 + cx1));
-        v[6] = __ldg(M + (r11 + cx0));
-        v[7] = __ldg(M + (r11 + cx1));
+        const float *p00 = M + o00;
+        const float *p10 = p00 + g.C;
+        const float *p01 = p00 + zstep;
+        const float *p11 = p01 + g.C;
+        v[0] = __ldg(p00);
+        v[1] = __ldg(p00 + 1);
+        v[2] = __ldg(p10);
+        v[3] = __ldg(p10 + 1);
+        v[4] = __ldg(p01);
+        v[5] = __ldg(p01 + 1);
+        v[6] = __ldg(p11);
+        v[7] = __ldg(p11 + 1);
     } else {
         const IX ch = g.CH;
-        v[0] = __ldg(M + (r00 + cx0) * ch + c);
-        v[1] = __ldg(M + (r00 + cx1) * ch + c);
-        v[2] = __ldg(M + (r10 + cx0) * ch + c);
-        v[3] = __ldg(M + (r10 + cx1) * ch + c);
-        v[4] = __ldg(M + (r01 + cx0) * ch + c);
-        v[5] = __ldg(M + (r01 + cx1) * ch + c);
-        v[6] = __ldg(M + (r11 + cx0) * ch + c);
-        v[7] = __ldg(M + (r11 + cx1) * ch + c);
+        const float *p00 = M + o00 * ch + c;
+        const float *p10 = p00 + g.C * ch;
+        const float *p01 = p00 + zstep * ch;
+        const float *p11 = p01 + g.C * ch;
+        v[0] = __ldg(p00);
+        v[1] = __ldg(p00 + ch);
+        v[2] = __ldg(p10);
+        v[3] = __ldg(p10 + ch);
+        v[4] = __ldg(p01);
+        v[5] = __ldg(p01 + ch);
+        v[6] = __ldg(p11);
+        v[7] = __ldg(p11 + ch);
     }
-    return inside;
 }
 
 // v = {c000, c100, c010, c110, c001, c101, c011, c111}
@@ -210,12 +238,16 @@ __device__ __forceinline__ float warp_interp(const float (&v)[8], const Tri<floa
     return finite_f(w) ? w : CUDART_NAN_F;
 }
 
+// `inside` is InsideK(t): a sample point with any corner outside the grid is NaN without touching memory (cc:516-522).
 template <typename CT, typename IX, bool CH1>
-__device__ __forceinline__ float warp_one(const float *__restrict__ M, const Geo &g, const Tri<CT> &t, int c) {
-    float v[8];
-    const bool inside = load_corners<IX, CH1>(M, g, t.x0, t.y0, t.z0, c, v);
-    const float w = warp_interp(v, t);
-    return inside ? w : CUDART_NAN_F;
+__device__ __forceinline__ float warp_one(const float *__restrict__ M, const Geo &g, const Tri<CT> &t, bool inside, int c) {
+    float w = CUDART_NAN_F;
+    if (inside) {
+        float v[8];
+        load_corners<IX, CH1>(M, g, t.x0, t.y0, t.z0, c, v);
+        w = warp_interp(v, t);
+    }
+    return w;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -377,6 +409,7 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         const T *D1 = D + g.N, *D2 = D + 2 * g.N;
         T *U1 = U + g.N, *U2 = U + 2 * g.N;
         const AxisK<CT> ak(g);
+        const InsideK ik(g);
         const GradK<IX> gk(g, x, y, ch);
         const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
         // Each block marches through a run of CONSECUTIVE slices [z_begin, z_end): the z neighbours of the gradient
@@ -395,8 +428,20 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             }
             float f_prev = __ldg(F + (z_begin > 0 ? v - plane : v) * ch);
             float f_cur = __ldg(F + v * ch);
+            const IX pf = plane * kPrefetchAhead;
             for (int z = z_begin; z < z_end; ++z, v += plane, zd += CT(1)) {
                 const float *Fv = F + v * ch;
+                if (kPrefetchAhead > 0 && z + kPrefetchAhead < g.S) {
+                    prefetch_line(Fv + pf * ch);
+                    if (w_src == 1) {
+                        prefetch_line(M + (v + pf) * ch);
+                        prefetch_line(D + v + pf);
+                        prefetch_line(D1 + v + pf);
+                        prefetch_line(D2 + v + pf);
+                    } else {
+                        prefetch_line((w_src == 0 ? M : Wbuf) + (v + pf) * ch);
+                    }
+                }
                 Stencil st;
                 load_stencil_xy<IX>(st, Fv, gk);
                 const float f_next = (z + 1 < g.S) ? __ldg(Fv + pch) : f_cur;
@@ -406,15 +451,11 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                 const float fixed_val = f_cur;
                 float moving_val;
                 if (w_src == 1) {
-                    bool ok;
-                    if (sizeof(CT) == 8)
-                        ok = finite_d(dx) && finite_d(dy) && finite_d(dz);  // cc:494-500
-                    else
-                        ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
-                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, ok ? dx : CT(0),
-                                                             ok ? dy : CT(0), ok ? dz : CT(0));
-                    const float w = warp_one<CT, IX, CH1>(M, g, t, 0);  // only channel 0 drives the force (cc:294-295)
-                    moving_val = ok ? w : CUDART_NAN_F;
+                    // a non-finite displacement component makes the voxel NaN (cc:494-500): it fails tri_coords'
+                    // range guard; with slices == 1 the unused z component is folded into x for that purpose
+                    if (g.is2d) dx += dz - dz;
+                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, dx, dy, dz);
+                    moving_val = warp_one<CT, IX, CH1>(M, g, t, ik(t), 0);  // only channel 0 drives the force (cc:294-295)
                     if (z + 1 < z_end) {
                         dx = D[v + plane];
                         dy = D1[v + plane];
@@ -524,21 +565,19 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const IX vxy = static_cast<IX>(y) * g.C + x;
     const T *D1 = D + g.N, *D2 = D + 2 * g.N;
     const AxisK<CT> ak(g);
+    const InsideK ik(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
     const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
     for (int z = z_begin; z < z_end; ++z) {
         const IX v = static_cast<IX>(z) * plane + vxy;
-        const CT dx = D[v], dy = D1[v], dz = D2[v];
-        bool ok;
-        if (sizeof(CT) == 8)
-            ok = finite_d(dx) && finite_d(dy) && finite_d(dz);
-        else
-            ok = finite_f(dx) && finite_f(dy) && finite_f(dz);
-        Tri<CT> t;
-        if (ok) t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, static_cast<CT>(z), dx, dy, dz);
+        CT dx = D[v];
+        const CT dy = D1[v], dz = D2[v];
+        if (g.is2d) dx += dz - dz;  // non-finite z component => NaN voxel even when z is not interpolated (cc:494-500)
+        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, static_cast<CT>(z), dx, dy, dz);
+        const bool inside = ik(t);
         const int nch = CH1 ? 1 : g.CH;
         for (int c = 0; c < nch; ++c) {
-            float w = ok ? warp_one<CT, IX, CH1>(M, g, t, c) : CUDART_NAN_F;
+            float w = warp_one<CT, IX, CH1>(M, g, t, inside, c);
             if (use_oob && !finite_f(w)) w = oob_value;
             W[v * ch + c] = w;
         }
@@ -604,6 +643,7 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const IX plane = static_cast<IX>(g.R) * g.C;
     const IX vxy = static_cast<IX>(y) * g.C + x;
     const AxisK<CT> ak(g);
+    const InsideK ik(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
     const long long N = g.N;
     const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);  // consecutive slices: gathers overlap
@@ -618,33 +658,66 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const CT pxl[3] = {ak.px, ak.py, ak.pz};
     for (int z = z_begin; z < z_end; ++z, zd += CT(1)) {
         const IX v = static_cast<IX>(z) * plane + vxy;
-        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
-        const int x1 = t.x0 + 1, y1 = t.y0 + 1, z1 = g.is2d ? t.z0 : (t.z0 + 1);
-        const bool vx0 = static_cast<unsigned>(t.x0) < static_cast<unsigned>(g.C);
-        const bool vx1 = static_cast<unsigned>(x1) < static_cast<unsigned>(g.C);
-        const bool vy0 = static_cast<unsigned>(t.y0) < static_cast<unsigned>(g.R);
-        const bool vy1 = static_cast<unsigned>(y1) < static_cast<unsigned>(g.R);
-        const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.S);
-        const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.S);
-        // gathers are issued unconditionally from clamped coordinates (all 24 in flight together); corners outside
-        // the grid are then replaced by zero (cc:424-427)
-        const int cx0 = min(max(t.x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
-        const int cy0 = min(max(t.y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
-        const int cz0 = min(max(t.z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
-        const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
-        const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
-        CT q[3][8];
+        if (kPrefetchAhead > 0 && z + kPrefetchAhead < g.S) {
+            const IX vp = v + plane * kPrefetchAhead;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const T *Uc = U + c * N;
-            q[c][0] = Uc[r00 + cx0];
-            q[c][1] = Uc[r00 + cx1];
-            q[c][2] = Uc[r10 + cx0];
-            q[c][3] = Uc[r10 + cx1];
-            q[c][4] = Uc[r01 + cx0];
-            q[c][5] = Uc[r01 + cx1];
-            q[c][6] = Uc[r11 + cx0];
-            q[c][7] = Uc[r11 + cx1];
+            for (int c = 0; c < 3; ++c) {
+                prefetch_line(U + c * N + vp);
+                prefetch_line(D + c * N + vp);
+            }
+        }
+        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
+        const CT tx = t.tx, ty = t.ty, tz = t.tz;
+        CT q[3][8];
+        const bool inside = ik(t);
+        if (inside) {
+            // all eight corners in the grid (the common case): one row offset shared by the three components,
+            // x+1 neighbours as immediate offsets, no predicates
+            const IX o00 = (static_cast<IX>(t.z0) * g.R + t.y0) * g.C + t.x0;
+            const IX zstep = g.is2d ? IX(0) : plane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T *p00 = U + c * N + o00;
+                const T *p10 = p00 + g.C;
+                const T *p01 = p00 + zstep;
+                const T *p11 = p01 + g.C;
+                q[c][0] = p00[0];
+                q[c][1] = p00[1];
+                q[c][2] = p10[0];
+                q[c][3] = p10[1];
+                q[c][4] = p01[0];
+                q[c][5] = p01[1];
+                q[c][6] = p11[0];
+                q[c][7] = p11[1];
+            }
+        } else {
+            // some corner outside: gather from clamped coordinates, then replace outside corners by zero (cc:424-427).
+            // A coordinate that failed the range guard has every corner outside.
+            const int x1 = t.x0 + 1, y1 = t.y0 + 1, z1 = g.is2d ? t.z0 : (t.z0 + 1);
+            const bool vx0 = t.ok && static_cast<unsigned>(t.x0) < static_cast<unsigned>(g.C);
+            const bool vx1 = t.ok && static_cast<unsigned>(x1) < static_cast<unsigned>(g.C);
+            const bool vy0 = static_cast<unsigned>(t.y0) < static_cast<unsigned>(g.R);
+            const bool vy1 = static_cast<unsigned>(y1) < static_cast<unsigned>(g.R);
+            const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.S);
+            const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.S);
+            const int cx0 = min(max(t.x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
+            const int cy0 = min(max(t.y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
+            const int cz0 = min(max(t.z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
+            const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
+            const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T *Uc = U + c * N;
+                q[c][0] = (vz0 && vy0 && vx0) ? Uc[r00 + cx0] : T(0);
+                q[c][1] = (vz0 && vy0 && vx1) ? Uc[r00 + cx1] : T(0);
+                q[c][2] = (vz0 && vy1 && vx0) ? Uc[r10 + cx0] : T(0);
+                q[c][3] = (vz0 && vy1 && vx1) ? Uc[r10 + cx1] : T(0);
+                // slices == 1: z1 == z0, the z0 plane is reused (cc:436-442)
+                q[c][4] = (vz1 && vy0 && vx0) ? Uc[r01 + cx0] : T(0);
+                q[c][5] = (vz1 && vy0 && vx1) ? Uc[r01 + cx1] : T(0);
+                q[c][6] = (vz1 && vy1 && vx0) ? Uc[r11 + cx0] : T(0);
+                q[c][7] = (vz1 && vy1 && vx1) ? Uc[r11 + cx1] : T(0);
+            }
         }
         // prefetch the next slice's displacement before consuming the gathers
         CT dn[3] = {CT(0), CT(0), CT(0)};
@@ -653,25 +726,14 @@ __global__ void __launch_bounds__(kTileX *kTileY)
 #pragma unroll
             for (int c = 0; c < 3; ++c) dn[c] = D[vn + c * N];
         }
-        const CT tx = t.tx, ty = t.ty, tz = t.tz;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const CT c000 = (vz0 && vy0 && vx0) ? q[c][0] : CT(0);
-            const CT c100 = (vz0 && vy0 && vx1) ? q[c][1] : CT(0);
-            const CT c010 = (vz0 && vy1 && vx0) ? q[c][2] : CT(0);
-            const CT c110 = (vz0 && vy1 && vx1) ? q[c][3] : CT(0);
-            CT c001, c101, c011, c111;
-            if (g.is2d) {  // cc:436-442: the z0 plane is reused (and still narrowed)
-                c001 = narrow_to_float<STRICT>(c000);
-                c101 = narrow_to_float<STRICT>(c100);
-                c011 = narrow_to_float<STRICT>(c010);
-                c111 = narrow_to_float<STRICT>(c110);
-            } else {
-                c001 = narrow_to_float<STRICT>((vz1 && vy0 && vx0) ? q[c][4] : CT(0));
-                c101 = narrow_to_float<STRICT>((vz1 && vy0 && vx1) ? q[c][5] : CT(0));
-                c011 = narrow_to_float<STRICT>((vz1 && vy1 && vx0) ? q[c][6] : CT(0));
-                c111 = narrow_to_float<STRICT>((vz1 && vy1 && vx1) ? q[c][7] : CT(0));
-            }
+            const CT c000 = q[c][0], c100 = q[c][1], c010 = q[c][2], c110 = q[c][3];
+            // the four upper-z corners are narrowed to float as the reference does (cc:439-442)
+            const CT c001 = narrow_to_float<STRICT>(q[c][4]);
+            const CT c101 = narrow_to_float<STRICT>(q[c][5]);
+            const CT c011 = narrow_to_float<STRICT>(q[c][6]);
+            const CT c111 = narrow_to_float<STRICT>(q[c][7]);
             const CT c00 = c000 * (CT(1) - tx) + c100 * tx;  // cc:445-451
             const CT c10 = c010 * (CT(1) - tx) + c110 * tx;
             const CT c01 = c001 * (CT(1) - tx) + c101 * tx;

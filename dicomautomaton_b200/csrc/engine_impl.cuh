@@ -42,7 +42,7 @@ class Engine final : public EngineBase {
             throw std::invalid_argument("volume extents and channel count must be >= 1");
         if (!(geom.pxl_dx > 0.0) || !(geom.pxl_dy > 0.0) || !(geom.pxl_dz > 0.0))
             throw std::invalid_argument("voxel spacing must be > 0");
-        if (geom.slices > (1 << 21) || geom.rows > (1 << 21) || geom.cols > (1 << 21))
+        if (geom.slices > (1 << 19) || geom.rows > (1 << 19) || geom.cols > (1 << 19))
             throw std::invalid_argument("volume extent too large");
         const long long N = geom.slices * geom.rows * geom.cols;
         if (N * 3 >= (1LL << 40)) throw std::invalid_argument("volume too large");

@@ -86,6 +86,66 @@ struct alignas(16) VecT {  // one 16-byte shared/global access: 4 floats or 2 do
     T v[W];
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Lane groups of the y and z passes.  fp32 (never STRICT): two x-adjacent outputs travel as ONE 64-bit register pair and
+// every tap is one packed FFMA2 (PTX fma.rn.f32x2, sm_100+) with the weight broadcast to both lanes -- the same
+// round-to-nearest FMA per lane as the scalar code, half the issue slots.  fp64 / STRICT: one output per group, plain
+// `sum += w * v` so that the translation unit's -fmad setting decides about contraction.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T, bool PACKED>
+struct LaneGroup {
+    using V = T;
+    static constexpr int L = 1;
+    template <typename VecLike>
+    static __device__ __forceinline__ V get(const VecLike &t, int p) { return t.v[p]; }
+    template <typename VecLike>
+    static __device__ __forceinline__ void put(VecLike &t, int p, V v) { t.v[p] = v; }
+    static __device__ __forceinline__ V zero() { return T(0); }
+    static __device__ __forceinline__ V pack(T lo, T) { return lo; }             // unused when L == 1
+    static __device__ __forceinline__ void unpack(V v, T &lo, T &hi) { lo = hi = v; }  // unused when L == 1
+    static __device__ __forceinline__ V mul2(V a, V b) { return a * b; }
+    static __device__ __forceinline__ V mul(V a, T w) { return w * a; }
+    static __device__ __forceinline__ V fma(V acc, V a, T w) {
+        acc += w * a;
+        return acc;
+    }
+};
+template <>
+struct LaneGroup<float, true> {
+    using V = unsigned long long;  // {lo = element 2p, hi = element 2p+1}
+    static constexpr int L = 2;
+    static __device__ __forceinline__ V pack(float lo, float hi) {
+        V r;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+        return r;
+    }
+    template <typename VecLike>
+    static __device__ __forceinline__ V get(const VecLike &t, int p) { return pack(t.v[2 * p], t.v[2 * p + 1]); }
+    template <typename VecLike>
+    static __device__ __forceinline__ void put(VecLike &t, int p, V v) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(t.v[2 * p]), "=f"(t.v[2 * p + 1]) : "l"(v));
+    }
+    static __device__ __forceinline__ V zero() { return 0ull; }
+    static __device__ __forceinline__ void unpack(V v, float &lo, float &hi) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    }
+    static __device__ __forceinline__ V mul2(V a, V b) {  // lane-wise product of two pairs
+        V r;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+        return r;
+    }
+    static __device__ __forceinline__ V mul(V a, float w) {
+        V r;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(pack(w, w)));
+        return r;
+    }
+    static __device__ __forceinline__ V fma(V acc, V a, float w) {
+        V r;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pack(w, w)), "l"(acc));
+        return r;
+    }
+};
+
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, int src_bytes) {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
@@ -163,15 +223,32 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
     return (zw > T(0)) ? (zs / zw) : z_centre;
 }
 
-// calls f(integral_constant<P>, zb + P) for P = 0..N-1 while zb + P <= last (compile-time ring phases)
-template <int N, int P, typename F>
-__device__ __forceinline__ void unroll_phases(F &f, const int zb, const int last) {
-    if constexpr (P < N) {
-        if (zb + P <= last) {
-            f(std::integral_constant<int, P>{}, zb + P);
-            unroll_phases<N, P + 1>(f, zb, last);
-        }
+// calls f(integral_constant<P>{}) for the run-time ring phase `phase` in [0, N): one uniform jump per slice, so that the
+// slice step's common code (staging, x and y passes) exists once and only the ring insert + z pass are per phase.
+template <int N, typename F>
+__device__ __forceinline__ void dispatch_phase(const int phase, F &f) {
+#define DCMA_PHASE_CASE(P)                                        \
+    case P:                                                       \
+        if constexpr (P < N) f(std::integral_constant<int, P>{}); \
+        break;
+    switch (phase) {
+        DCMA_PHASE_CASE(0)
+        DCMA_PHASE_CASE(1)
+        DCMA_PHASE_CASE(2)
+        DCMA_PHASE_CASE(3)
+        DCMA_PHASE_CASE(4)
+        DCMA_PHASE_CASE(5)
+        DCMA_PHASE_CASE(6)
+        DCMA_PHASE_CASE(7)
+        DCMA_PHASE_CASE(8)
+        DCMA_PHASE_CASE(9)
+        DCMA_PHASE_CASE(10)
+        DCMA_PHASE_CASE(11)
+        DCMA_PHASE_CASE(12)
+        default: break;
     }
+#undef DCMA_PHASE_CASE
+    static_assert(N <= 13, "ring too long for dispatch_phase");
 }
 
 // grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks.
@@ -186,6 +263,11 @@ __global__ void __launch_bounds__(NT, MINB)
     constexpr int VW = Cfg::VW, HX = Cfg::HX, PW = Cfg::PW, PH = Cfg::PH, QX = Cfg::QX, OY = Cfg::OY, TAPS = Cfg::TAPS;
     constexpr int XT = Cfg::XT, XN = Cfg::XN, NV = Cfg::NV, CPR = Cfg::CPR, NCP = Cfg::NCP;
     using Vec = VecT<T>;
+    // fp32 (never STRICT): packed two-lane arithmetic and ONE deferred normalisation per pass pair (see below)
+    constexpr bool PACKED = (!STRICT && sizeof(T) == 4);
+    using LG = LaneGroup<T, PACKED>;
+    using GV = typename LG::V;
+    constexpr int NG = VW / LG::L;  // lane groups per 16-byte vector
     if (it > ctrl->converged_at) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -251,35 +333,44 @@ __global__ void __launch_bounds__(NT, MINB)
     const int qx = tid & (QX - 1), ry = tid / QX;
     const int gx_out = x0 + qx * VW;
     const int yl0 = ry * OY;  // first owned (local) output row; owned rows are adjacent
-    T nx[VW], ny[OY];          // per-position normalisers (wsum or 1/wsum), fixed across slices
+    // per-position normalisers (wsum, or 1/wsum when not STRICT), fixed across slices.  PACKED: the x and y
+    // normalisers are applied together, once, after the y pass (they do not depend on the y or z tap): nxy = nx * ny.
+    T nx[VW], ny[OY];
+    GV nxy[OY][NG];
 #pragma unroll
     for (int i = 0; i < VW; ++i) nx[i] = tab_x[gx_out + i];
 #pragma unroll
     for (int j = 0; j < OY; ++j) ny[j] = tab_y[y0 + yl0 + j];
+    if constexpr (PACKED) {
+#pragma unroll
+        for (int j = 0; j < OY; ++j)
+#pragma unroll
+            for (int i = 0; i < NG; ++i) nxy[j][i] = LG::pack(nx[2 * i] * ny[j], nx[2 * i + 1] * ny[j]);
+    }
 
-    // z window: the last TAPS xy-smoothed values of each owned output, in registers, used as a RING: the slice loop
-    // is unrolled TAPS times so that every ring index is a compile-time constant (no register shuffling per slice).
-    T win[OY][VW][TAPS];
+    // z window: the last TAPS xy-smoothed values of each owned output, in registers, used as a RING: the ring insert
+    // and the z pass exist once per ring phase so that every ring index is a compile-time constant.
+    GV win[OY][NG][TAPS];
 #pragma unroll
     for (int j = 0; j < OY; ++j)
 #pragma unroll
-        for (int i = 0; i < VW; ++i)
+        for (int i = 0; i < NG; ++i)
 #pragma unroll
-            for (int k = 0; k < TAPS; ++k) win[j][i][k] = T(0);
+            for (int k = 0; k < TAPS; ++k) win[j][i][k] = LG::zero();
 
     const int zp_first = z_begin - R, zp_last = z_end - 1 + R;
     stage(zp_first, 0);
     cp_async_commit();
 
-    // one slice step; P = (zp - zp_first) % TAPS is the ring slot that receives this slice's xy-smoothed values
-    auto step = [&](auto phase, const int zp) {
-        constexpr int P = decltype(phase)::value;
+    int phase = 0;  // (zp - zp_first) % TAPS: the ring slot that receives this slice's xy-smoothed values
+    for (int zp = zp_first; zp <= zp_last; ++zp) {
         const int buf = (zp - zp_first) & 1;
         cp_async_wait_all();
         __syncthreads();  // s_in[buf] complete; everyone is done with s_x and s_in[buf^1] of the previous step
         if (zp + 1 <= zp_last) stage(zp + 1, buf ^ 1);
         cp_async_commit();
 
+        GV acc[OY][NG];  // this slice's xy-smoothed values of the owned outputs (zero for a slice outside the grid)
         const bool slice_in = (zp >= 0 && zp < g.S);
         if (slice_in) {
             const T *sb = s_in + buf * PH * PW;
@@ -296,19 +387,57 @@ __global__ void __launch_bounds__(NT, MINB)
                     for (int i = 0; i < VW; ++i) a[m * VW + i] = t.v[i];
                 }
                 Vec o;
+                if constexpr (PACKED) {
+                    // Packed x pass.  Aligned register pairs A[m] = (a[2m], a[2m+1]).  Output pair p = (out[2p],
+                    // out[2p+1]) takes tap k from (a[off+2p+k], a[off+2p+k+1]), an aligned pair only when off+k is
+                    // even: those taps go to E[p].  The others are accumulated for the SHIFTED output pairs
+                    // O[q] = (out[2q-1], out[2q]), whose operands (a[off+2q-1+k], a[off+2q+k]) are aligned, and
+                    // out[2p] = E[p].lo + O[p].hi, out[2p+1] = E[p].hi + O[p+1].lo.  Unnormalised (see nxy).
+                    constexpr int off = HX - R, NP = VW * NV / 2;
+                    GV A[NP];
 #pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    T sum = DCMA_WX(0) * a[HX - R + i];
+                    for (int m = 0; m < NP; ++m) A[m] = LG::pack(a[2 * m], a[2 * m + 1]);
+                    GV E[VW / 2], O[VW / 2 + 1];
 #pragma unroll
-                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WX(k) * a[HX - R + i + k];
-                    o.v[i] = normalise<T, STRICT>(sum, nx[i]);
+                    for (int k = 0; k < TAPS; ++k) {
+                        if (((off + k) & 1) == 0) {
+#pragma unroll
+                            for (int pp = 0; pp < VW / 2; ++pp) {
+                                const int m = (off + k) / 2 + pp;
+                                E[pp] = (k == ((off & 1) ? 1 : 0)) ? LG::mul(A[m], DCMA_WX(k)) : LG::fma(E[pp], A[m], DCMA_WX(k));
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q <= VW / 2; ++q) {
+                                const int m = (off + k - 1) / 2 + q;  // pair (a[off+k-1+2q], a[off+k+2q])
+                                const GV Am = (m >= 0 && m < NP) ? A[m] : LG::zero();
+                                O[q] = (k == ((off & 1) ? 0 : 1)) ? LG::mul(Am, DCMA_WX(k)) : LG::fma(O[q], Am, DCMA_WX(k));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < VW / 2; ++pp) {
+                        float e_lo, e_hi, o_lo, o_hi, o2_lo, o2_hi;
+                        LG::unpack(E[pp], e_lo, e_hi);
+                        LG::unpack(O[pp], o_lo, o_hi);
+                        LG::unpack(O[pp + 1], o2_lo, o2_hi);
+                        o.v[2 * pp] = e_lo + o_hi;
+                        o.v[2 * pp + 1] = e_hi + o2_lo;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VW; ++i) {
+                        T sum = DCMA_WX(0) * a[HX - R + i];
+#pragma unroll
+                        for (int k = 1; k < TAPS; ++k) sum += DCMA_WX(k) * a[HX - R + i + k];
+                        o.v[i] = normalise<T, STRICT>(sum, nx[i]);
+                    }
                 }
                 *reinterpret_cast<Vec *>(s_x + row * TX + qx * VW) = o;
             }
             __syncthreads();
-            // ---- y pass: s_x -> ring slot P.  Rows are streamed once; output j takes row m as its tap k = m - j
+            // ---- y pass: s_x -> acc.  Rows are streamed once; output j takes row m as its tap k = m - j
             // (ascending k: the reference's order); OY adjacent rows share their taps.
-            T acc[OY][VW];
 #pragma unroll
             for (int m = 0; m < OY + 2 * R; ++m) {
                 const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
@@ -317,27 +446,41 @@ __global__ void __launch_bounds__(NT, MINB)
                     const int k = m - j;
                     if (k < 0 || k >= TAPS) continue;
 #pragma unroll
-                    for (int i = 0; i < VW; ++i) {
+                    for (int i = 0; i < NG; ++i) {
                         if (k == 0)
-                            acc[j][i] = DCMA_WY(0) * t.v[i];
+                            acc[j][i] = LG::mul(LG::get(t, i), DCMA_WY(0));
                         else
-                            acc[j][i] += DCMA_WY(k) * t.v[i];
+                            acc[j][i] = LG::fma(acc[j][i], LG::get(t, i), DCMA_WY(k));
                     }
                 }
             }
 #pragma unroll
             for (int j = 0; j < OY; ++j)
 #pragma unroll
-                for (int i = 0; i < VW; ++i) win[j][i][P] = normalise<T, STRICT>(acc[j][i], ny[j]);
+                for (int i = 0; i < NG; ++i) {
+                    if constexpr (STRICT)
+                        acc[j][i] = acc[j][i] / ny[j];  // STRICT => LG::V == T
+                    else if constexpr (PACKED)
+                        acc[j][i] = LG::mul2(acc[j][i], nxy[j][i]);
+                    else
+                        acc[j][i] = LG::mul(acc[j][i], ny[j]);
+                }
         } else {
 #pragma unroll
             for (int j = 0; j < OY; ++j)
 #pragma unroll
-                for (int i = 0; i < VW; ++i) win[j][i][P] = T(0);
+                for (int i = 0; i < NG; ++i) acc[j][i] = LG::zero();
         }
-        // ---- z pass from the register ring: tap k (oldest first) lives in slot (P + 1 + k) % TAPS
+
+        // ---- ring insert + z pass from the register ring: tap k (oldest first) lives in slot (P + 1 + k) % TAPS
         const int zo = zp - R;  // output slice completed by this step
-        if (zo >= z_begin) {    // zo < z_end holds by construction of zp_last
+        auto ring = [&](auto ph) {
+            constexpr int P = decltype(ph)::value;
+#pragma unroll
+            for (int j = 0; j < OY; ++j)
+#pragma unroll
+                for (int i = 0; i < NG; ++i) win[j][i][P] = acc[j][i];
+            if (zo < z_begin) return;  // warm-up slices of this chunk; zo < z_end holds by construction of zp_last
             const T nz = tab_z[zo];
 #pragma unroll
             for (int j = 0; j < OY; ++j) {
@@ -345,13 +488,20 @@ __global__ void __launch_bounds__(NT, MINB)
                 Vec o;
                 bool bad = false;
 #pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    T sum = DCMA_WZ(0) * win[j][i][(P + 1) % TAPS];
+                for (int i = 0; i < NG; ++i) {
+                    GV sum = LG::mul(win[j][i][(P + 1) % TAPS], DCMA_WZ(0));
 #pragma unroll
-                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WZ(k) * win[j][i][(P + 1 + k) % TAPS];
-                    o.v[i] = normalise<T, STRICT>(sum, nz);
-                    bad = bad || !isfinite(o.v[i]);
+                    for (int k = 1; k < TAPS; ++k) sum = LG::fma(sum, win[j][i][(P + 1 + k) % TAPS], DCMA_WZ(k));
+                    if constexpr (STRICT)
+                        LG::put(o, i, sum / nz);
+                    else
+                        LG::put(o, i, LG::mul(sum, nz));
                 }
+                // one finite test per vector: x*0 is 0 for finite x and NaN otherwise
+                T chk = o.v[0] * T(0);
+#pragma unroll
+                for (int i = 1; i < VW; ++i) chk += o.v[i] * T(0);
+                bad = !(chk == T(0));
                 if (bad) {
                     // a non-finite result <=> a non-finite tap somewhere in the (2r+1)^3 support: redo it literally
 #pragma unroll
@@ -370,10 +520,10 @@ __global__ void __launch_bounds__(NT, MINB)
                     }
                 }
             }
-        }
-    };
-
-    for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
+        };
+        dispatch_phase<TAPS>(phase, ring);
+        phase = (phase + 1 == TAPS) ? 0 : phase + 1;
+    }
 }
 
 #undef DCMA_WX
