@@ -751,23 +751,28 @@ __global__ void __launch_bounds__(kTileX *kTileY)
 // ------------------------------------------------------------------------------------------------------------------
 // boundary conversions: reference AoS double [z][y][x][3]  <->  device SoA T [3][z][y][x]
 // ------------------------------------------------------------------------------------------------------------------
+// voxels [v0, v1) of the SoA field <-> a dense AoS chunk of (v1 - v0) * 3 doubles
 template <typename T>
-__global__ void __launch_bounds__(256) k_export_aos(const T *__restrict__ soa, double *__restrict__ aos, const long long N) {
+__global__ void __launch_bounds__(256) k_export_aos(const T *__restrict__ soa, double *__restrict__ aos, const long long N,
+                                                     const long long v0, const long long v1) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * N; i += stride) {
+    const long long n = 3 * (v1 - v0);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const long long v = i / 3;
         const int c = static_cast<int>(i - v * 3);
-        aos[i] = static_cast<double>(soa[v + c * N]);  // coalesced write, 3-way strided (cached) read
+        aos[i] = static_cast<double>(soa[v0 + v + c * N]);  // coalesced write, 3-way strided (cached) read
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_import_aos(const double *__restrict__ aos, T *__restrict__ soa, const long long N) {
+__global__ void __launch_bounds__(256) k_import_aos(const double *__restrict__ aos, T *__restrict__ soa, const long long N,
+                                                     const long long v0, const long long v1) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * N; i += stride) {
+    const long long n = 3 * (v1 - v0);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const long long v = i / 3;
         const int c = static_cast<int>(i - v * 3);
-        soa[v + c * N] = static_cast<T>(aos[i]);
+        soa[v0 + v + c * N] = static_cast<T>(aos[i]);
     }
 }
 

@@ -52,7 +52,7 @@ void warp_image_host(const dcma_b200_geom &geom, const float *image, const doubl
         const int zlen = 16;
         const dim3 grid(ntx, nty, (g.S + zlen - 1) / zlen);
         const int grid_lin = static_cast<int>(std::min<long long>((3 * N + 255) / 256, 148LL * 16));
-        k_import_aos<double><<<grid_lin, 256>>>(dA, dS, N);
+        k_import_aos<double><<<grid_lin, 256>>>(dA, dS, N, 0, N);
         if (g.CH == 1)
             k_warp<double, true, long long, true><<<grid, dim3(kTileX, kTileY)>>>(dM, dS, dW, g, zlen, use_oob ? 1 : 0, oob_value);
         else

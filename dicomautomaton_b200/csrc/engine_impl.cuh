@@ -119,6 +119,9 @@ class Engine final : public EngineBase {
         cudaStreamSynchronize(stream_);
         for (void *p : allocs_) cudaFree(p);
         if (h_ctrl_) cudaFreeHost(h_ctrl_);
+        for (cudaEvent_t e : ev_stage_)
+            if (e) cudaEventDestroy(e);
+        if (copy_stream_) cudaStreamDestroy(copy_stream_);
         if (own_stream_) cudaStreamDestroy(stream_);
     }
 
@@ -272,16 +275,9 @@ class Engine final : public EngineBase {
                 break;
             }
             case DCMA_B200_BUF_UPDATE:
-            case DCMA_B200_BUF_DEFORMATION: {
-                double *tmp = nullptr;
-                DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
-                k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, tmp, N);
-                DCMA_CUDA(cudaGetLastError());
-                DCMA_CUDA(cudaMemcpyAsync(host, tmp, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream_));
-                DCMA_CUDA(cudaStreamSynchronize(stream_));
-                cudaFree(tmp);
+            case DCMA_B200_BUF_DEFORMATION:
+                export_field_host(buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, static_cast<double *>(host));
                 break;
-            }
             default: throw std::invalid_argument("unknown buffer id");
         }
         DCMA_CUDA(cudaStreamSynchronize(stream_));
@@ -302,16 +298,9 @@ class Engine final : public EngineBase {
                 w_src_ = 2;
                 break;
             case DCMA_B200_BUF_UPDATE:
-            case DCMA_B200_BUF_DEFORMATION: {
-                double *tmp = nullptr;
-                DCMA_CUDA(cudaMalloc(&tmp, sizeof(double) * 3 * N));
-                DCMA_CUDA(cudaMemcpyAsync(tmp, host, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, stream_));
-                k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(tmp, buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, N);
-                DCMA_CUDA(cudaGetLastError());
-                DCMA_CUDA(cudaStreamSynchronize(stream_));
-                cudaFree(tmp);
+            case DCMA_B200_BUF_DEFORMATION:
+                import_field_host(static_cast<const double *>(host), buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_);
                 break;
-            }
             default: throw std::invalid_argument("buffer is not writable");
         }
         DCMA_CUDA(cudaStreamSynchronize(stream_));
@@ -319,8 +308,53 @@ class Engine final : public EngineBase {
 
     void export_deformation_device(double *device_out) override {
         DCMA_CUDA(cudaSetDevice(dev_));
-        k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(dD_, device_out, g_.N);
+        k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(dD_, device_out, g_.N, 0, g_.N);
         DCMA_CUDA(cudaGetLastError());
+    }
+
+    // export_deformation_volume (cc:110-113): SoA T -> the reference's AoS double layout, converted chunk by chunk
+    // through two small staging buffers so that no field-sized allocation is made and the conversion of chunk i+1
+    // overlaps the PCIe copy of chunk i (the copy engine and the SMs work on different staging halves).
+    static constexpr long long kStageVoxels = 1LL << 21;  // 2 Mi voxels = 48 MiB of AoS doubles per half
+    double *staging(int half) {
+        if (!d_stage_[half]) d_stage_[half] = alloc<double>(3 * kStageVoxels);
+        return d_stage_[half];
+    }
+    void export_field_host(const T *field, double *host) {
+        if (!ev_stage_[0]) {
+            DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[0], cudaEventDisableTiming));
+            DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[1], cudaEventDisableTiming));
+            DCMA_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        }
+        cudaEvent_t done;
+        DCMA_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        int k = 0;
+        for (long long v0 = 0; v0 < g_.N; v0 += kStageVoxels, ++k) {
+            const long long v1 = std::min(g_.N, v0 + kStageVoxels);
+            const int half = k & 1;
+            double *st = staging(half);
+            // the kernel may overwrite this half only after the copy that last read it has finished
+            DCMA_CUDA(cudaStreamWaitEvent(stream_, ev_stage_[half], 0));
+            k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(field, st, g_.N, v0, v1);
+            DCMA_CUDA(cudaGetLastError());
+            DCMA_CUDA(cudaEventRecord(done, stream_));
+            DCMA_CUDA(cudaStreamWaitEvent(copy_stream_, done, 0));
+            DCMA_CUDA(cudaMemcpyAsync(host + 3 * v0, st, sizeof(double) * 3 * (v1 - v0), cudaMemcpyDeviceToHost, copy_stream_));
+            DCMA_CUDA(cudaEventRecord(ev_stage_[half], copy_stream_));
+        }
+        DCMA_CUDA(cudaStreamSynchronize(copy_stream_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+        cudaEventDestroy(done);
+    }
+    void import_field_host(const double *host, T *field) {
+        for (long long v0 = 0; v0 < g_.N; v0 += kStageVoxels) {
+            const long long v1 = std::min(g_.N, v0 + kStageVoxels);
+            double *st = staging(0);
+            DCMA_CUDA(cudaMemcpyAsync(st, host + 3 * v0, sizeof(double) * 3 * (v1 - v0), cudaMemcpyHostToDevice, stream_));
+            k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(st, field, g_.N, v0, v1);
+            DCMA_CUDA(cudaGetLastError());
+        }
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
     }
 
   private:
@@ -616,9 +650,9 @@ class Engine final : public EngineBase {
         // 128-thread CTAs, 2 adjacent output rows x one 16-byte vector per thread; the register z window (72 regs)
         // puts the kernel at ~165 registers, so 3 CTAs/SM.  float: 64x16 tile; double: 32x16 tile.
         constexpr int TX = (sizeof(T) == 4) ? 64 : 32;
-        constexpr int TY = 16;
-        constexpr int NT = 128;
-        constexpr int MINB = 3;
+        constexpr int TY = DCMA_SMOOTH_TY;
+        constexpr int NT = DCMA_SMOOTH_NT;
+        constexpr int MINB = DCMA_SMOOTH_MINB;
         const bool vec = (g_.C % static_cast<int>(16 / sizeof(T)) == 0);
         if (vec)
             launch_smooth3d_cfg<R, TX, TY, NT, MINB, true>(in, out, pl, it);
@@ -653,6 +687,9 @@ class Engine final : public EngineBase {
     double *d_part_sum_ = nullptr;
     long long *d_part_cnt_ = nullptr;
     Ctrl *d_ctrl_ = nullptr, *h_ctrl_ = nullptr;
+    double *d_stage_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream_ = nullptr;
     SmoothPlan<T> plan_u_, plan_d_;
     std::map<double, SmoothPlan<T>> extra_plans_;
     int w_src_ = 0;

@@ -29,6 +29,23 @@ using namespace ::dcma;
 
 constexpr int kMaxFastRadius = 6;
 
+// Tuning knobs of the fused kernel (tools/build_variant.py overrides them for experiments).
+#ifndef DCMA_SMOOTH_NT
+#define DCMA_SMOOTH_NT 128
+#endif
+#ifndef DCMA_SMOOTH_TY
+#define DCMA_SMOOTH_TY 16
+#endif
+#ifndef DCMA_SMOOTH_MINB
+#define DCMA_SMOOTH_MINB 3
+#endif
+#ifndef DCMA_SMOOTH_XPRELOAD
+#define DCMA_SMOOTH_XPRELOAD 0
+#endif
+#ifndef DCMA_SMOOTH_PF
+#define DCMA_SMOOTH_PF 0  // slices ahead of the cp.async stage that are requested into L2 (0 = off)
+#endif
+
 // Per-launch constants of one smoothing call (kernel parameter space => uniform/constant-bank reads).
 template <typename T>
 struct SmoothWeights {
@@ -223,6 +240,17 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
     return (zw > T(0)) ? (zs / zw) : z_centre;
 }
 
+// calls f(integral_constant<P>, zb + P) for P = 0..N-1 while zb + P <= last (compile-time ring phases)
+template <int N, int P, typename F>
+__device__ __forceinline__ void unroll_phases(F &f, const int zb, const int last) {
+    if constexpr (P < N) {
+        if (zb + P <= last) {
+            f(std::integral_constant<int, P>{}, zb + P);
+            unroll_phases<N, P + 1>(f, zb, last);
+        }
+    }
+}
+
 // calls f(integral_constant<P>{}) for the run-time ring phase `phase` in [0, N): one uniform jump per slice, so that the
 // slice step's common code (staging, x and y passes) exists once and only the ring insert + z pass are per phase.
 template <int N, typename F>
@@ -297,7 +325,8 @@ __global__ void __launch_bounds__(NT, MINB)
 #define DCMA_WZ(k) wzh[((k) <= R) ? (k) : (2 * R - (k))]
 
     // ---- per-thread staging plan, fixed across slices: source offset inside a slice (-1: outside the grid -> zeros)
-    int cp_src[NCP], cp_dst[NCP];
+    // (16-byte chunk e = tid + n*NT of the staged tile lands at element offset e*VW, because PW == CPR*VW)
+    int cp_src[NCP];
     if (VEC) {
 #pragma unroll
         for (int n = 0; n < NCP; ++n) {
@@ -305,10 +334,19 @@ __global__ void __launch_bounds__(NT, MINB)
             const int row = e / CPR, cc = e - row * CPR;
             const int gy = y0 - R + row, gx = x0 - HX + cc * VW;
             const bool ok = (gy >= 0) && (gy < g.R) && (gx >= 0) && (gx + VW <= g.C);
-            cp_dst[n] = (e < PH * CPR) ? (row * PW + cc * VW) : -1;
             cp_src[n] = ok ? (gy * g.C + gx) : -1;
         }
     }
+    static_assert(PW == CPR * VW, "staged row width must be a whole number of 16-byte chunks");
+    auto l2_prefetch = [&](int zp) {  // one request per 128-byte line of the slice tile
+        if (DCMA_SMOOTH_PF <= 0 || !VEC || zp < 0 || zp >= g.S) return;
+        const T *sp = src + zp * plane;
+#pragma unroll
+        for (int n = 0; n < NCP; ++n) {
+            if (cp_src[n] >= 0 && ((cp_src[n] * static_cast<int>(sizeof(T))) & 127) == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + cp_src[n]));
+        }
+    };
     auto stage = [&](int zp, int buf) {
         if (zp < 0 || zp >= g.S) return;  // slice outside the grid: contributes zeros, nothing to load
         T *sb = s_in + buf * PH * PW;
@@ -316,7 +354,9 @@ __global__ void __launch_bounds__(NT, MINB)
         if (VEC) {
 #pragma unroll
             for (int n = 0; n < NCP; ++n) {
-                if (cp_dst[n] >= 0) cp_async_16(sb + cp_dst[n], (cp_src[n] >= 0) ? (sp + cp_src[n]) : src, (cp_src[n] >= 0) ? 16 : 0);
+                const int e = tid + n * NT;
+                if ((n + 1) * NT <= PH * CPR || e < PH * CPR)
+                    cp_async_16(sb + e * VW, (cp_src[n] >= 0) ? (sp + cp_src[n]) : src, (cp_src[n] >= 0) ? 16 : 0);
             }
         } else {
             for (int e = tid; e < PH * PW; e += NT) {
@@ -362,19 +402,36 @@ __global__ void __launch_bounds__(NT, MINB)
     stage(zp_first, 0);
     cp_async_commit();
 
-    int phase = 0;  // (zp - zp_first) % TAPS: the ring slot that receives this slice's xy-smoothed values
-    for (int zp = zp_first; zp <= zp_last; ++zp) {
+    // One slice step = xstep(zp) [staging + x pass, phase independent] followed by ring(P) [y pass into ring slot
+    // P = (zp - zp_first) % TAPS, then the z pass].
+    bool slice_in = false;
+    int zo = 0;  // output slice completed by the current step
+    auto xstep = [&](const int zp) {
         const int buf = (zp - zp_first) & 1;
         cp_async_wait_all();
         __syncthreads();  // s_in[buf] complete; everyone is done with s_x and s_in[buf^1] of the previous step
         if (zp + 1 <= zp_last) stage(zp + 1, buf ^ 1);
         cp_async_commit();
+        if (zp + 1 + DCMA_SMOOTH_PF <= zp_last) l2_prefetch(zp + 1 + DCMA_SMOOTH_PF);
 
-        GV acc[OY][NG];  // this slice's xy-smoothed values of the owned outputs (zero for a slice outside the grid)
-        const bool slice_in = (zp >= 0 && zp < g.S);
+        slice_in = (zp >= 0 && zp < g.S);
+        zo = zp - R;
         if (slice_in) {
             const T *sb = s_in + buf * PH * PW;
             // ---- x pass: s_in -> s_x.  Task = one vector of VW outputs; q == qx for every task of this thread.
+            // fp32: the operands of ALL x tasks are requested before the first task computes (the three shared-memory
+            // latencies overlap instead of adding up; fp64 has no registers to spare for that)
+            constexpr bool PRELOAD = PACKED && (DCMA_SMOOTH_XPRELOAD != 0);
+            Vec pre[PRELOAD ? XN : 1][PRELOAD ? NV : 1];
+            if constexpr (PRELOAD) {
+#pragma unroll
+                for (int n = 0; n < XN; ++n) {
+                    const int row = ry + n * (NT / QX);
+                    if ((XT % NT != 0) && row >= PH) break;
+#pragma unroll
+                    for (int m = 0; m < NV; ++m) pre[n][m] = *reinterpret_cast<const Vec *>(sb + row * PW + (qx + m) * VW);
+                }
+            }
 #pragma unroll
             for (int n = 0; n < XN; ++n) {
                 const int row = ry + n * (NT / QX);
@@ -382,7 +439,11 @@ __global__ void __launch_bounds__(NT, MINB)
                 T a[VW * NV];
 #pragma unroll
                 for (int m = 0; m < NV; ++m) {
-                    const Vec t = *reinterpret_cast<const Vec *>(sb + row * PW + (qx + m) * VW);
+                    Vec t;
+                    if constexpr (PRELOAD)
+                        t = pre[n][m];
+                    else
+                        t = *reinterpret_cast<const Vec *>(sb + row * PW + (qx + m) * VW);
 #pragma unroll
                     for (int i = 0; i < VW; ++i) a[m * VW + i] = t.v[i];
                 }
@@ -436,66 +497,78 @@ __global__ void __launch_bounds__(NT, MINB)
                 *reinterpret_cast<Vec *>(s_x + row * TX + qx * VW) = o;
             }
             __syncthreads();
-            // ---- y pass: s_x -> acc.  Rows are streamed once; output j takes row m as its tap k = m - j
-            // (ascending k: the reference's order); OY adjacent rows share their taps.
+        }
+    };
+
+    // ---- per ring phase P (compile-time ring indices): y pass straight into ring slot P, then the z pass.
+    // Tap k of the z pass (oldest first) lives in slot (P + 1 + k) % TAPS.
+    auto ring = [&](auto ph) {
+        {
+            constexpr int P = decltype(ph)::value;
+            if (slice_in) {
+                // y pass: s_x -> win[..][P].  Rows are streamed once; output j takes row m as its tap k = m - j
+                // (ascending k: the reference's order); OY adjacent rows share their taps.
 #pragma unroll
-            for (int m = 0; m < OY + 2 * R; ++m) {
-                const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
+                for (int m = 0; m < OY + 2 * R; ++m) {
+                    const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
 #pragma unroll
-                for (int j = 0; j < OY; ++j) {
-                    const int k = m - j;
-                    if (k < 0 || k >= TAPS) continue;
+                    for (int j = 0; j < OY; ++j) {
+                        const int k = m - j;
+                        if (k < 0 || k >= TAPS) continue;
 #pragma unroll
-                    for (int i = 0; i < NG; ++i) {
-                        if (k == 0)
-                            acc[j][i] = LG::mul(LG::get(t, i), DCMA_WY(0));
-                        else
-                            acc[j][i] = LG::fma(acc[j][i], LG::get(t, i), DCMA_WY(k));
+                        for (int i = 0; i < NG; ++i) {
+                            if (k == 0)
+                                win[j][i][P] = LG::mul(LG::get(t, i), DCMA_WY(0));
+                            else
+                                win[j][i][P] = LG::fma(win[j][i][P], LG::get(t, i), DCMA_WY(k));
+                        }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < OY; ++j)
+#pragma unroll
+                    for (int i = 0; i < NG; ++i) {
+                        if constexpr (STRICT)
+                            win[j][i][P] = win[j][i][P] / ny[j];  // STRICT => LG::V == T
+                        else if constexpr (PACKED)
+                            win[j][i][P] = LG::mul2(win[j][i][P], nxy[j][i]);
+                        else
+                            win[j][i][P] = LG::mul(win[j][i][P], ny[j]);
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < OY; ++j)
+#pragma unroll
+                    for (int i = 0; i < NG; ++i) win[j][i][P] = LG::zero();
             }
-#pragma unroll
-            for (int j = 0; j < OY; ++j)
-#pragma unroll
-                for (int i = 0; i < NG; ++i) {
-                    if constexpr (STRICT)
-                        acc[j][i] = acc[j][i] / ny[j];  // STRICT => LG::V == T
-                    else if constexpr (PACKED)
-                        acc[j][i] = LG::mul2(acc[j][i], nxy[j][i]);
-                    else
-                        acc[j][i] = LG::mul(acc[j][i], ny[j]);
-                }
-        } else {
-#pragma unroll
-            for (int j = 0; j < OY; ++j)
-#pragma unroll
-                for (int i = 0; i < NG; ++i) acc[j][i] = LG::zero();
-        }
-
-        // ---- ring insert + z pass from the register ring: tap k (oldest first) lives in slot (P + 1 + k) % TAPS
-        const int zo = zp - R;  // output slice completed by this step
-        auto ring = [&](auto ph) {
-            constexpr int P = decltype(ph)::value;
-#pragma unroll
-            for (int j = 0; j < OY; ++j)
-#pragma unroll
-                for (int i = 0; i < NG; ++i) win[j][i][P] = acc[j][i];
             if (zo < z_begin) return;  // warm-up slices of this chunk; zo < z_end holds by construction of zp_last
             const T nz = tab_z[zo];
+            // JB rows advance together, tap-major: independent FMA chains back to back (fp32: all rows; fp64 keeps
+            // one row at a time, its register file has no room for more accumulators)
+            constexpr int JB = PACKED ? OY : 1;
 #pragma unroll
-            for (int j = 0; j < OY; ++j) {
+            for (int jb = 0; jb < OY; jb += JB) {
+                GV zs[JB][NG];
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+                    for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+                        for (int i = 0; i < NG; ++i)
+                            zs[jj][i] = (k == 0) ? LG::mul(win[jb + jj][i][(P + 1) % TAPS], DCMA_WZ(0))
+                                                 : LG::fma(zs[jj][i], win[jb + jj][i][(P + 1 + k) % TAPS], DCMA_WZ(k));
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                const int j = jb + jj;
                 const int gy = y0 + yl0 + j;
                 Vec o;
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < NG; ++i) {
-                    GV sum = LG::mul(win[j][i][(P + 1) % TAPS], DCMA_WZ(0));
-#pragma unroll
-                    for (int k = 1; k < TAPS; ++k) sum = LG::fma(sum, win[j][i][(P + 1 + k) % TAPS], DCMA_WZ(k));
                     if constexpr (STRICT)
-                        LG::put(o, i, sum / nz);
+                        LG::put(o, i, zs[jj][i] / nz);
                     else
-                        LG::put(o, i, LG::mul(sum, nz));
+                        LG::put(o, i, LG::mul(zs[jj][i], nz));
                 }
                 // one finite test per vector: x*0 is 0 for finite x and NaN otherwise
                 T chk = o.v[0] * T(0);
@@ -519,10 +592,27 @@ __global__ void __launch_bounds__(NT, MINB)
                             if (gx_out + i < g.C) p[i] = o.v[i];
                     }
                 }
+                }
             }
+        }
+    };
+
+    if constexpr (PACKED) {
+        // fp32: one copy of the step; a uniform jump per slice selects the ring phase (small code, fits the I-cache)
+        int phase = 0;
+        for (int zp = zp_first; zp <= zp_last; ++zp) {
+            xstep(zp);
+            dispatch_phase<TAPS>(phase, ring);
+            phase = (phase + 1 == TAPS) ? 0 : phase + 1;
+        }
+    } else {
+        // fp64: the whole step is unrolled per ring phase (measured 10-25 % faster than the dispatch form here: the
+        // scheduler interleaves the x pass of a step with the ring arithmetic around it)
+        auto step = [&](auto ph, const int zp) {
+            xstep(zp);
+            ring(ph);
         };
-        dispatch_phase<TAPS>(phase, ring);
-        phase = (phase + 1 == TAPS) ? 0 : phase + 1;
+        for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
     }
 }
 
