@@ -428,19 +428,30 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             }
             float f_prev = __ldg(F + (z_begin > 0 ? v - plane : v) * ch);
             float f_cur = __ldg(F + v * ch);
-            const IX pf = plane * kPrefetchAhead;
+            // L2 prefetch, one instruction per warp and step: a tile row is one warp, and lane l asks for ONE line of
+            // the row kPrefetchAhead slices ahead -- lane 0: F, lane 1: M (or W), lanes 2..: the lines of D's components.
+            constexpr int NL = (sizeof(T) * kTileX + 127) / 128;  // 128-byte lines per field row segment
+            const char *pf_ptr = nullptr;
+            long long pf_step = 0;
+            {
+                const int lane = threadIdx.x;
+                const long long row = (static_cast<long long>(z_begin) + kPrefetchAhead) * plane +
+                                      static_cast<long long>(y) * g.C + blockIdx.x * kTileX;
+                if (lane < 2) {
+                    const float *base = (lane == 0) ? F : ((w_src == 2) ? Wbuf : M);
+                    pf_ptr = reinterpret_cast<const char *>(base + row * ch);
+                    pf_step = static_cast<long long>(plane) * ch * static_cast<long long>(sizeof(float));
+                } else if (w_src == 1 && lane < 2 + 3 * NL) {
+                    const int c = (lane - 2) / NL, h = (lane - 2) - c * NL;
+                    pf_ptr = reinterpret_cast<const char *>(D + c * g.N + row) + h * 128;
+                    pf_step = static_cast<long long>(plane) * static_cast<long long>(sizeof(T));
+                }
+            }
             for (int z = z_begin; z < z_end; ++z, v += plane, zd += CT(1)) {
                 const float *Fv = F + v * ch;
-                if (kPrefetchAhead > 0 && z + kPrefetchAhead < g.S) {
-                    prefetch_line(Fv + pf * ch);
-                    if (w_src == 1) {
-                        prefetch_line(M + (v + pf) * ch);
-                        prefetch_line(D + v + pf);
-                        prefetch_line(D1 + v + pf);
-                        prefetch_line(D2 + v + pf);
-                    } else {
-                        prefetch_line((w_src == 0 ? M : Wbuf) + (v + pf) * ch);
-                    }
+                if (kPrefetchAhead > 0) {
+                    if (pf_ptr != nullptr && z + kPrefetchAhead < g.S) prefetch_line(pf_ptr);
+                    pf_ptr += pf_step;
                 }
                 Stencil st;
                 load_stencil_xy<IX>(st, Fv, gk);
@@ -656,15 +667,25 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         for (int c = 0; c < 3; ++c) d[c] = D[v0 + c * N];
     }
     const CT pxl[3] = {ak.px, ak.py, ak.pz};
+    // L2 prefetch, one instruction per warp and step (see k_warp_force): lanes 0..3*NL-1 own the lines of U's three
+    // components, the next 3*NL lanes those of D's, kPrefetchAhead slices ahead of the slice being composed.
+    constexpr int NL = (sizeof(T) * kTileX + 127) / 128;
+    const char *pf_ptr = nullptr;
+    const long long pf_step = (threadIdx.x < 6 * NL) ? static_cast<long long>(plane) * static_cast<long long>(sizeof(T)) : 0;
+    {
+        const int lane = threadIdx.x;
+        const long long row = (static_cast<long long>(z_begin) + kPrefetchAhead) * plane +
+                              static_cast<long long>(y) * g.C + blockIdx.x * kTileX;
+        if (lane < 6 * NL) {
+            const int a = lane / (3 * NL), r = lane - a * 3 * NL, c = r / NL, h = r - c * NL;
+            pf_ptr = reinterpret_cast<const char *>((a == 0 ? U : D) + c * N + row) + h * 128;
+        }
+    }
     for (int z = z_begin; z < z_end; ++z, zd += CT(1)) {
         const IX v = static_cast<IX>(z) * plane + vxy;
-        if (kPrefetchAhead > 0 && z + kPrefetchAhead < g.S) {
-            const IX vp = v + plane * kPrefetchAhead;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                prefetch_line(U + c * N + vp);
-                prefetch_line(D + c * N + vp);
-            }
+        if (kPrefetchAhead > 0) {
+            if (pf_ptr != nullptr && z + kPrefetchAhead < g.S) prefetch_line(pf_ptr);
+            pf_ptr += pf_step;
         }
         const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
         const CT tx = t.tx, ty = t.ty, tz = t.tz;
