@@ -39,6 +39,8 @@ struct Ctrl {
     long long iters_done;    // compute_single_iteration equivalents executed since load
     long long converged_at;  // loop iteration index at which the stop rule fired, LLONG_MAX otherwise
     double threshold;        // convergence_threshold
+    unsigned int ticket;     // blocks of the running force kernel that have published their MSE partial
+    unsigned int pad_;
 };
 
 constexpr long long kNotConverged = 0x7fffffffffffffffLL;

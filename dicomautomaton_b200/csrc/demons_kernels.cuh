@@ -390,12 +390,16 @@ __device__ __forceinline__ void demons_force(float fixed_val, float moving_val, 
 // gradient is recomputed from F (7-point stencil served by L1/L2) instead of being read back as 3 field components.
 // MSE terms: per-thread sum -> warp shuffle -> block -> one (sum, count) partial per block (deterministic).
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reduce_final_block(const int tid, const double *part_sum, const long long *part_cnt,
+                                                   const int nparts, Ctrl *ctrl, double *mse_hist, const long long it,
+                                                   const long long hist_idx, const int count_iter);
+
 template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
                  const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
-                 const ForceK fk, double *__restrict__ part_sum, long long *__restrict__ part_cnt, const Ctrl *__restrict__ ctrl,
-                 const long long it) {
+                 const ForceK fk, double *part_sum, long long *part_cnt, Ctrl *ctrl, const long long it,
+                 const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter) {
     using CT = T;  // compute type of coordinates / interpolation / force == field storage type
     if (it > ctrl->converged_at) return;
     CT acc = 0;
@@ -514,34 +518,51 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         part_sum[b] = aa;
         part_cnt[b] = c;
     }
+    // Fused final reduction: the LAST block to publish its partial reduces all of them (in the fixed order of
+    // k_reduce_final, so the result does not depend on which block that is) and applies the stop rule.
+    if (fused_reduce) {
+        __shared__ int s_last;
+        const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            __threadfence();
+            const unsigned t = atomicAdd(&ctrl->ticket, 1u);
+            s_last = (t == static_cast<unsigned>(nblocks - 1));
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x == 0 && threadIdx.y == 0) ctrl->ticket = 0;
+            reduce_final_block(threadIdx.y * kTileX + threadIdx.x, part_sum, part_cnt, nblocks, ctrl, mse_hist, it,
+                               hist_idx, count_iter);
+        }
+    }
 }
 
-// Final reduction + the loop's stop rule (cc:340-342 and cc:987-994), one block, fixed order => deterministic.
+// Final reduction + the loop's stop rule (cc:340-342 and cc:987-994) by ONE 256-thread block, fixed order =>
+// deterministic.  `tid` = linear thread index in the block.  Called by every thread of the block.
 //   count_iter != 0: this FORCE stage belongs to loop iteration `it` (iters_done, history and convergence updated)
-__global__ void __launch_bounds__(256)
-    k_reduce_final(const double *__restrict__ part_sum, const long long *__restrict__ part_cnt, const int nparts,
-                   Ctrl *__restrict__ ctrl, double *__restrict__ mse_hist, const long long it, const long long hist_idx,
-                   const int count_iter) {
-    if (it > ctrl->converged_at) return;
+__device__ __forceinline__ void reduce_final_block(const int tid, const double *part_sum, const long long *part_cnt,
+                                                   const int nparts, Ctrl *ctrl, double *mse_hist, const long long it,
+                                                   const long long hist_idx, const int count_iter) {
     __shared__ double s_acc[256];
     __shared__ long long s_cnt[256];
     double a = 0.0;
     long long c = 0;
-    for (int i = threadIdx.x; i < nparts; i += 256) {
+    for (int i = tid; i < nparts; i += 256) {
         a += part_sum[i];
         c += part_cnt[i];
     }
-    s_acc[threadIdx.x] = a;
-    s_cnt[threadIdx.x] = c;
+    s_acc[tid] = a;
+    s_cnt[tid] = c;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            s_acc[threadIdx.x] += s_acc[threadIdx.x + o];
-            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+        if (tid < o) {
+            s_acc[tid] += s_acc[tid + o];
+            s_cnt[tid] += s_cnt[tid + o];
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double mse = s_acc[0];
         const long long n = s_cnt[0];
         if (n > 0) mse /= static_cast<double>(n);
@@ -558,6 +579,15 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
+}
+
+// the same as its own launch (stage API, unfused mode)
+__global__ void __launch_bounds__(256)
+    k_reduce_final(const double *__restrict__ part_sum, const long long *__restrict__ part_cnt, const int nparts,
+                   Ctrl *__restrict__ ctrl, double *__restrict__ mse_hist, const long long it, const long long hist_idx,
+                   const int count_iter) {
+    if (it > ctrl->converged_at) return;
+    reduce_final_block(threadIdx.x, part_sum, part_cnt, nparts, ctrl, mse_hist, it, hist_idx, count_iter);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -388,6 +388,8 @@ class Engine final : public EngineBase {
         c.iters_done = 0;
         c.converged_at = kNotConverged;
         c.threshold = p_.convergence_threshold;
+        c.ticket = 0;
+        c.pad_ = 0;
         *h_ctrl_ = c;
         DCMA_CUDA(cudaMemcpyAsync(d_ctrl_, h_ctrl_, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
         DCMA_CUDA(cudaStreamSynchronize(stream_));  // h_ctrl_ is reused as the D2H landing buffer
@@ -471,7 +473,7 @@ class Engine final : public EngineBase {
         const bool diffeo = (p_.use_diffeomorphic != 0);
         if (p_.fused) {
             prof_begin(DCMA_B200_STAGE_FORCE);
-            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false);
+            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false, /*fused_reduce=*/true);
             prof_end();
         } else {
             if (w_src_ == 1) {
@@ -484,9 +486,11 @@ class Engine final : public EngineBase {
             launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false);
             prof_end();
         }
-        prof_begin(DCMA_B200_STAGE_REDUCE);
-        launch_reduce(it, d_hist, it, 1);
-        prof_end();
+        if (!p_.fused) {
+            prof_begin(DCMA_B200_STAGE_REDUCE);
+            launch_reduce(it, d_hist, it, 1);
+            prof_end();
+        }
         if (diffeo && plan_u_.active) {
             prof_begin(DCMA_B200_STAGE_SMOOTH_U);
             smooth(dU_, plan_u_, it);
@@ -509,7 +513,8 @@ class Engine final : public EngineBase {
         w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
     }
 
-    void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true) {
+    void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true,
+                      bool fused_reduce = false) {
         if (w_src == 2) ensure_warped_buffer();
         ForceK fk;
         fk.norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
@@ -519,7 +524,8 @@ class Engine final : public EngineBase {
         const dim3 blk(kTileX, kTileY);
 #define DCMA_LAUNCH_FORCE(IX, CH1)                                                                                   \
     k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
-                                                                  d_part_cnt_, d_ctrl_, it)
+                                                                  d_part_cnt_, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
+                                                                  hist_idx, count_iter)
         if (small_index_) {
             if (g_.CH == 1) DCMA_LAUNCH_FORCE(int, true); else DCMA_LAUNCH_FORCE(int, false);
         } else {
