@@ -35,7 +35,7 @@ class Params(C.Structure):
                 ("verbosity", C.c_int64),
                 ("field_mode", C.c_int32), ("device", C.c_int32), ("check_every", C.c_int32),
                 ("pyramid_levels", C.c_int32), ("use_symmetric_force", C.c_int32), ("fused", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("n_devices", C.c_int32), ("halo_planes", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class RunStats(C.Structure):
@@ -64,6 +64,18 @@ SYMBOLS = {
     "dcma_b200_engine_sync": (C.c_int, [_vp]),
     "dcma_b200_engine_device_bytes": (C.c_int64, [_vp]),
     "dcma_b200_warp_image": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, _cp, C.c_size_t]),
+    "dcma_b200_slab_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, _ip, _ip, _ip, _ip]),
+    "dcma_b200_slab_group_create_local": (C.c_int, [C.POINTER(_vp), C.POINTER(Geom), C.POINTER(Params),
+                                                    C.POINTER(C.c_int32), C.c_int32, C.c_int64, _cp, C.c_size_t]),
+    "dcma_b200_nccl_unique_id": (C.c_int, [_vp, _cp, C.c_size_t]),
+    "dcma_b200_slab_group_create_nccl": (C.c_int, [C.POINTER(_vp), C.POINTER(Geom), C.POINTER(Params), _vp, C.c_int32,
+                                                   C.c_int32, C.c_int32, C.c_int64, _cp, C.c_size_t]),
+    "dcma_b200_slab_group_destroy": (None, [_vp]),
+    "dcma_b200_slab_group_load": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "dcma_b200_slab_group_run": (C.c_int, [_vp, C.c_int64, _vp, C.POINTER(RunStats)]),
+    "dcma_b200_slab_group_range": (C.c_int, [_vp, _ip, _ip]),
+    "dcma_b200_slab_group_get_deformation": (C.c_int, [_vp, _vp]),
+    "dcma_b200_slab_group_halo_bytes": (C.c_int64, [_vp]),
 }
 
 _LIB = None

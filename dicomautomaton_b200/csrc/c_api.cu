@@ -8,14 +8,32 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "engine.h"
+#include "slab.h"
 
 struct dcma_b200_engine {
     dcma::EngineBase *impl;
     dcma_b200_geom geom;
 };
+struct dcma_b200_slab_group {
+    dcma::SlabGroup *impl;
+};
+
+namespace dcma {
+EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab) {
+    if (p.pyramid_levels > 1 || p.use_symmetric_force)
+        throw std::invalid_argument("pyramid_levels > 1 / use_symmetric_force are not available at the engine level");
+    switch (p.field_mode) {
+        case DCMA_B200_FIELD_FP64: return make_engine_f64(g, p, stream, slab);
+        case DCMA_B200_FIELD_FP64_STRICT: return make_engine_f64_strict(g, p, stream, slab);
+        case DCMA_B200_FIELD_FP32: return make_engine_f32(g, p, stream, slab);
+        default: throw std::invalid_argument("unknown field_mode");
+    }
+}
+}  // namespace dcma
 
 namespace {
 
@@ -54,14 +72,7 @@ int guarded(F &&f, char *errbuf = nullptr, size_t errbuf_len = 0) {
 }
 
 dcma::EngineBase *make(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream) {
-    if (p.pyramid_levels > 1 || p.use_symmetric_force)
-        throw std::invalid_argument("pyramid_levels > 1 / use_symmetric_force are not available at the engine level");
-    switch (p.field_mode) {
-        case DCMA_B200_FIELD_FP64: return dcma::make_engine_f64(g, p, stream);
-        case DCMA_B200_FIELD_FP64_STRICT: return dcma::make_engine_f64_strict(g, p, stream);
-        case DCMA_B200_FIELD_FP32: return dcma::make_engine_f32(g, p, stream);
-        default: throw std::invalid_argument("unknown field_mode");
-    }
+    return dcma::make_engine(g, p, stream, dcma::SlabSpec{});
 }
 
 }  // namespace
@@ -101,6 +112,8 @@ void dcma_b200_demons_params_default(dcma_b200_demons_params *p) {
     p->pyramid_levels = 1;
     p->use_symmetric_force = 0;
     p->fused = 1;
+    p->n_devices = 0;
+    p->halo_planes = 0;
 }
 
 int dcma_b200_engine_create(dcma_b200_engine **out, const dcma_b200_geom *geom, const dcma_b200_demons_params *params,
@@ -175,6 +188,29 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
                 dcma::EngineBase *p = nullptr;
                 ~Holder() { delete p; }
             } h;
+            if (params->n_devices > 1) {
+                // the volume is sharded into z-slabs over devices 0..n_devices-1 of this process
+                std::vector<int> dev(params->n_devices);
+                for (int i = 0; i < params->n_devices; ++i) dev[i] = i;
+                dcma::SlabGroup grp(*geom, *params, dev, params->halo_planes > 0 ? params->halo_planes : -1);
+                const auto s0 = clk::now();
+                grp.load(fixed, moving, false);
+                const auto s1 = clk::now();
+                dcma_b200_run_stats local;
+                grp.run(params->max_iterations, mse_history, &local);
+                const auto s2 = clk::now();
+                grp.get_deformation(deformation_out);
+                const auto s3 = clk::now();
+                if (stats) {
+                    *stats = local;
+                    const long long n = geom->slices * geom->rows * geom->cols;
+                    stats->h2d_ms = std::chrono::duration<double, std::milli>(s1 - s0).count();
+                    stats->d2h_ms = std::chrono::duration<double, std::milli>(s3 - s2).count();
+                    stats->h2d_bytes = (n + n * params->n_devices) * geom->channels * static_cast<long long>(sizeof(float));
+                    stats->d2h_bytes = 3 * n * static_cast<long long>(sizeof(double));
+                }
+                return;
+            }
             h.p = make(*geom, *params, nullptr);
             const auto t0 = clk::now();
             h.p->load(fixed, moving, false);
@@ -195,6 +231,76 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
         },
         errbuf, errbuf_len);
 }
+
+int dcma_b200_slab_partition(int64_t slices, int world, int rank, int64_t halo_planes, int64_t *zoff, int64_t *local,
+                             int64_t *own0, int64_t *own1) {
+    return guarded([&]() {
+        const dcma::SlabSpec s = dcma::slab_for_rank(slices, world, rank, halo_planes);
+        if (zoff) *zoff = s.zoff;
+        if (local) *local = s.local;
+        if (own0) *own0 = s.own0;
+        if (own1) *own1 = s.own1;
+    });
+}
+
+int dcma_b200_slab_group_create_local(dcma_b200_slab_group **out, const dcma_b200_geom *geom, const dcma_b200_demons_params *params,
+                                      const int32_t *devices, int32_t n_devices, int64_t halo_planes, char *errbuf,
+                                      size_t errbuf_len) {
+    if (!out || !geom || !params || !devices || n_devices < 1) return fail(DCMA_B200_EINVAL, "bad argument", errbuf, errbuf_len);
+    *out = nullptr;
+    return guarded(
+        [&]() {
+            std::vector<int> dev(devices, devices + n_devices);
+            *out = new dcma_b200_slab_group{new dcma::SlabGroup(*geom, *params, dev, halo_planes)};
+        },
+        errbuf, errbuf_len);
+}
+
+int dcma_b200_nccl_unique_id(unsigned char id[128], char *errbuf, size_t errbuf_len) {
+    if (!id) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded([&]() { dcma::nccl_unique_id(id); }, errbuf, errbuf_len);
+}
+
+int dcma_b200_slab_group_create_nccl(dcma_b200_slab_group **out, const dcma_b200_geom *geom, const dcma_b200_demons_params *params,
+                                     const unsigned char id[128], int32_t rank, int32_t world, int32_t device,
+                                     int64_t halo_planes, char *errbuf, size_t errbuf_len) {
+    if (!out || !geom || !params || !id) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    *out = nullptr;
+    return guarded(
+        [&]() { *out = new dcma_b200_slab_group{new dcma::SlabGroup(*geom, *params, id, rank, world, device, halo_planes)}; },
+        errbuf, errbuf_len);
+}
+
+void dcma_b200_slab_group_destroy(dcma_b200_slab_group *g) {
+    if (!g) return;
+    try {
+        delete g->impl;
+    } catch (...) {
+    }
+    delete g;
+}
+
+int dcma_b200_slab_group_load(dcma_b200_slab_group *g, const float *fixed, const float *moving, int on_device) {
+    if (!g || !fixed || !moving) return fail(DCMA_B200_EINVAL, "null argument", nullptr, 0);
+    return guarded([&]() { g->impl->load(fixed, moving, on_device != 0); });
+}
+
+int dcma_b200_slab_group_run(dcma_b200_slab_group *g, int64_t max_iterations, double *mse_history, dcma_b200_run_stats *stats) {
+    if (!g) return fail(DCMA_B200_EINVAL, "null group", nullptr, 0);
+    return guarded([&]() { g->impl->run(max_iterations, mse_history, stats); });
+}
+
+int dcma_b200_slab_group_range(dcma_b200_slab_group *g, int64_t *z0, int64_t *z1) {
+    if (!g || !z0 || !z1) return fail(DCMA_B200_EINVAL, "null argument", nullptr, 0);
+    return guarded([&]() { g->impl->owned_range(z0, z1); });
+}
+
+int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deformation_out) {
+    if (!g || !deformation_out) return fail(DCMA_B200_EINVAL, "null argument", nullptr, 0);
+    return guarded([&]() { g->impl->get_deformation(deformation_out); });
+}
+
+int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g) { return g ? g->impl->halo_bytes_last_run() : 0; }
 
 int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
                          int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len) {

@@ -23,12 +23,17 @@ struct CudaError : public std::runtime_error {
     } while (0)
 
 // Geometry of the dense volume: header of `demons_volume<T>` (reference src/Alignment_Demons.h:64-74).
+// A z-slab engine holds only the slices [zoff, zoff + S) of a volume of Sg slices (its owned slices plus halo planes
+// that neighbouring slabs fill in) and computes the local slices [zb, ze); a whole-volume engine has Sg == S, zoff == 0,
+// [zb, ze) == [0, S).  Every in-grid / border rule of the reference is evaluated on the GLOBAL slice index z + zoff.
 struct Geo {
-    int S, R, C, CH;     // slices, rows, cols, channels
-    long long N;         // S*R*C voxels
+    int S, R, C, CH;     // LOCAL slices held in the buffers, rows, cols, channels
+    int Sg, zoff;        // slices of the whole volume; global index of local slice 0
+    int zb, ze;          // local slice range this engine computes (owned slices)
+    long long N;         // S*R*C local voxels (component stride of the SoA fields)
     double px, py, pz;   // spacing in mm (x=column, y=row, z=slice)
     double ipx, ipy, ipz;  // reciprocals, used only by the non-strict modes
-    int is2d;            // S == 1: no z interpolation (cc:383, cc:477)
+    int is2d;            // Sg == 1: no z interpolation (cc:383, cc:477)
 };
 
 // Device-resident loop state: replaces the host variables of AlignViaDemons' loop (reference cc:980-995).
@@ -40,7 +45,8 @@ struct Ctrl {
     long long converged_at;  // loop iteration index at which the stop rule fired, LLONG_MAX otherwise
     double threshold;        // convergence_threshold
     unsigned int ticket;     // blocks of the running force kernel that have published their MSE partial
-    unsigned int pad_;
+    unsigned int halo_overflow;  // slab engines: a compose gather needed a plane outside the local buffers
+    double last_sum;         // sum of squared differences / valid count of the most recent FORCE stage (this slab)
 };
 
 constexpr long long kNotConverged = 0x7fffffffffffffffLL;

@@ -168,7 +168,7 @@ struct InsideK {
     unsigned cx, cy, cz;  // x0 < C-1, y0 < R-1, z0 < S-1 (or z0 < S when slices == 1: z1 = z0, cc:510-513)
     __device__ __forceinline__ explicit InsideK(const Geo &g)
         : cx(static_cast<unsigned>(g.C - 1)), cy(static_cast<unsigned>(g.R - 1)),
-          cz(static_cast<unsigned>(g.is2d ? g.S : g.S - 1)) {}
+          cz(static_cast<unsigned>(g.is2d ? g.Sg : g.Sg - 1)) {}  // GLOBAL slice index
     template <typename CT>
     __device__ __forceinline__ bool operator()(const Tri<CT> &t) const {
         return t.ok && static_cast<unsigned>(t.x0) < cx && static_cast<unsigned>(t.y0) < cy &&
@@ -284,9 +284,9 @@ __device__ __forceinline__ void load_stencil_xy(Stencil &s, const float *__restr
     s.yu = __ldg(Fv + k.yu);
     s.yd = __ldg(Fv + k.yd);
 }
-__device__ __forceinline__ float z_scale(const Geo &g, int z) {
-    if (g.S <= 1) return 0.0f;
-    return (z > 0 && z + 1 < g.S) ? 0.5f : 1.0f;  // S > 1: at a border the one-sided difference has distance 1
+__device__ __forceinline__ float z_scale(const Geo &g, int zg /* global slice index */) {
+    if (g.Sg <= 1) return 0.0f;
+    return (zg > 0 && zg + 1 < g.Sg) ? 0.5f : 1.0f;  // Sg > 1: at a border the one-sided difference has distance 1
 }
 __device__ __forceinline__ void grad_fixed(const Stencil &s, float sx, float sy, double &gx, double &gy, double &gz) {
     // (vr - vl) / (xr - xl) with xr - xl in {1, 2}: multiplying by 1 or 0.5 is the same operation bit for bit;
@@ -394,6 +394,26 @@ __device__ __forceinline__ void reduce_final_block(const int tid, const double *
                                                    const int nparts, Ctrl *ctrl, double *mse_hist, const long long it,
                                                    const long long hist_idx, const int count_iter);
 
+// MSE of one FORCE stage from (sum of squared differences, valid count) and the loop's stop rule (cc:340-342, 987-994).
+//   count_iter != 0: this FORCE stage belongs to loop iteration `it` (iters_done, history and convergence updated)
+__device__ __forceinline__ void apply_stop_rule(Ctrl *ctrl, double sum, long long n, double *mse_hist, const long long it,
+                                                const long long hist_idx, const int count_iter) {
+    double mse = sum;
+    if (n > 0) mse /= static_cast<double>(n);
+    ctrl->last_mse = mse;
+    ctrl->last_n = n;
+    if (count_iter) {
+        if (mse_hist) mse_hist[hist_idx] = mse;
+        ctrl->iters_done += 1;
+        const double change = fabs(ctrl->prev_mse - mse);
+        if (change < ctrl->threshold && it > 0) {
+            ctrl->converged_at = it;  // this iteration's update is still applied (the reference breaks after it)
+        } else {
+            ctrl->prev_mse = mse;
+        }
+    }
+}
+
 template <typename T, bool STRICT, typename IX, bool CH1>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
@@ -419,18 +439,18 @@ __global__ void __launch_bounds__(kTileX *kTileY)
         // Each block marches through a run of CONSECUTIVE slices [z_begin, z_end): the z neighbours of the gradient
         // stencil roll through registers (one new F load per voxel instead of three), the moving-image gathers of
         // consecutive slices overlap in L1/L2, and the displacement of the next slice is requested one step ahead.
-        const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+        const int z_begin = g.zb + blockIdx.z * zlen, z_end = min(z_begin + zlen, g.ze);
         if (z_begin < z_end) {
             IX v = static_cast<IX>(z_begin) * plane + vxy;
             const IX pch = plane * ch;
-            CT zd = static_cast<CT>(z_begin);
+            CT zd = static_cast<CT>(z_begin + g.zoff);  // sample coordinates and the moving image are GLOBAL
             CT dx = 0, dy = 0, dz = 0;
             if (w_src == 1) {
                 dx = D[v];
                 dy = D1[v];
                 dz = D2[v];
             }
-            float f_prev = __ldg(F + (z_begin > 0 ? v - plane : v) * ch);
+            float f_prev = __ldg(F + (z_begin + g.zoff > 0 ? v - plane : v) * ch);
             float f_cur = __ldg(F + v * ch);
             // L2 prefetch, one instruction per warp and step: a tile row is one warp, and lane l asks for ONE line of
             // the row kPrefetchAhead slices ahead -- lane 0: F, lane 1: M (or W), lanes 2..: the lines of D's components.
@@ -442,7 +462,7 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                 const long long row = (static_cast<long long>(z_begin) + kPrefetchAhead) * plane +
                                       static_cast<long long>(y) * g.C + blockIdx.x * kTileX;
                 if (lane < 2) {
-                    const float *base = (lane == 0) ? F : ((w_src == 2) ? Wbuf : M);
+                    const float *base = (lane == 0) ? F : ((w_src == 2) ? Wbuf : M + static_cast<long long>(g.zoff) * plane * ch);
                     pf_ptr = reinterpret_cast<const char *>(base + row * ch);
                     pf_step = static_cast<long long>(plane) * ch * static_cast<long long>(sizeof(float));
                 } else if (w_src == 1 && lane < 2 + 3 * NL) {
@@ -459,17 +479,17 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                 }
                 Stencil st;
                 load_stencil_xy<IX>(st, Fv, gk);
-                const float f_next = (z + 1 < g.S) ? __ldg(Fv + pch) : f_cur;
+                const float f_next = (z + g.zoff + 1 < g.Sg) ? __ldg(Fv + pch) : f_cur;
                 st.zp = f_prev;
                 st.zn = f_next;
-                st.sz = z_scale(g, z);
+                st.sz = z_scale(g, z + g.zoff);
                 const float fixed_val = f_cur;
                 float moving_val;
                 if (w_src == 1) {
                     // a non-finite displacement component makes the voxel NaN (cc:494-500): it fails tri_coords'
                     // range guard; with slices == 1 the unused z component is folded into x for that purpose
                     if (g.is2d) dx += dz - dz;
-                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, dx, dy, dz);
+                    const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z + g.zoff, xd, yd, zd, dx, dy, dz);
                     moving_val = warp_one<CT, IX, CH1>(M, g, t, ik(t), 0);  // only channel 0 drives the force (cc:294-295)
                     if (z + 1 < z_end) {
                         dx = D[v + plane];
@@ -477,7 +497,8 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                         dz = D2[v + plane];
                     }
                 } else {
-                    moving_val = __ldg((w_src == 0 ? M : Wbuf) + v * ch);
+                    // W := M at the voxel itself (first iteration): M is the whole volume, W a local buffer
+                    moving_val = __ldg((w_src == 0 ? M + static_cast<IX>(g.zoff) * pch : Wbuf) + v * ch);
                 }
                 CT gx, gy, gz;
                 grad_fixed(st, gk.sx, gk.sy, gx, gy, gz);
@@ -563,22 +584,31 @@ __device__ __forceinline__ void reduce_final_block(const int tid, const double *
         __syncthreads();
     }
     if (tid == 0) {
-        double mse = s_acc[0];
-        const long long n = s_cnt[0];
-        if (n > 0) mse /= static_cast<double>(n);
-        ctrl->last_mse = mse;
-        ctrl->last_n = n;
-        if (count_iter) {
-            if (mse_hist) mse_hist[hist_idx] = mse;
-            ctrl->iters_done += 1;
-            const double change = fabs(ctrl->prev_mse - mse);
-            if (change < ctrl->threshold && it > 0) {
-                ctrl->converged_at = it;  // this iteration's update is still applied (the reference breaks after it)
-            } else {
-                ctrl->prev_mse = mse;
-            }
-        }
+        ctrl->last_sum = s_acc[0];
+        apply_stop_rule(ctrl, s_acc[0], s_cnt[0], mse_hist, it, hist_idx, count_iter);
     }
+}
+
+// z-slab runs: every slab publishes (sum of squared differences, valid count) of its owned slices; after they have been
+// gathered (NCCL all-gather or peer copies) each engine applies the stop rule to the totals, summed in rank order so
+// that all ranks take the same decision bit for bit.   gather = world x {sum, (double)count}.
+__global__ void k_stop_rule(Ctrl *__restrict__ ctrl, const double *__restrict__ gather, const int world,
+                            double *__restrict__ mse_hist, const long long it, const long long hist_idx) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (it > ctrl->converged_at) return;
+    double sum = 0.0, cnt = 0.0;
+    for (int r = 0; r < world; ++r) {
+        sum += gather[2 * r];
+        cnt += gather[2 * r + 1];
+    }
+    apply_stop_rule(ctrl, sum, static_cast<long long>(cnt), mse_hist, it, hist_idx, 1);
+}
+
+// this slab's (sum, count) of the most recent FORCE stage, as two doubles (the element type of the gather)
+__global__ void k_publish_mse(const Ctrl *__restrict__ ctrl, double *__restrict__ out2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out2[0] = ctrl->last_sum;
+    out2[1] = static_cast<double>(ctrl->last_n);
 }
 
 // the same as its own launch (stage API, unfused mode)
@@ -608,13 +638,13 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const AxisK<CT> ak(g);
     const InsideK ik(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
-    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+    const int z_begin = g.zb + blockIdx.z * zlen, z_end = min(z_begin + zlen, g.ze);
     for (int z = z_begin; z < z_end; ++z) {
         const IX v = static_cast<IX>(z) * plane + vxy;
         CT dx = D[v];
         const CT dy = D1[v], dz = D2[v];
         if (g.is2d) dx += dz - dz;  // non-finite z component => NaN voxel even when z is not interpolated (cc:494-500)
-        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, static_cast<CT>(z), dx, dy, dz);
+        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z + g.zoff, xd, yd, static_cast<CT>(z + g.zoff), dx, dy, dz);
         const bool inside = ik(t);
         const int nch = CH1 ? 1 : g.CH;
         for (int c = 0; c < nch; ++c) {
@@ -634,15 +664,15 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const long long ch = g.CH;
     const long long plane = static_cast<long long>(g.R) * g.C;
     const GradK<long long> gk(g, x, y, ch);
-    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);
+    const int z_begin = g.zb + blockIdx.z * zlen, z_end = min(z_begin + zlen, g.ze);
     for (int z = z_begin; z < z_end; ++z) {
         const long long v = static_cast<long long>(z) * plane + static_cast<long long>(y) * g.C + x;
         const float *Fv = F + v * ch;
         Stencil st;
         load_stencil_xy<long long>(st, Fv, gk);
-        st.zp = __ldg(Fv - ((z > 0) ? plane * ch : 0));
-        st.zn = __ldg(Fv + ((z + 1 < g.S) ? plane * ch : 0));
-        st.sz = z_scale(g, z);
+        st.zp = __ldg(Fv - ((z + g.zoff > 0) ? plane * ch : 0));
+        st.zn = __ldg(Fv + ((z + g.zoff + 1 < g.Sg) ? plane * ch : 0));
+        st.sz = z_scale(g, z + g.zoff);
         double gx, gy, gz;
         grad_fixed(st, gk.sx, gk.sy, gx, gy, gz);
         G_aos[v * 3 + 0] = gx;
@@ -674,7 +704,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, bool STRICT, typename IX>
 __global__ void __launch_bounds__(kTileX *kTileY)
-    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int zlen, const Ctrl *__restrict__ ctrl,
+    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int zlen, Ctrl *__restrict__ ctrl,
               const long long it) {
     using CT = T;
     if (it > ctrl->converged_at) return;
@@ -687,9 +717,9 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     const InsideK ik(g);
     const CT xd = static_cast<CT>(x), yd = static_cast<CT>(y);
     const long long N = g.N;
-    const int z_begin = blockIdx.z * zlen, z_end = min(z_begin + zlen, g.S);  // consecutive slices: gathers overlap
+    const int z_begin = g.zb + blockIdx.z * zlen, z_end = min(z_begin + zlen, g.ze);  // consecutive slices: gathers overlap
     if (z_begin >= z_end) return;
-    CT zd = static_cast<CT>(z_begin);
+    CT zd = static_cast<CT>(z_begin + g.zoff);  // sample coordinates are GLOBAL; U and D are indexed locally
     CT d[3];
     {
         const IX v0 = static_cast<IX>(z_begin) * plane + vxy;
@@ -717,14 +747,16 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             if (pf_ptr != nullptr && z + kPrefetchAhead < g.S) prefetch_line(pf_ptr);
             pf_ptr += pf_step;
         }
-        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z, xd, yd, zd, d[0], d[1], d[2]);
+        const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z + g.zoff, xd, yd, zd, d[0], d[1], d[2]);
         const CT tx = t.tx, ty = t.ty, tz = t.tz;
         CT q[3][8];
-        const bool inside = ik(t);
+        const int lz0 = t.z0 - g.zoff;  // local slice of the lower corners
+        // all corners inside the grid AND inside this slab's buffers (always true for a whole-volume engine)
+        const bool inside = ik(t) && static_cast<unsigned>(lz0) < static_cast<unsigned>(g.is2d ? g.S : g.S - 1);
         if (inside) {
             // all eight corners in the grid (the common case): one row offset shared by the three components,
             // x+1 neighbours as immediate offsets, no predicates
-            const IX o00 = (static_cast<IX>(t.z0) * g.R + t.y0) * g.C + t.x0;
+            const IX o00 = (static_cast<IX>(lz0) * g.R + t.y0) * g.C + t.x0;
             const IX zstep = g.is2d ? IX(0) : plane;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -749,11 +781,16 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             const bool vx1 = t.ok && static_cast<unsigned>(x1) < static_cast<unsigned>(g.C);
             const bool vy0 = static_cast<unsigned>(t.y0) < static_cast<unsigned>(g.R);
             const bool vy1 = static_cast<unsigned>(y1) < static_cast<unsigned>(g.R);
-            const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.S);
-            const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.S);
+            const bool vz0 = static_cast<unsigned>(t.z0) < static_cast<unsigned>(g.Sg);
+            const bool vz1 = static_cast<unsigned>(z1) < static_cast<unsigned>(g.Sg);
+            const int lz1 = z1 - g.zoff;
+            // a corner inside the grid whose plane this slab does not hold: the halo is too thin for this displacement
+            if (t.ok && ((vz0 && static_cast<unsigned>(lz0) >= static_cast<unsigned>(g.S)) ||
+                         (vz1 && static_cast<unsigned>(lz1) >= static_cast<unsigned>(g.S))))
+                atomicOr(&ctrl->halo_overflow, 1u);
             const int cx0 = min(max(t.x0, 0), g.C - 1), cx1 = min(max(x1, 0), g.C - 1);
             const int cy0 = min(max(t.y0, 0), g.R - 1), cy1 = min(max(y1, 0), g.R - 1);
-            const int cz0 = min(max(t.z0, 0), g.S - 1), cz1 = min(max(z1, 0), g.S - 1);
+            const int cz0 = min(max(lz0, 0), g.S - 1), cz1 = min(max(lz1, 0), g.S - 1);
             const IX r00 = (static_cast<IX>(cz0) * g.R + cy0) * g.C, r10 = (static_cast<IX>(cz0) * g.R + cy1) * g.C;
             const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
 #pragma unroll

@@ -6,10 +6,35 @@
 
 namespace dcma {
 
+// Which slices of the volume an engine holds and computes (z-slab sharding).  The default is the whole
+// volume.  Local slice l is global slice zoff + l; the engine holds `local` slices and computes [own0, own1) of them.
+struct SlabSpec {
+    int64_t zoff = 0, local = 0, own0 = 0, own1 = 0;  // local == 0: whole volume
+};
+
+// The stages of one loop iteration, for drivers that interleave halo exchanges (slab.cu).
+enum class IterStage { Force, SmoothU, Update, SmoothD };
+
 // Device-resident replacement of the reference's `sycl_demons_engine` (src/Alignment_Demons.cc:52-704).
 class EngineBase {
   public:
     virtual ~EngineBase() {}
+    // ---- z-slab drivers only ----
+    virtual void begin_run(int64_t max_iterations) = 0;                       // reset the loop state, allocate the history
+    virtual void iter_stage(IterStage st, long long it, bool global_mse) = 0;  // enqueue one stage of iteration `it`
+    virtual void publish_mse(double *dev_out2) = 0;                           // (sum, count) of the last FORCE -> 2 doubles
+    virtual void stop_rule(const double *dev_gather, int world, long long it) = 0;
+    virtual void end_run(double *mse_history_host, dcma_b200_run_stats *stats) = 0;
+    virtual bool converged_poll() = 0;      // synchronising read of the device-side convergence flag
+    virtual bool halo_overflowed() = 0;     // synchronising read
+    virtual bool update_smoothed() const = 0, deformation_smoothed() const = 0, diffeomorphic() const = 0;
+    virtual int smoothing_radius_z(bool update_field) const = 0;
+    virtual void *field_base(int buffer) = 0;     // DCMA_B200_BUF_UPDATE / _DEFORMATION: device pointer of component 0
+    virtual int64_t field_elem_size() const = 0;  // 4 or 8
+    virtual int64_t field_comp_stride() const = 0, plane_elems() const = 0;
+    virtual void *stream_handle() = 0;
+    virtual void get_owned_deformation(double *host_aos) = 0;  // owned slices only, AoS doubles
+    virtual SlabSpec slab() const = 0;
     virtual void load(const float *fixed, const float *moving, bool on_device) = 0;
     virtual void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) = 0;
     virtual void stage(int stage, double sigma_mm, double *mse_out, int64_t *n_valid_out) = 0;
@@ -22,9 +47,11 @@ class EngineBase {
 };
 
 // one factory per precision-mode translation unit
-EngineBase *make_engine_f64(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream);
-EngineBase *make_engine_f64_strict(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream);
-EngineBase *make_engine_f32(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream);
+// `g` is always the geometry of the WHOLE volume; `slab` selects the part this engine holds.
+EngineBase *make_engine_f64(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
+EngineBase *make_engine_f64_strict(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
+EngineBase *make_engine_f32(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
+EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
 
 // warp_moving semantics on host buffers (strict fp64 translation unit)
 void warp_image_host(const dcma_b200_geom &g, const float *image, const double *deformation_aos, bool use_oob,

@@ -4,7 +4,7 @@
 #include "engine_impl.cuh"
 
 namespace dcma {
-EngineBase *make_engine_f32(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream) {
-    return new dcma_f32::Engine<float, false>(g, p, stream);
+EngineBase *make_engine_f32(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab) {
+    return new dcma_f32::Engine<float, false>(g, p, stream, slab);
 }
 }  // namespace dcma

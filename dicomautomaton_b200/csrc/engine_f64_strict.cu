@@ -4,8 +4,8 @@
 #include "engine_impl.cuh"
 
 namespace dcma {
-EngineBase *make_engine_f64_strict(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream) {
-    return new dcma_f64s::Engine<double, true>(g, p, stream);
+EngineBase *make_engine_f64_strict(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab) {
+    return new dcma_f64s::Engine<double, true>(g, p, stream, slab);
 }
 
 // warp_moving (cc:467-550) on host buffers: out[p] = image(p + D(p)), reference validity rule, optional NaN replacement.
@@ -20,6 +20,10 @@ void warp_image_host(const dcma_b200_geom &geom, const float *image, const doubl
     if (device >= 0) DCMA_CUDA(cudaSetDevice(device));
     Geo g;
     g.S = static_cast<int>(geom.slices);
+    g.Sg = g.S;
+    g.zoff = 0;
+    g.zb = 0;
+    g.ze = g.S;
     g.R = static_cast<int>(geom.rows);
     g.C = static_cast<int>(geom.cols);
     g.CH = static_cast<int>(geom.channels);

@@ -37,20 +37,31 @@ struct SmoothPlan {
 template <typename T, bool STRICT>
 class Engine final : public EngineBase {
   public:
-    Engine(const dcma_b200_geom &geom, const dcma_b200_demons_params &params, void *stream_in) : p_(params) {
+    Engine(const dcma_b200_geom &geom, const dcma_b200_demons_params &params, void *stream_in, const SlabSpec &slab_in)
+        : p_(params), slab_(slab_in) {
         if (geom.slices < 1 || geom.rows < 1 || geom.cols < 1 || geom.channels < 1)
             throw std::invalid_argument("volume extents and channel count must be >= 1");
         if (!(geom.pxl_dx > 0.0) || !(geom.pxl_dy > 0.0) || !(geom.pxl_dz > 0.0))
             throw std::invalid_argument("voxel spacing must be > 0");
         if (geom.slices > (1 << 19) || geom.rows > (1 << 19) || geom.cols > (1 << 19))
             throw std::invalid_argument("volume extent too large");
-        const long long N = geom.slices * geom.rows * geom.cols;
-        if (N * 3 >= (1LL << 40)) throw std::invalid_argument("volume too large");
-        g_.S = static_cast<int>(geom.slices);
+        if (slab_.local <= 0) slab_ = SlabSpec{0, geom.slices, 0, geom.slices};  // whole volume
+        if (slab_.zoff < 0 || slab_.zoff + slab_.local > geom.slices || slab_.own0 < 0 || slab_.own1 > slab_.local ||
+            slab_.own0 >= slab_.own1)
+            throw std::invalid_argument("bad slab specification");
+        const long long Ng = geom.slices * geom.rows * geom.cols;     // voxels of the whole volume (moving image)
+        const long long N = slab_.local * geom.rows * geom.cols;      // voxels this engine holds
+        if (Ng * 3 >= (1LL << 40)) throw std::invalid_argument("volume too large");
+        g_.S = static_cast<int>(slab_.local);
+        g_.Sg = static_cast<int>(geom.slices);
+        g_.zoff = static_cast<int>(slab_.zoff);
+        g_.zb = static_cast<int>(slab_.own0);
+        g_.ze = static_cast<int>(slab_.own1);
         g_.R = static_cast<int>(geom.rows);
         g_.C = static_cast<int>(geom.cols);
         g_.CH = static_cast<int>(geom.channels);
         g_.N = N;
+        Ng_ = Ng;
         g_.px = geom.pxl_dx;
         g_.py = geom.pxl_dy;
         g_.pz = geom.pxl_dz;
@@ -58,7 +69,7 @@ class Engine final : public EngineBase {
         g_.ipy = 1.0 / geom.pxl_dy;
         g_.ipz = 1.0 / geom.pxl_dz;
         g_.is2d = (geom.slices == 1) ? 1 : 0;
-        small_index_ = (N * geom.channels < 2000000000LL);  // 32-bit element offsets inside the per-voxel kernels
+        small_index_ = (Ng * geom.channels < 2000000000LL);  // 32-bit element offsets inside the per-voxel kernels
 
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -83,22 +94,23 @@ class Engine final : public EngineBase {
             own_stream_ = true;
         }
 
-        // per-voxel kernels: 3-D grid of 32x8 tiles, striding over slices; ~16 resident-CTA waves worth of blocks
+        // per-voxel kernels: 3-D grid of 32x8 tiles, striding over the owned slices; ~16 resident-CTA waves of blocks
         const int ntx = (g_.C + kTileX - 1) / kTileX, nty = (g_.R + kTileY - 1) / kTileY;
         if (nty > 65535) throw std::invalid_argument("too many rows");
         const long long per_plane = static_cast<long long>(ntx) * nty;
+        const int So = g_.ze - g_.zb;  // owned slices
         // runs of ~16 consecutive slices per block (rolling z stencil, gather reuse), at least ~8 waves of blocks
         const long long want = static_cast<long long>(sms_) * 8 * 8;
-        int gz = static_cast<int>(std::max<long long>((g_.S + 15) / 16, std::min<long long>(g_.S, (want + per_plane - 1) / per_plane)));
-        gz = std::max(1, std::min(gz, std::min(g_.S, 65535)));
-        zlen_ = (g_.S + gz - 1) / gz;
-        gz = (g_.S + zlen_ - 1) / zlen_;
+        int gz = static_cast<int>(std::max<long long>((So + 15) / 16, std::min<long long>(So, (want + per_plane - 1) / per_plane)));
+        gz = std::max(1, std::min(gz, std::min(So, 65535)));
+        zlen_ = (So + gz - 1) / gz;
+        gz = (So + zlen_ - 1) / zlen_;
         grid3_ = dim3(ntx, nty, gz);
         grid_vox_ = static_cast<int>(per_plane * grid3_.z);  // number of MSE partials
         grid_lin_ = static_cast<int>(std::min<long long>((3 * N + 255) / 256, static_cast<long long>(sms_) * 16));
 
         dF_ = alloc<float>(N * g_.CH);
-        dM_ = alloc<float>(N * g_.CH);
+        dM_ = alloc<float>(Ng * g_.CH);  // the moving image is always held whole: the warp gathers have no a-priori bound
         dD_ = alloc<T>(3 * N);
         dU_ = alloc<T>(3 * N);
         dTmp_ = alloc<T>(3 * N);
@@ -119,6 +131,9 @@ class Engine final : public EngineBase {
         cudaStreamSynchronize(stream_);
         for (void *p : allocs_) cudaFree(p);
         if (h_ctrl_) cudaFreeHost(h_ctrl_);
+        if (d_hist_) cudaFree(d_hist_);
+        if (ev_run0_) cudaEventDestroy(ev_run0_);
+        if (ev_run1_) cudaEventDestroy(ev_run1_);
         for (cudaEvent_t e : ev_stage_)
             if (e) cudaEventDestroy(e);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -133,12 +148,14 @@ class Engine final : public EngineBase {
     }
 
     // ---- cc:181-186 ------------------------------------------------------------------------------------------
+    // `fixed` and `moving` always point at WHOLE volumes; a slab engine takes its own slices of the fixed image.
     void load(const float *fixed, const float *moving, bool on_device) override {
         DCMA_CUDA(cudaSetDevice(dev_));
-        const size_t bytes = sizeof(float) * g_.N * g_.CH;
         const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        DCMA_CUDA(cudaMemcpyAsync(dF_, fixed, bytes, kind, stream_));
-        DCMA_CUDA(cudaMemcpyAsync(dM_, moving, bytes, kind, stream_));
+        const size_t plane_bytes = sizeof(float) * static_cast<size_t>(g_.R) * g_.C * g_.CH;
+        DCMA_CUDA(cudaMemcpyAsync(dF_, fixed + static_cast<size_t>(g_.zoff) * g_.R * g_.C * g_.CH, plane_bytes * g_.S, kind,
+                                  stream_));
+        DCMA_CUDA(cudaMemcpyAsync(dM_, moving, sizeof(float) * Ng_ * g_.CH, kind, stream_));
         DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * g_.N, stream_));
         DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(T) * 3 * g_.N, stream_));
         w_src_ = 0;  // W := M (cc:183)
@@ -151,55 +168,74 @@ class Engine final : public EngineBase {
     void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) override {
         DCMA_CUDA(cudaSetDevice(dev_));
         if (!loaded_) throw std::logic_error("engine_run called before engine_load");
+        if (is_slab()) throw std::logic_error("a z-slab engine is driven by its slab group, not by engine_run");
         if (stats) std::memset(stats, 0, sizeof(*stats));
         if (max_iterations <= 0) return;
-        reset_ctrl();
-        double *d_hist = nullptr;
-        DCMA_CUDA(cudaMalloc(&d_hist, sizeof(double) * max_iterations));
-        launches_ = 0;
-        prof_.clear();
+        begin_run(max_iterations);
         profiling_ = profile;
 
-        cudaEvent_t ev0, ev1;
-        DCMA_CUDA(cudaEventCreate(&ev0));
-        DCMA_CUDA(cudaEventCreate(&ev1));
-        DCMA_CUDA(cudaEventRecord(ev0, stream_));
-
-        // The stop rule runs on the device (k_reduce_final); the host only polls it.  With threshold <= 0 the rule
-        // `|prev-mse| < threshold` can never fire, so no poll is needed at all.
+        // The stop rule runs on the device (tail of the force kernel); the host only polls it.  With threshold <= 0
+        // the rule `|prev-mse| < threshold` can never fire, so no poll is needed at all.
         const bool can_converge = (p_.convergence_threshold > 0.0);
         const int64_t poll = (p_.check_every > 0) ? p_.check_every : 4;
-        int64_t it = 0;
-        for (; it < max_iterations; ++it) {
-            iteration(it, d_hist);
-            if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations)) {
-                DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
-                DCMA_CUDA(cudaStreamSynchronize(stream_));
-                if (h_ctrl_->converged_at != kNotConverged) {
-                    ++it;
-                    break;
-                }
-            }
+        for (int64_t it = 0; it < max_iterations; ++it) {
+            iteration(it, d_hist_);
+            if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations) && converged_poll()) break;
         }
-        DCMA_CUDA(cudaEventRecord(ev1, stream_));
+        end_run(mse_history_host, stats);
+    }
+
+    // ---- the same loop in pieces, for drivers that interleave halo exchanges between the stages (slab.cu) -------
+    void begin_run(int64_t max_iterations) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        if (!loaded_) throw std::logic_error("run called before load");
+        reset_ctrl();
+        if (d_hist_) cudaFree(d_hist_);
+        d_hist_ = nullptr;
+        DCMA_CUDA(cudaMalloc(&d_hist_, sizeof(double) * std::max<int64_t>(max_iterations, 1)));
+        launches_ = 0;
+        prof_.clear();
+        profiling_ = false;
+        DCMA_CUDA(cudaEventCreate(&ev_run0_));
+        DCMA_CUDA(cudaEventCreate(&ev_run1_));
+        DCMA_CUDA(cudaEventRecord(ev_run0_, stream_));
+    }
+    bool converged_poll() override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+        return h_ctrl_->converged_at != kNotConverged;
+    }
+    bool halo_overflowed() override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+        return h_ctrl_->halo_overflow != 0;
+    }
+    void end_run(double *mse_history_host, dcma_b200_run_stats *stats) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        DCMA_CUDA(cudaEventRecord(ev_run1_, stream_));
         DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
         DCMA_CUDA(cudaStreamSynchronize(stream_));
         const int64_t done = h_ctrl_->iters_done;
         if (mse_history_host && done > 0)
-            DCMA_CUDA(cudaMemcpy(mse_history_host, d_hist, sizeof(double) * done, cudaMemcpyDeviceToHost));
-        if (p_.verbosity >= 1) {
+            DCMA_CUDA(cudaMemcpy(mse_history_host, d_hist_, sizeof(double) * done, cudaMemcpyDeviceToHost));
+        if (p_.verbosity >= 1 && (!is_slab() || g_.zoff + g_.zb == 0)) {
             std::vector<double> h(done);
-            if (done > 0) DCMA_CUDA(cudaMemcpy(h.data(), d_hist, sizeof(double) * done, cudaMemcpyDeviceToHost));
+            if (done > 0) DCMA_CUDA(cudaMemcpy(h.data(), d_hist_, sizeof(double) * done, cudaMemcpyDeviceToHost));
             for (int64_t i = 0; i < done; ++i) std::fprintf(stderr, "Iteration %lld: MSE = %.17g\n", (long long)i, h[i]);
             if (h_ctrl_->converged_at != kNotConverged)
                 std::fprintf(stderr, "Converged after %lld iterations\n", (long long)h_ctrl_->converged_at);
         }
-        cudaFree(d_hist);
+        cudaFree(d_hist_);
+        d_hist_ = nullptr;
         float ms = 0.f;
-        DCMA_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
+        DCMA_CUDA(cudaEventElapsedTime(&ms, ev_run0_, ev_run1_));
+        cudaEventDestroy(ev_run0_);
+        cudaEventDestroy(ev_run1_);
+        ev_run0_ = ev_run1_ = nullptr;
         if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
             stats->iterations_done = done;
             stats->kernel_launches = launches_;
             stats->loop_ms = ms;
@@ -216,6 +252,56 @@ class Engine final : public EngineBase {
         }
         prof_.clear();
         profiling_ = false;
+    }
+    // one stage of loop iteration `it`; global_mse: the force kernel only publishes this slab's (sum, count), the
+    // stop rule is applied by stop_rule() once the slabs' values have been gathered
+    void iter_stage(IterStage st, long long it, bool global_mse) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        const bool diffeo = (p_.use_diffeomorphic != 0);
+        switch (st) {
+            case IterStage::Force:
+                launch_force(w_src_, it, d_hist_, it, global_mse ? 0 : 1, /*reduce=*/false, /*fused_reduce=*/true);
+                break;
+            case IterStage::SmoothU:
+                if (diffeo && plan_u_.active) smooth(dU_, plan_u_, it);
+                break;
+            case IterStage::Update:
+                if (diffeo)
+                    launch_compose(it);
+                else
+                    launch_add(it);
+                break;
+            case IterStage::SmoothD:
+                if (plan_d_.active) smooth(dD_, plan_d_, it);
+                w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
+                break;
+        }
+    }
+    void publish_mse(double *dev_out2) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        k_publish_mse<<<1, 32, 0, stream_>>>(d_ctrl_, dev_out2);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    void stop_rule(const double *dev_gather, int world, long long it) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        k_stop_rule<<<1, 32, 0, stream_>>>(d_ctrl_, dev_gather, world, d_hist_, it, it);
+        DCMA_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    bool update_smoothed() const override { return p_.use_diffeomorphic != 0 && plan_u_.active; }
+    bool deformation_smoothed() const override { return plan_d_.active; }
+    bool diffeomorphic() const override { return p_.use_diffeomorphic != 0; }
+    int smoothing_radius_z(bool update_field) const override { return update_field ? plan_u_.r[2] : plan_d_.r[2]; }
+    void *field_base(int buffer) override { return buffer == DCMA_B200_BUF_UPDATE ? static_cast<void *>(dU_) : static_cast<void *>(dD_); }
+    int64_t field_elem_size() const override { return static_cast<int64_t>(sizeof(T)); }
+    int64_t field_comp_stride() const override { return g_.N; }
+    int64_t plane_elems() const override { return static_cast<int64_t>(g_.R) * g_.C; }
+    void *stream_handle() override { return stream_; }
+    SlabSpec slab() const override { return slab_; }
+    void get_owned_deformation(double *host_aos) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        export_field_host(dD_, host_aos);
     }
 
     // ---- one reference engine method at a time ------------------------------------------------------------------
@@ -255,10 +341,11 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaSetDevice(dev_));
         const long long N = g_.N;
         switch (buffer) {
-            case DCMA_B200_BUF_FIXED:
-            case DCMA_B200_BUF_MOVING:
-                DCMA_CUDA(cudaMemcpyAsync(host, buffer == DCMA_B200_BUF_FIXED ? dF_ : dM_, sizeof(float) * N * g_.CH,
-                                          cudaMemcpyDeviceToHost, stream_));
+            case DCMA_B200_BUF_FIXED:  // the slices this engine holds
+                DCMA_CUDA(cudaMemcpyAsync(host, dF_, sizeof(float) * N * g_.CH, cudaMemcpyDeviceToHost, stream_));
+                break;
+            case DCMA_B200_BUF_MOVING:  // always the whole volume
+                DCMA_CUDA(cudaMemcpyAsync(host, dM_, sizeof(float) * Ng_ * g_.CH, cudaMemcpyDeviceToHost, stream_));
                 break;
             case DCMA_B200_BUF_WARPED:
                 materialise_warped();
@@ -288,9 +375,10 @@ class Engine final : public EngineBase {
         const long long N = g_.N;
         switch (buffer) {
             case DCMA_B200_BUF_FIXED:
+                DCMA_CUDA(cudaMemcpyAsync(dF_, host, sizeof(float) * N * g_.CH, cudaMemcpyHostToDevice, stream_));
+                break;
             case DCMA_B200_BUF_MOVING:
-                DCMA_CUDA(cudaMemcpyAsync(buffer == DCMA_B200_BUF_FIXED ? dF_ : dM_, host, sizeof(float) * N * g_.CH,
-                                          cudaMemcpyHostToDevice, stream_));
+                DCMA_CUDA(cudaMemcpyAsync(dM_, host, sizeof(float) * Ng_ * g_.CH, cudaMemcpyHostToDevice, stream_));
                 break;
             case DCMA_B200_BUF_WARPED:
                 ensure_warped_buffer();
@@ -308,7 +396,7 @@ class Engine final : public EngineBase {
 
     void export_deformation_device(double *device_out) override {
         DCMA_CUDA(cudaSetDevice(dev_));
-        k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(dD_, device_out, g_.N, 0, g_.N);
+        k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(dD_, device_out, g_.N, owned_v0(), owned_v1());
         DCMA_CUDA(cudaGetLastError());
     }
 
@@ -329,8 +417,9 @@ class Engine final : public EngineBase {
         cudaEvent_t done;
         DCMA_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         int k = 0;
-        for (long long v0 = 0; v0 < g_.N; v0 += kStageVoxels, ++k) {
-            const long long v1 = std::min(g_.N, v0 + kStageVoxels);
+        const long long vb = owned_v0(), ve = owned_v1();  // owned slices only; the AoS output starts at the first of them
+        for (long long v0 = vb; v0 < ve; v0 += kStageVoxels, ++k) {
+            const long long v1 = std::min(ve, v0 + kStageVoxels);
             const int half = k & 1;
             double *st = staging(half);
             // the kernel may overwrite this half only after the copy that last read it has finished
@@ -339,7 +428,7 @@ class Engine final : public EngineBase {
             DCMA_CUDA(cudaGetLastError());
             DCMA_CUDA(cudaEventRecord(done, stream_));
             DCMA_CUDA(cudaStreamWaitEvent(copy_stream_, done, 0));
-            DCMA_CUDA(cudaMemcpyAsync(host + 3 * v0, st, sizeof(double) * 3 * (v1 - v0), cudaMemcpyDeviceToHost, copy_stream_));
+            DCMA_CUDA(cudaMemcpyAsync(host + 3 * (v0 - vb), st, sizeof(double) * 3 * (v1 - v0), cudaMemcpyDeviceToHost, copy_stream_));
             DCMA_CUDA(cudaEventRecord(ev_stage_[half], copy_stream_));
         }
         DCMA_CUDA(cudaStreamSynchronize(copy_stream_));
@@ -347,10 +436,11 @@ class Engine final : public EngineBase {
         cudaEventDestroy(done);
     }
     void import_field_host(const double *host, T *field) {
-        for (long long v0 = 0; v0 < g_.N; v0 += kStageVoxels) {
-            const long long v1 = std::min(g_.N, v0 + kStageVoxels);
+        const long long vb = owned_v0(), ve = owned_v1();
+        for (long long v0 = vb; v0 < ve; v0 += kStageVoxels) {
+            const long long v1 = std::min(ve, v0 + kStageVoxels);
             double *st = staging(0);
-            DCMA_CUDA(cudaMemcpyAsync(st, host + 3 * v0, sizeof(double) * 3 * (v1 - v0), cudaMemcpyHostToDevice, stream_));
+            DCMA_CUDA(cudaMemcpyAsync(st, host + 3 * (v0 - vb), sizeof(double) * 3 * (v1 - v0), cudaMemcpyHostToDevice, stream_));
             k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(st, field, g_.N, v0, v1);
             DCMA_CUDA(cudaGetLastError());
         }
@@ -389,7 +479,8 @@ class Engine final : public EngineBase {
         c.converged_at = kNotConverged;
         c.threshold = p_.convergence_threshold;
         c.ticket = 0;
-        c.pad_ = 0;
+        c.halo_overflow = 0;
+        c.last_sum = 0.0;
         *h_ctrl_ = c;
         DCMA_CUDA(cudaMemcpyAsync(d_ctrl_, h_ctrl_, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
         DCMA_CUDA(cudaStreamSynchronize(stream_));  // h_ctrl_ is reused as the D2H landing buffer
@@ -400,7 +491,7 @@ class Engine final : public EngineBase {
         pl.active = (sigma_mm > 0.0);
         if (!pl.active) return;
         const double pxl[3] = {g_.px, g_.py, g_.pz};
-        const int extent[3] = {g_.C, g_.R, g_.S};
+        const int extent[3] = {g_.C, g_.R, g_.Sg};  // the z tables cover the WHOLE volume; kernels get them shifted by zoff
         for (int a = 0; a < 3; ++a) {
             const long long rad = std::max<long long>(1, static_cast<long long>(3.0 * sigma_mm / pxl[a]));
             if (rad > 100000) throw std::invalid_argument("smoothing radius too large");
@@ -558,7 +649,7 @@ class Engine final : public EngineBase {
     void ensure_warped_buffer() {
         if (!dW_) {
             dW_ = alloc<float>(g_.N * g_.CH);
-            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_, sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
+            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_ + local_offset_in_moving(), sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
         }
     }
     void launch_warp_to_buffer(long long it = 0) {
@@ -583,7 +674,7 @@ class Engine final : public EngineBase {
     void materialise_warped() {
         ensure_warped_buffer();
         if (w_src_ == 0) {
-            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_, sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
+            DCMA_CUDA(cudaMemcpyAsync(dW_, dM_ + local_offset_in_moving(), sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
         } else if (w_src_ == 1) {
             launch_warp_to_buffer();
         }
@@ -631,10 +722,11 @@ class Engine final : public EngineBase {
         const long long nxy = static_cast<long long>(gx) * gy * 3;
         int best_nz = 1;
         double best_score = -1.0;
-        const int nz_max = std::max(1, std::min(g_.S / std::max(2 * R, 1), static_cast<int>(65535 / 3)));
+        const int So = g_.ze - g_.zb;  // owned slices
+        const int nz_max = std::max(1, std::min(So / std::max(2 * R, 1), static_cast<int>(65535 / 3)));
         for (int nzc = 1; nzc <= nz_max; ++nzc) {
-            const int zc = (g_.S + nzc - 1) / nzc;
-            const int nz_eff = (g_.S + zc - 1) / zc;
+            const int zc = (So + nzc - 1) / nzc;
+            const int nz_eff = (So + zc - 1) / zc;
             const double waves = static_cast<double>(nxy) * nz_eff / slots;
             const double score = (static_cast<double>(zc) / (zc + 2 * R)) * (waves / std::ceil(waves));
             if (score > best_score + 1e-9) {
@@ -642,10 +734,10 @@ class Engine final : public EngineBase {
                 best_nz = nz_eff;
             }
         }
-        const int zchunk = (g_.S + best_nz - 1) / best_nz;
-        const int nz = (g_.S + zchunk - 1) / zchunk;
+        const int zchunk = (So + best_nz - 1) / best_nz;
+        const int nz = (So + zchunk - 1) / zchunk;
         if (3LL * nz > 65535 || gy > 65535) throw std::invalid_argument("volume exceeds the smoothing kernel's grid limits");
-        kern<<<dim3(gx, gy, 3 * nz), NT, Cfg::smem_bytes, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2],
+        kern<<<dim3(gx, gy, 3 * nz), NT, Cfg::smem_bytes, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2] + g_.zoff,
                                                                      pl.dw[0], pl.dw[1], pl.dw[2], zchunk, nz, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
@@ -678,7 +770,16 @@ class Engine final : public EngineBase {
         }
     }
 
+    bool is_slab() const { return g_.S != g_.Sg || g_.zb != 0 || g_.ze != g_.S; }
+    long long owned_v0() const { return static_cast<long long>(g_.zb) * g_.R * g_.C; }
+    long long owned_v1() const { return static_cast<long long>(g_.ze) * g_.R * g_.C; }
+    long long local_offset_in_moving() const { return static_cast<long long>(g_.zoff) * g_.R * g_.C * g_.CH; }
+
     Geo g_;
+    long long Ng_ = 0;  // voxels of the whole volume
+    SlabSpec slab_;
+    double *d_hist_ = nullptr;
+    cudaEvent_t ev_run0_ = nullptr, ev_run1_ = nullptr;
     dcma_b200_demons_params p_;
     int dev_ = 0, sms_ = 148;
     cudaStream_t stream_ = nullptr;

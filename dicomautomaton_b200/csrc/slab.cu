@@ -1,0 +1,371 @@
+// dcma_b200 -- z-slab sharding of ONE registration over several GPUs (BASELINE config 4).
+//
+// The reference holds the whole volume in one address space (src/Alignment_Demons.cc:171-187) and has no multi-device
+// path; this file is the B200 analogue of its loop (cc:980-995) for a volume cut into contiguous z-slabs:
+//   * every slab engine holds its owned slices plus `halo` planes on each interior side; the moving image is replicated
+//     (the warp gathers at p + D(p) have no a-priori bound);
+//   * per iteration the neighbours exchange  r_z planes of U   before smooth(U),
+//                                            halo planes of U~ before the diffeomorphic composition (its gathers),
+//                                            r_z planes of D   before smooth(D),
+//     and all slabs gather their (sum of squared differences, valid count) so that each applies the reference's stop
+//     rule to the same totals (summed in rank order: every rank takes the same decision bit for bit);
+//   * arithmetic per voxel is exactly that of the whole-volume engine: a slab run reproduces its field bit for bit.
+// Two transports: peer copies between engines of ONE process (any mix of devices; also the single-GPU test vehicle),
+// and NCCL send/recv + all-gather between processes (one rank per GPU, the bench/torchrun layout).  NCCL is loaded
+// with dlopen so that the library itself has no link-time dependency on it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "slab.h"
+
+namespace dcma {
+
+SlabSpec slab_for_rank(int64_t slices, int world, int rank, int64_t halo) {
+    if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad world/rank");
+    if (halo < 0) throw std::invalid_argument("negative halo");
+    const int64_t base = slices / world, rem = slices % world;
+    if (base < 1) throw std::invalid_argument("more slabs than slices");
+    if (world > 1 && base < halo) throw std::invalid_argument("slabs thinner than the halo: use fewer devices or a smaller halo");
+    const int64_t z0 = rank * base + std::min<int64_t>(rank, rem);
+    const int64_t z1 = z0 + base + (rank < rem ? 1 : 0);
+    const int64_t lo = std::max<int64_t>(0, z0 - halo), hi = std::min<int64_t>(slices, z1 + halo);
+    SlabSpec s;
+    s.zoff = lo;
+    s.local = hi - lo;
+    s.own0 = z0 - lo;
+    s.own1 = z1 - lo;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+NcclApi &nccl() {
+    static NcclApi api;
+    if (api.handle) return api;
+    const char *names[] = {std::getenv("DCMA_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) throw std::runtime_error("NCCL (libnccl.so.2) could not be loaded; set DCMA_B200_NCCL_LIB to its path");
+#define DCMA_NCCL_SYM(field, sym)                                                              \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, #sym));               \
+    if (!api.field) throw std::runtime_error(std::string("NCCL symbol missing: ") + #sym)
+    DCMA_NCCL_SYM(GetUniqueId, ncclGetUniqueId);
+    DCMA_NCCL_SYM(CommInitRank, ncclCommInitRank);
+    DCMA_NCCL_SYM(CommDestroy, ncclCommDestroy);
+    DCMA_NCCL_SYM(Send, ncclSend);
+    DCMA_NCCL_SYM(Recv, ncclRecv);
+    DCMA_NCCL_SYM(GroupStart, ncclGroupStart);
+    DCMA_NCCL_SYM(GroupEnd, ncclGroupEnd);
+    DCMA_NCCL_SYM(AllGather, ncclAllGather);
+    DCMA_NCCL_SYM(GetErrorString, ncclGetErrorString);
+#undef DCMA_NCCL_SYM
+    return api;
+}
+
+#define DCMA_NCCL(expr)                                                                                            \
+    do {                                                                                                           \
+        ncclResult_t _r = (expr);                                                                                  \
+        if (_r != ncclSuccess && _r != ncclInProgress)                                                             \
+            throw std::runtime_error(std::string(#expr) + " failed: " + nccl().GetErrorString(_r));               \
+    } while (0)
+}  // namespace
+
+void nccl_unique_id(unsigned char id[128]) {
+    ncclUniqueId u;
+    DCMA_NCCL(nccl().GetUniqueId(&u));
+    static_assert(sizeof(u.internal) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id, u.internal, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SlabGroup
+// ---------------------------------------------------------------------------------------------------------------
+struct SlabGroup::Local {
+    std::unique_ptr<EngineBase> eng;
+    int rank = 0, device = 0;
+    double *d_mse2 = nullptr;    // this slab's (sum, count)
+    double *d_gather = nullptr;  // world x (sum, count)
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+};
+
+SlabGroup::~SlabGroup() {
+    for (auto &l : locals_) {
+        cudaSetDevice(l->device);
+        if (l->eng) cudaStreamSynchronize(static_cast<cudaStream_t>(l->eng->stream_handle()));
+        cudaFree(l->d_mse2);
+        cudaFree(l->d_gather);
+        if (l->ev_ready) cudaEventDestroy(l->ev_ready);
+        if (l->ev_done) cudaEventDestroy(l->ev_done);
+        l->eng.reset();
+    }
+    if (comm_) {
+        try {
+            nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
+        } catch (...) {
+        }
+    }
+}
+
+int64_t SlabGroup::default_halo(const dcma_b200_geom &g, const dcma_b200_demons_params &p) {
+    auto rz = [&](double sigma) -> int64_t {
+        return sigma > 0.0 ? std::max<int64_t>(1, static_cast<int64_t>(3.0 * sigma / g.pxl_dz)) : 0;  // cc:574-576
+    };
+    const int64_t r = std::max(rz(p.deformation_field_smoothing_sigma), p.use_diffeomorphic ? rz(p.update_field_smoothing_sigma) : 0);
+    // composition gathers reach ceil(|D_z| / pxl_dz) + 1 planes: 8 planes cover 7 voxels of z displacement
+    return std::max<int64_t>(r, p.use_diffeomorphic ? 8 : 1);
+}
+
+void SlabGroup::add_local(const dcma_b200_geom &g, const dcma_b200_demons_params &p, int rank, int device) {
+    auto l = std::make_unique<Local>();
+    l->rank = rank;
+    dcma_b200_demons_params pp = p;
+    pp.device = device;
+    const SlabSpec spec = slab_for_rank(g.slices, world_, rank, halo_);
+    l->eng.reset(make_engine(g, pp, nullptr, spec));
+    l->device = l->eng->device();
+    DCMA_CUDA(cudaSetDevice(l->device));
+    DCMA_CUDA(cudaMalloc(&l->d_mse2, 2 * sizeof(double)));
+    DCMA_CUDA(cudaMalloc(&l->d_gather, 2 * sizeof(double) * world_));
+    DCMA_CUDA(cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming));
+    DCMA_CUDA(cudaEventCreateWithFlags(&l->ev_done, cudaEventDisableTiming));
+    locals_.push_back(std::move(l));
+}
+
+SlabGroup::SlabGroup(const dcma_b200_geom &g, const dcma_b200_demons_params &p, const std::vector<int> &devices, int64_t halo)
+    : geom_(g), params_(p), world_(static_cast<int>(devices.size())), halo_(halo < 0 ? default_halo(g, p) : halo) {
+    if (devices.empty()) throw std::invalid_argument("no devices");
+    for (int r = 0; r < world_; ++r) add_local(g, p, r, devices[r]);
+    // peer access makes the halo copies direct NVLink transfers; failure only means staged copies
+    for (auto &a : locals_)
+        for (auto &b : locals_)
+            if (a->device != b->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, a->device, b->device);
+                if (can) {
+                    cudaSetDevice(a->device);
+                    if (cudaDeviceEnablePeerAccess(b->device, 0) != cudaSuccess) cudaGetLastError();
+                }
+            }
+}
+
+SlabGroup::SlabGroup(const dcma_b200_geom &g, const dcma_b200_demons_params &p, const unsigned char id[128], int rank, int world,
+                     int device, int64_t halo)
+    : geom_(g), params_(p), world_(world), halo_(halo < 0 ? default_halo(g, p) : halo) {
+    if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad world/rank");
+    add_local(g, p, rank, device);
+    DCMA_CUDA(cudaSetDevice(locals_[0]->device));
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    ncclComm_t c = nullptr;
+    DCMA_NCCL(nccl().CommInitRank(&c, world, u, rank));
+    comm_ = c;
+}
+
+void SlabGroup::load(const float *fixed, const float *moving, bool on_device) {
+    if (on_device && locals_.size() > 1) {
+        // device pointers belong to one device; peer-readable copies work through UVA
+    }
+    for (auto &l : locals_) l->eng->load(fixed, moving, on_device);
+}
+
+// planes [l0, l0 + n) of component c of `buffer`
+static inline char *plane_ptr(EngineBase *e, int buffer, int c, int64_t l0) {
+    return static_cast<char *>(e->field_base(buffer)) + (c * e->field_comp_stride() + l0 * e->plane_elems()) * e->field_elem_size();
+}
+
+void SlabGroup::exchange(int buffer, int64_t n) {
+    if (world_ == 1 || n <= 0) return;
+    if (n > halo_) throw std::logic_error("exchange wider than the halo");
+    if (comm_) {
+        // ---- NCCL: one grouped send/recv set with both z-neighbours, on the engine's stream
+        Local &l = *locals_[0];
+        EngineBase *e = l.eng.get();
+        const SlabSpec s = e->slab();
+        const size_t bytes = static_cast<size_t>(n) * e->plane_elems() * e->field_elem_size();
+        cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
+        DCMA_CUDA(cudaSetDevice(l.device));
+        DCMA_NCCL(nccl().GroupStart());
+        for (int c = 0; c < 3; ++c) {
+            if (l.rank > 0) {  // lower neighbour: my first owned planes go down, its last owned planes come into my lower halo
+                DCMA_NCCL(nccl().Send(plane_ptr(e, buffer, c, s.own0), bytes, ncclChar, l.rank - 1, static_cast<ncclComm_t>(comm_), st));
+                DCMA_NCCL(nccl().Recv(plane_ptr(e, buffer, c, s.own0 - n), bytes, ncclChar, l.rank - 1, static_cast<ncclComm_t>(comm_), st));
+            }
+            if (l.rank + 1 < world_) {
+                DCMA_NCCL(nccl().Send(plane_ptr(e, buffer, c, s.own1 - n), bytes, ncclChar, l.rank + 1, static_cast<ncclComm_t>(comm_), st));
+                DCMA_NCCL(nccl().Recv(plane_ptr(e, buffer, c, s.own1), bytes, ncclChar, l.rank + 1, static_cast<ncclComm_t>(comm_), st));
+            }
+        }
+        DCMA_NCCL(nccl().GroupEnd());
+        halo_bytes_ += 2 * 3 * bytes * ((l.rank > 0 ? 1 : 0) + (l.rank + 1 < world_ ? 1 : 0));
+        return;
+    }
+    // ---- one process: peer copies, ordered by events (producer ready -> copy on the receiver's stream -> both sides
+    // wait for the copies before they touch the planes again)
+    for (auto &l : locals_) {
+        DCMA_CUDA(cudaSetDevice(l->device));
+        DCMA_CUDA(cudaEventRecord(l->ev_ready, static_cast<cudaStream_t>(l->eng->stream_handle())));
+    }
+    for (int r = 0; r + 1 < world_; ++r) {
+        Local &lo = *locals_[r], &hi = *locals_[r + 1];
+        EngineBase *a = lo.eng.get(), *b = hi.eng.get();
+        const SlabSpec sa = a->slab(), sb = b->slab();
+        const size_t bytes = static_cast<size_t>(n) * a->plane_elems() * a->field_elem_size();
+        cudaStream_t st_a = static_cast<cudaStream_t>(a->stream_handle()), st_b = static_cast<cudaStream_t>(b->stream_handle());
+        // up: a's last owned planes -> b's lower halo, on b's stream
+        DCMA_CUDA(cudaSetDevice(hi.device));
+        DCMA_CUDA(cudaStreamWaitEvent(st_b, lo.ev_ready, 0));
+        for (int c = 0; c < 3; ++c)
+            DCMA_CUDA(cudaMemcpyPeerAsync(plane_ptr(b, buffer, c, sb.own0 - n), hi.device, plane_ptr(a, buffer, c, sa.own1 - n), lo.device, bytes, st_b));
+        // down: b's first owned planes -> a's upper halo, on a's stream
+        DCMA_CUDA(cudaSetDevice(lo.device));
+        DCMA_CUDA(cudaStreamWaitEvent(st_a, hi.ev_ready, 0));
+        for (int c = 0; c < 3; ++c)
+            DCMA_CUDA(cudaMemcpyPeerAsync(plane_ptr(a, buffer, c, sa.own1), lo.device, plane_ptr(b, buffer, c, sb.own0), hi.device, bytes, st_a));
+        halo_bytes_ += 2 * 3 * bytes;
+    }
+    for (auto &l : locals_) {
+        DCMA_CUDA(cudaSetDevice(l->device));
+        DCMA_CUDA(cudaEventRecord(l->ev_done, static_cast<cudaStream_t>(l->eng->stream_handle())));
+    }
+    for (int r = 0; r + 1 < world_; ++r) {
+        Local &lo = *locals_[r], &hi = *locals_[r + 1];
+        DCMA_CUDA(cudaSetDevice(lo.device));
+        DCMA_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(lo.eng->stream_handle()), hi.ev_done, 0));
+        DCMA_CUDA(cudaSetDevice(hi.device));
+        DCMA_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(hi.eng->stream_handle()), lo.ev_done, 0));
+    }
+}
+
+void SlabGroup::gather_mse_and_stop_rule(long long it) {
+    for (auto &l : locals_) l->eng->publish_mse(l->d_mse2);
+    if (comm_) {
+        Local &l = *locals_[0];
+        DCMA_CUDA(cudaSetDevice(l.device));
+        DCMA_NCCL(nccl().AllGather(l.d_mse2, l.d_gather, 2, ncclDouble, static_cast<ncclComm_t>(comm_),
+                                   static_cast<cudaStream_t>(l.eng->stream_handle())));
+    } else {
+        for (auto &l : locals_) {
+            DCMA_CUDA(cudaSetDevice(l->device));
+            DCMA_CUDA(cudaEventRecord(l->ev_ready, static_cast<cudaStream_t>(l->eng->stream_handle())));
+        }
+        for (auto &dst : locals_) {
+            DCMA_CUDA(cudaSetDevice(dst->device));
+            cudaStream_t st = static_cast<cudaStream_t>(dst->eng->stream_handle());
+            for (auto &src : locals_) {
+                if (src.get() != dst.get()) DCMA_CUDA(cudaStreamWaitEvent(st, src->ev_ready, 0));
+                DCMA_CUDA(cudaMemcpyPeerAsync(dst->d_gather + 2 * src->rank, dst->device, src->d_mse2, src->device, 2 * sizeof(double), st));
+            }
+        }
+        // d_mse2 is rewritten only by the next iteration's publish, which every stream reaches after the exchanges
+        // below have synchronised it with its neighbours; a full fence keeps this independent of the stage pattern
+        for (auto &l : locals_) {
+            DCMA_CUDA(cudaSetDevice(l->device));
+            DCMA_CUDA(cudaEventRecord(l->ev_done, static_cast<cudaStream_t>(l->eng->stream_handle())));
+        }
+        for (auto &a : locals_)
+            for (auto &b : locals_)
+                if (a.get() != b.get()) {
+                    DCMA_CUDA(cudaSetDevice(a->device));
+                    DCMA_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(a->eng->stream_handle()), b->ev_done, 0));
+                }
+    }
+    for (auto &l : locals_) l->eng->stop_rule(l->d_gather, world_, it);
+}
+
+void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_run_stats *stats) {
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (max_iterations <= 0) return;
+    halo_bytes_ = 0;
+    EngineBase *e0 = locals_[0]->eng.get();
+    const bool diffeo = e0->diffeomorphic();
+    const int64_t rz_u = e0->update_smoothed() ? e0->smoothing_radius_z(true) : 0;
+    const int64_t rz_d = e0->deformation_smoothed() ? e0->smoothing_radius_z(false) : 0;
+    if (world_ > 1 && std::max(rz_u, rz_d) > halo_) throw std::invalid_argument("halo thinner than the smoothing radius along z");
+    const bool can_converge = (params_.convergence_threshold > 0.0);
+    const int64_t poll = (params_.check_every > 0) ? params_.check_every : 4;
+    for (auto &l : locals_) l->eng->begin_run(max_iterations);
+    for (int64_t it = 0; it < max_iterations; ++it) {
+        for (auto &l : locals_) l->eng->iter_stage(IterStage::Force, it, /*global_mse=*/true);
+        gather_mse_and_stop_rule(it);
+        if (rz_u > 0) {
+            exchange(DCMA_B200_BUF_UPDATE, rz_u);
+            for (auto &l : locals_) l->eng->iter_stage(IterStage::SmoothU, it, true);
+        }
+        if (diffeo) exchange(DCMA_B200_BUF_UPDATE, halo_);  // the composition gathers U~ at p + D(p)
+        for (auto &l : locals_) l->eng->iter_stage(IterStage::Update, it, true);
+        if (rz_d > 0) exchange(DCMA_B200_BUF_DEFORMATION, rz_d);
+        for (auto &l : locals_) l->eng->iter_stage(IterStage::SmoothD, it, true);
+        if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations) && e0->converged_poll()) break;
+    }
+    dcma_b200_run_stats st0;
+    bool first = true;
+    for (auto &l : locals_) {
+        dcma_b200_run_stats st;
+        l->eng->end_run(first ? mse_history_host : nullptr, &st);
+        if (first) {
+            st0 = st;
+        } else {
+            st0.loop_ms = std::max(st0.loop_ms, st.loop_ms);
+            st0.kernel_launches += st.kernel_launches;
+        }
+        first = false;
+    }
+    if (stats) *stats = st0;
+    for (auto &l : locals_)
+        if (l->eng->halo_overflowed())
+            throw std::logic_error("a composition gather left the slab halo (|D_z| too large for halo_planes = " +
+                                   std::to_string(halo_) + "); re-run with a larger halo or fewer slabs");
+}
+
+void SlabGroup::owned_range(int64_t *z0, int64_t *z1) const {
+    // the slices owned by THIS process (all of them for a one-process group)
+    const SlabSpec a = locals_.front()->eng->slab(), b = locals_.back()->eng->slab();
+    *z0 = a.zoff + a.own0;
+    *z1 = b.zoff + b.own1;
+}
+
+void SlabGroup::get_deformation(double *host_aos) {
+    int64_t z0, z1;
+    owned_range(&z0, &z1);
+    const int64_t plane3 = 3 * geom_.rows * geom_.cols;
+    for (auto &l : locals_) {
+        const SlabSpec s = l->eng->slab();
+        l->eng->get_owned_deformation(host_aos + (s.zoff + s.own0 - z0) * plane3);
+    }
+}
+
+int64_t SlabGroup::device_bytes() const {
+    int64_t b = 0;
+    for (auto &l : locals_) b += l->eng->device_bytes();
+    return b;
+}
+
+}  // namespace dcma

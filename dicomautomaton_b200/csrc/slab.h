@@ -1,0 +1,46 @@
+// dcma_b200 -- z-slab group: one registration sharded over several engines (see slab.cu).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "engine.h"
+
+namespace dcma {
+
+// contiguous balanced z-slabs (earlier ranks take the remainder) extended by `halo` planes on interior sides
+SlabSpec slab_for_rank(int64_t slices, int world, int rank, int64_t halo);
+void nccl_unique_id(unsigned char id[128]);
+
+class SlabGroup {
+  public:
+    // one process, one engine per entry of `devices` (repeats allowed), halos by peer copies
+    SlabGroup(const dcma_b200_geom &g, const dcma_b200_demons_params &p, const std::vector<int> &devices, int64_t halo);
+    // one rank of `world` processes, halos by NCCL send/recv
+    SlabGroup(const dcma_b200_geom &g, const dcma_b200_demons_params &p, const unsigned char id[128], int rank, int world,
+              int device, int64_t halo);
+    ~SlabGroup();
+    void load(const float *fixed_whole, const float *moving_whole, bool on_device);
+    void run(int64_t max_iterations, double *mse_history_host, dcma_b200_run_stats *stats);
+    void owned_range(int64_t *z0, int64_t *z1) const;  // slices held by THIS process
+    void get_deformation(double *host_aos);             // those slices, AoS doubles
+    int64_t device_bytes() const;
+    int64_t halo() const { return halo_; }
+    int64_t halo_bytes_last_run() const { return halo_bytes_; }
+    static int64_t default_halo(const dcma_b200_geom &g, const dcma_b200_demons_params &p);
+
+  private:
+    struct Local;
+    void add_local(const dcma_b200_geom &g, const dcma_b200_demons_params &p, int rank, int device);
+    void exchange(int buffer, int64_t planes);
+    void gather_mse_and_stop_rule(long long it);
+    dcma_b200_geom geom_;
+    dcma_b200_demons_params params_;
+    int world_ = 1;
+    int64_t halo_ = 0;
+    int64_t halo_bytes_ = 0;
+    void *comm_ = nullptr;  // ncclComm_t
+    std::vector<std::unique_ptr<Local>> locals_;
+};
+
+}  // namespace dcma

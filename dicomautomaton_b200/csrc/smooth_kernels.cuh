@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256)
     if (it > ctrl->converged_at) return;
     const long long N = g.N;
     const long long stride_thr = static_cast<long long>(gridDim.x) * blockDim.x;
-    const int extent = (axis == 0) ? g.C : (axis == 1) ? g.R : g.S;
+    const int extent = (axis == 0) ? g.C : (axis == 1) ? g.R : g.Sg;  // the z rule uses GLOBAL slice indices
     const long long stride = (axis == 0) ? 1 : (axis == 1) ? g.C : static_cast<long long>(g.R) * g.C;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3 * N; i += stride_thr) {
         const long long v = i % N;
@@ -77,11 +77,14 @@ __global__ void __launch_bounds__(256)
         const long long r1 = v / g.C;
         const int y = static_cast<int>(r1 % g.R);
         const int z = static_cast<int>(r1 / g.R);
-        const int pos = (axis == 0) ? x : (axis == 1) ? y : z;
+        // x and y passes run on every local slice (halo planes included: the z pass reads them); the z pass only on
+        // the owned slices
+        if (axis == 2 && (z < g.zb || z >= g.ze)) continue;
+        const int pos = (axis == 0) ? x : (axis == 1) ? y : z + g.zoff;
         T sum = 0, wsum = 0;
         for (int k = -rad; k <= rad; ++k) {
             const int q = pos + k;
-            if (q >= 0 && q < extent) {
+            if (q >= 0 && q < extent && (axis != 2 || (z + k >= 0 && z + k < g.S))) {
                 const T val = in[i + k * stride];
                 if (isfinite(val)) {
                     const T wk = static_cast<T>(w[k + rad]);
@@ -203,8 +206,8 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
     const long long plane = static_cast<long long>(g.R) * g.C;
     T zs = 0, zw = 0, z_centre = 0;
     for (int kz = -R; kz <= R; ++kz) {
-        const int zz = z + kz;
-        if (zz < 0 || zz >= g.S) continue;
+        const int zz = z + kz;  // local slice; in-grid test on the global index
+        if (zz + g.zoff < 0 || zz + g.zoff >= g.Sg || zz < 0 || zz >= g.S) continue;
         T ys = 0, yw = 0, y_centre = 0;
         for (int ky = -R; ky <= R; ++ky) {
             const int yy = y + ky;
@@ -306,8 +309,8 @@ __global__ void __launch_bounds__(NT, MINB)
     const int comp = blockIdx.z / nzchunks;
     const int chunk = blockIdx.z - comp * nzchunks;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int z_begin = chunk * zchunk;
-    const int z_end = min(z_begin + zchunk, g.S);
+    const int z_begin = g.zb + chunk * zchunk;
+    const int z_end = min(z_begin + zchunk, g.ze);
     const long long plane = static_cast<long long>(g.R) * g.C;
     const T *src = in + comp * g.N;
     T *dst = out + comp * g.N;
@@ -348,7 +351,8 @@ __global__ void __launch_bounds__(NT, MINB)
         }
     };
     auto stage = [&](int zp, int buf) {
-        if (zp < 0 || zp >= g.S) return;  // slice outside the grid: contributes zeros, nothing to load
+        // slice outside the GLOBAL grid: contributes zeros, nothing to load (a slab's halo planes are inside it)
+        if (zp + g.zoff < 0 || zp + g.zoff >= g.Sg || zp < 0 || zp >= g.S) return;
         T *sb = s_in + buf * PH * PW;
         const T *sp = src + zp * plane;
         if (VEC) {
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(NT, MINB)
         cp_async_commit();
         if (zp + 1 + DCMA_SMOOTH_PF <= zp_last) l2_prefetch(zp + 1 + DCMA_SMOOTH_PF);
 
-        slice_in = (zp >= 0 && zp < g.S);
+        slice_in = (zp + g.zoff >= 0 && zp + g.zoff < g.Sg && zp >= 0 && zp < g.S);
         zo = zp - R;
         if (slice_in) {
             const T *sb = s_in + buf * PH * PW;

@@ -38,6 +38,8 @@ class AlignViaDemonsParams:
     pyramid_levels: int = 1
     use_symmetric_force: bool = False
     fused: bool = True
+    n_devices: int = 0   # AlignViaDemons only: > 1 shards the volume into z-slabs over devices 0..n-1 of this process
+    halo_planes: int = 0
 
     def to_c(self) -> capi.Params:
         p = capi.default_params()
@@ -58,6 +60,8 @@ class AlignViaDemonsParams:
         p.pyramid_levels = int(self.pyramid_levels)
         p.use_symmetric_force = 1 if self.use_symmetric_force else 0
         p.fused = 1 if self.fused else 0
+        p.n_devices = int(self.n_devices)
+        p.halo_planes = int(self.halo_planes)
         return p
 
 
@@ -216,6 +220,106 @@ class DemonsEngine:
 
     def warp_moving(self):
         self._stage(capi.STAGE_WARP)
+
+
+def slab_partition(slices: int, world: int, rank: int, halo_planes: int):
+    """(zoff, local, own0, own1) of one z-slab: pure host arithmetic of the library (no GPU needed)."""
+    v = [C.c_int64(0) for _ in range(4)]
+    capi.check(capi.lib().dcma_b200_slab_partition(int(slices), int(world), int(rank), int(halo_planes),
+                                                   *[C.byref(x) for x in v]))
+    return tuple(int(x.value) for x in v)
+
+
+class DemonsSlabGroup:
+    """One registration sharded into z-slabs (BASELINE config 4): `DemonsSlabGroup.local(...)` drives
+    several engines from this process (peer copies), `DemonsSlabGroup.nccl(...)` is one rank of a multi-process run
+    (one process per GPU; halos by NCCL).  The reference has no counterpart (one address space, cc:171-187)."""
+
+    def __init__(self):
+        raise TypeError("use DemonsSlabGroup.local(...) or DemonsSlabGroup.nccl(...)")
+
+    @classmethod
+    def _new(cls, shape, spacing, params, channels):
+        self = cls.__new__(cls)
+        self._lib = capi.lib()
+        self.params = params
+        self.shape = tuple(int(v) for v in shape)
+        self.channels = int(channels)
+        self._geom = capi.Geom(self.shape[0], self.shape[1], self.shape[2], self.channels, float(spacing[0]),
+                               float(spacing[1]), float(spacing[2]))
+        self._cparams = params.to_c()
+        self._h = C.c_void_p()
+        return self
+
+    @classmethod
+    def local(cls, shape, spacing, params: AlignViaDemonsParams, devices, halo_planes: int = -1, channels: int = 1):
+        self = cls._new(shape, spacing, params, channels)
+        dev = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        err = C.create_string_buffer(512)
+        capi.check(self._lib.dcma_b200_slab_group_create_local(C.byref(self._h), C.byref(self._geom), C.byref(self._cparams),
+                                                               dev, len(devices), int(halo_planes), err, len(err)), err)
+        return self
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        err = C.create_string_buffer(512)
+        capi.check(capi.lib().dcma_b200_nccl_unique_id(buf, err, len(err)), err)
+        return bytes(buf)
+
+    @classmethod
+    def nccl(cls, shape, spacing, params: AlignViaDemonsParams, unique_id: bytes, rank: int, world: int, device: int,
+             halo_planes: int = -1, channels: int = 1):
+        self = cls._new(shape, spacing, params, channels)
+        buf = (C.c_ubyte * 128)(*unique_id)
+        err = C.create_string_buffer(512)
+        capi.check(self._lib.dcma_b200_slab_group_create_nccl(C.byref(self._h), C.byref(self._geom), C.byref(self._cparams),
+                                                              buf, int(rank), int(world), int(device), int(halo_planes),
+                                                              err, len(err)), err)
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dcma_b200_slab_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, fixed: np.ndarray, moving: np.ndarray):
+        """WHOLE volumes (host float32)."""
+        fixed = np.ascontiguousarray(fixed, dtype=np.float32)
+        moving = np.ascontiguousarray(moving, dtype=np.float32)
+        capi.check(self._lib.dcma_b200_slab_group_load(self._h, fixed.ctypes.data, moving.ctypes.data, 0))
+
+    def load_device(self, fixed_ptr: int, moving_ptr: int):
+        capi.check(self._lib.dcma_b200_slab_group_load(self._h, C.c_void_p(fixed_ptr), C.c_void_p(moving_ptr), 1))
+
+    def run(self, max_iterations: Optional[int] = None):
+        n = int(self.params.max_iterations if max_iterations is None else max_iterations)
+        hist = np.full(max(n, 1), np.nan, dtype=np.float64)
+        stats = capi.RunStats()
+        capi.check(self._lib.dcma_b200_slab_group_run(self._h, n, hist.ctypes.data, C.byref(stats)))
+        return hist[:stats.iterations_done].copy(), stats
+
+    def owned_range(self):
+        z0, z1 = C.c_int64(0), C.c_int64(0)
+        capi.check(self._lib.dcma_b200_slab_group_range(self._h, C.byref(z0), C.byref(z1)))
+        return int(z0.value), int(z1.value)
+
+    def get_deformation(self) -> np.ndarray:
+        """Deformation of the slices this process holds: (z1 - z0, rows, cols, 3) float64 mm."""
+        z0, z1 = self.owned_range()
+        out = np.empty((z1 - z0, self.shape[1], self.shape[2], 3), dtype=np.float64)
+        capi.check(self._lib.dcma_b200_slab_group_get_deformation(self._h, out.ctypes.data))
+        return out
+
+    @property
+    def halo_bytes(self) -> int:
+        return int(self._lib.dcma_b200_slab_group_halo_bytes(self._h))
 
 
 def AlignViaDemons(params: AlignViaDemonsParams, moving: demons_volume, stationary: demons_volume,

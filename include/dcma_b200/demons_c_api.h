@@ -75,7 +75,10 @@ typedef struct {
     int32_t pyramid_levels;      /* 1 = reference behaviour (single resolution) */
     int32_t use_symmetric_force; /* 0 = reference behaviour (fixed-image gradient only) */
     int32_t fused;               /* 1 (default) = fused loop kernels; 0 = one kernel per reference stage */
-    int32_t reserved[6];
+    int32_t n_devices;           /* dcma_b200_demons_register only: > 1 shards the volume into z-slabs over devices
+                                    0..n_devices-1 of this process (0/1 = single device, reference-like) */
+    int32_t halo_planes;         /* z-slab halo; 0 = default */
+    int32_t reserved[4];
 } dcma_b200_demons_params;
 
 /* Timing/launch statistics of one run (all device-timed with CUDA events on the engine's stream). */
@@ -158,6 +161,42 @@ DCMA_B200_API int dcma_b200_engine_export_deformation_device(dcma_b200_engine *e
 DCMA_B200_API int dcma_b200_engine_sync(dcma_b200_engine *e);
 /* Bytes of HBM the engine holds. */
 DCMA_B200_API int64_t dcma_b200_engine_device_bytes(const dcma_b200_engine *e);
+
+/* ---- one registration sharded into z-slabs over several GPUs (no counterpart in the reference, which keeps the whole
+ * volume in one address space, src/Alignment_Demons.cc:171-187; SURVEY.md 8(e), BASELINE config 4) ------------------
+ * Every slab engine holds its slices plus `halo_planes` planes per interior side; the moving image is replicated.  Per
+ * iteration the z-neighbours exchange halo planes before each stencil/gather stage and all slabs gather their MSE terms;
+ * the result equals the whole-volume engine's bit for bit.  halo_planes < 0 selects the default
+ * (max(smoothing radius along z, 8)); a composition gather that leaves the halo fails the run with DCMA_B200_ESTATE. */
+typedef struct dcma_b200_slab_group dcma_b200_slab_group;
+
+/* Pure host helper: the slab of `rank` -- local slice 0 is global slice *zoff, the engine holds *local slices and owns
+ * the local range [*own0, *own1). */
+DCMA_B200_API int dcma_b200_slab_partition(int64_t slices, int world, int rank, int64_t halo_planes, int64_t *zoff,
+                                           int64_t *local, int64_t *own0, int64_t *own1);
+/* One process drives `n_devices` engines (device ordinals may repeat); halos move by peer copies over NVLink. */
+DCMA_B200_API int dcma_b200_slab_group_create_local(dcma_b200_slab_group **out, const dcma_b200_geom *geom,
+                                                    const dcma_b200_demons_params *params, const int32_t *devices,
+                                                    int32_t n_devices, int64_t halo_planes, char *errbuf, size_t errbuf_len);
+/* One rank per process (the torchrun layout): rank 0 calls dcma_b200_nccl_unique_id and broadcasts the 128 bytes by
+ * any means; every rank then creates its part of the group.  Halos move by ncclSend/ncclRecv, MSE terms by
+ * ncclAllGather.  NCCL is loaded at run time (libnccl.so.2, or the path in DCMA_B200_NCCL_LIB). */
+DCMA_B200_API int dcma_b200_nccl_unique_id(unsigned char id[128], char *errbuf, size_t errbuf_len);
+DCMA_B200_API int dcma_b200_slab_group_create_nccl(dcma_b200_slab_group **out, const dcma_b200_geom *geom,
+                                                   const dcma_b200_demons_params *params, const unsigned char id[128],
+                                                   int32_t rank, int32_t world, int32_t device, int64_t halo_planes,
+                                                   char *errbuf, size_t errbuf_len);
+DCMA_B200_API void dcma_b200_slab_group_destroy(dcma_b200_slab_group *g);
+/* fixed / moving: WHOLE volumes (host pointers, or device pointers readable from every engine's device). */
+DCMA_B200_API int dcma_b200_slab_group_load(dcma_b200_slab_group *g, const float *fixed, const float *moving_on_fixed_grid,
+                                            int on_device);
+/* The loop of AlignViaDemons (cc:980-995) over all slabs; mse_history/stats as dcma_b200_engine_run. */
+DCMA_B200_API int dcma_b200_slab_group_run(dcma_b200_slab_group *g, int64_t max_iterations, double *mse_history,
+                                           dcma_b200_run_stats *stats);
+/* Slices [*z0, *z1) held by THIS process (everything for a local group) and their deformation, AoS doubles. */
+DCMA_B200_API int dcma_b200_slab_group_range(dcma_b200_slab_group *g, int64_t *z0, int64_t *z1);
+DCMA_B200_API int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deformation_out);
+DCMA_B200_API int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g); /* bytes exchanged by the last run */
 
 /* ---- warp an image with a deformation field on the same grid (warp_moving semantics, cc:467-550) ------------ */
 /* out[p] = image(p + D(p)) with the reference's strict validity rule; `oob_value` replaces NaN when finite

@@ -79,3 +79,24 @@ def test_radius_rule_matches_reference():
     assert parallel.smoothing_radius(1.5, 2.5) == 1
     assert parallel.smoothing_radius(0.1, 1.0) == 1
     assert parallel.smoothing_radius(0.0, 1.0) == 0
+
+
+def test_library_slab_partition_matches_python_partition():
+    """dcma_b200_slab_partition (pure host arithmetic of the C library, no GPU): owned ranges tile the volume, halos are
+    clipped at the global faces, and the owned ranges equal parallel.slab_partition."""
+    from dicomautomaton_b200 import capi, parallel
+    from dicomautomaton_b200.demons import slab_partition
+    for slices, world, halo in ((256, 8, 8), (37, 3, 4), (10, 1, 4), (64, 4, 0)):
+        ref = parallel.slab_partition(slices, world)
+        z = 0
+        for r in range(world):
+            zoff, local, own0, own1 = slab_partition(slices, world, r, halo)
+            assert (zoff + own0, zoff + own1) == ref[r]
+            assert zoff == max(0, ref[r][0] - halo) and zoff + local == min(slices, ref[r][1] + halo)
+            assert zoff + own0 == z
+            z = zoff + own1
+        assert z == slices
+    with pytest.raises(capi.DcmaError):
+        slab_partition(16, 4, 0, 8)   # slabs thinner than the halo
+    with pytest.raises(capi.DcmaError):
+        slab_partition(3, 4, 0, 0)    # more slabs than slices
