@@ -34,6 +34,7 @@ UNITS = {
     "engine_f64_strict.cu": ["-fmad=false"],
     "engine_f32.cu": [],
     "slab.cu": [],
+    "pyramid.cu": [],
     "c_api.cu": [],
 }
 

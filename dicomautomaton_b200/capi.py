@@ -35,7 +35,8 @@ class Params(C.Structure):
                 ("verbosity", C.c_int64),
                 ("field_mode", C.c_int32), ("device", C.c_int32), ("check_every", C.c_int32),
                 ("pyramid_levels", C.c_int32), ("use_symmetric_force", C.c_int32), ("fused", C.c_int32),
-                ("n_devices", C.c_int32), ("halo_planes", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("n_devices", C.c_int32), ("halo_planes", C.c_int32), ("pyramid_iterations", C.c_int32 * 3),
+                ("reserved", C.c_int32 * 1)]
 
 
 class RunStats(C.Structure):
@@ -64,6 +65,8 @@ SYMBOLS = {
     "dcma_b200_engine_sync": (C.c_int, [_vp]),
     "dcma_b200_engine_device_bytes": (C.c_int64, [_vp]),
     "dcma_b200_warp_image": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, _cp, C.c_size_t]),
+    "dcma_b200_restrict_image": (C.c_int, [C.POINTER(Geom), _vp, C.POINTER(Geom), _vp, C.c_int, _cp, C.c_size_t]),
+    "dcma_b200_prolong_field": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_slab_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, _ip, _ip, _ip, _ip]),
     "dcma_b200_slab_group_create_local": (C.c_int, [C.POINTER(_vp), C.POINTER(Geom), C.POINTER(Params),
                                                     C.POINTER(C.c_int32), C.c_int32, C.c_int64, _cp, C.c_size_t]),

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "engine.h"
+#include "pyramid.h"
 #include "slab.h"
 
 struct dcma_b200_engine {
@@ -24,8 +25,8 @@ struct dcma_b200_slab_group {
 
 namespace dcma {
 EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab) {
-    if (p.pyramid_levels > 1 || p.use_symmetric_force)
-        throw std::invalid_argument("pyramid_levels > 1 / use_symmetric_force are not available at the engine level");
+    if (p.pyramid_levels > 1)
+        throw std::invalid_argument("pyramid_levels > 1 is a property of dcma_b200_demons_register, not of one engine");
     switch (p.field_mode) {
         case DCMA_B200_FIELD_FP64: return make_engine_f64(g, p, stream, slab);
         case DCMA_B200_FIELD_FP64_STRICT: return make_engine_f64_strict(g, p, stream, slab);
@@ -114,6 +115,7 @@ void dcma_b200_demons_params_default(dcma_b200_demons_params *p) {
     p->fused = 1;
     p->n_devices = 0;
     p->halo_planes = 0;
+    p->pyramid_iterations[0] = p->pyramid_iterations[1] = p->pyramid_iterations[2] = 0;
 }
 
 int dcma_b200_engine_create(dcma_b200_engine **out, const dcma_b200_geom *geom, const dcma_b200_demons_params *params,
@@ -188,6 +190,19 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
                 dcma::EngineBase *p = nullptr;
                 ~Holder() { delete p; }
             } h;
+            if (params->pyramid_levels > 1) {
+                const auto s0 = clk::now();
+                dcma_b200_run_stats local;
+                dcma::pyramid_register(*geom, fixed, moving, *params, deformation_out, mse_history, &local);
+                if (stats) {
+                    *stats = local;
+                    const long long n = geom->slices * geom->rows * geom->cols;
+                    stats->h2d_bytes = 2 * n * geom->channels * static_cast<long long>(sizeof(float));
+                    stats->d2h_bytes = 3 * n * static_cast<long long>(sizeof(double));
+                    stats->h2d_ms = std::chrono::duration<double, std::milli>(clk::now() - s0).count() - local.loop_ms;
+                }
+                return;
+            }
             if (params->n_devices > 1) {
                 // the volume is sharded into z-slabs over devices 0..n_devices-1 of this process
                 std::vector<int> dev(params->n_devices);
@@ -301,6 +316,18 @@ int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deform
 }
 
 int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g) { return g ? g->impl->halo_bytes_last_run() : 0; }
+
+int dcma_b200_restrict_image(const dcma_b200_geom *fine, const float *image, dcma_b200_geom *coarse, float *out, int device,
+                             char *errbuf, size_t errbuf_len) {
+    if (!fine || !coarse || (out && !image)) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded([&]() { dcma::restrict_image_host(*fine, image, coarse, out, device); }, errbuf, errbuf_len);
+}
+
+int dcma_b200_prolong_field(const dcma_b200_geom *fine, const double *coarse_field, double *out, int device, char *errbuf,
+                            size_t errbuf_len) {
+    if (!fine || !coarse_field || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded([&]() { dcma::prolong_field_host(*fine, coarse_field, out, device); }, errbuf, errbuf_len);
+}
 
 int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
                          int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len) {

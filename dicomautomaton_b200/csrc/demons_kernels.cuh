@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
                  const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
                  const ForceK fk, double *part_sum, long long *part_cnt, Ctrl *ctrl, const long long it,
-                 const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter) {
+                 const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter,
+                 const int symmetric /* extension a11: J = (grad F + grad W)/2; needs w_src == 2 */) {
     using CT = T;  // compute type of coordinates / interpolation / force == field storage type
     if (it > ctrl->converged_at) return;
     CT acc = 0;
@@ -452,6 +453,11 @@ __global__ void __launch_bounds__(kTileX *kTileY)
             }
             float f_prev = __ldg(F + (z_begin + g.zoff > 0 ? v - plane : v) * ch);
             float f_cur = __ldg(F + v * ch);
+            float w_prev = 0.f, w_cur = 0.f;  // rolling z stencil of W (symmetric force only)
+            if (symmetric) {
+                w_prev = __ldg(Wbuf + (z_begin + g.zoff > 0 ? v - plane : v) * ch);
+                w_cur = __ldg(Wbuf + v * ch);
+            }
             // L2 prefetch, one instruction per warp and step: a tile row is one warp, and lane l asks for ONE line of
             // the row kPrefetchAhead slices ahead -- lane 0: F, lane 1: M (or W), lanes 2..: the lines of D's components.
             constexpr int NL = (sizeof(T) * kTileX + 127) / 128;  // 128-byte lines per field row segment
@@ -502,6 +508,23 @@ __global__ void __launch_bounds__(kTileX *kTileY)
                 }
                 CT gx, gy, gz;
                 grad_fixed(st, gk.sx, gk.sy, gx, gy, gz);
+                if (symmetric) {
+                    // gradient of the warped image by the same rule (central difference in index units, one-sided at
+                    // the borders, zero next to a non-finite voxel), then the mean of the two gradients
+                    Stencil sw;
+                    load_stencil_xy<IX>(sw, Wbuf + v * ch, gk);
+                    const float w_next = (z + g.zoff + 1 < g.Sg) ? __ldg(Wbuf + v * ch + pch) : w_cur;
+                    sw.zp = w_prev;
+                    sw.zn = w_next;
+                    sw.sz = st.sz;
+                    CT hx, hy, hz;
+                    grad_fixed(sw, gk.sx, gk.sy, hx, hy, hz);
+                    gx = (gx + hx) * CT(0.5);
+                    gy = (gy + hy) * CT(0.5);
+                    gz = (gz + hz) * CT(0.5);
+                    w_prev = w_cur;
+                    w_cur = w_next;
+                }
                 CT ux, uy, uz, term;
                 int valid;
                 demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);

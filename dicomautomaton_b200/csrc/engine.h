@@ -41,6 +41,9 @@ class EngineBase {
     virtual void get(int buffer, void *host) = 0;
     virtual void set(int buffer, const void *host) = 0;
     virtual void export_deformation_device(double *device_out) = 0;
+    virtual void import_deformation_device(const double *device_aos) = 0;  // warm start: D := field, W := warp(M, D)
+    virtual const float *fixed_dev() const = 0;
+    virtual const float *moving_dev() const = 0;
     virtual void sync() = 0;
     virtual int64_t device_bytes() const = 0;
     virtual int device() const = 0;

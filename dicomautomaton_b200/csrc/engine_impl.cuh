@@ -45,6 +45,8 @@ class Engine final : public EngineBase {
             throw std::invalid_argument("voxel spacing must be > 0");
         if (geom.slices > (1 << 19) || geom.rows > (1 << 19) || geom.cols > (1 << 19))
             throw std::invalid_argument("volume extent too large");
+        if (slab_.local > 0 && slab_.local != geom.slices && p_.use_symmetric_force)
+            throw std::invalid_argument("use_symmetric_force is not available with z-slab sharding yet (W needs a z halo)");
         if (slab_.local <= 0) slab_ = SlabSpec{0, geom.slices, 0, geom.slices};  // whole volume
         if (slab_.zoff < 0 || slab_.zoff + slab_.local > geom.slices || slab_.own0 < 0 || slab_.own1 > slab_.local ||
             slab_.own0 >= slab_.own1)
@@ -400,6 +402,16 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaGetLastError());
     }
 
+    // warm start (pyramid): D := the given field; the next force evaluation warps M through it
+    void import_deformation_device(const double *device_aos) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(device_aos, dD_, g_.N, owned_v0(), owned_v1());
+        DCMA_CUDA(cudaGetLastError());
+        w_src_ = 1;
+    }
+    const float *fixed_dev() const override { return dF_; }
+    const float *moving_dev() const override { return dM_; }
+
     // export_deformation_volume (cc:110-113): SoA T -> the reference's AoS double layout, converted chunk by chunk
     // through two small staging buffers so that no field-sized allocation is made and the conversion of chunk i+1
     // overlaps the PCIe copy of chunk i (the copy engine and the SMs work on different staging halves).
@@ -562,7 +574,15 @@ class Engine final : public EngineBase {
     // compute_single_iteration, cc:81-108, with warp_moving moved to the front of the NEXT iteration's force kernel.
     void iteration(long long it, double *d_hist) {
         const bool diffeo = (p_.use_diffeomorphic != 0);
-        if (p_.fused) {
+        if (p_.use_symmetric_force) {
+            // the symmetric force needs the gradient of W, i.e. W in memory with its neighbours (extension, row a11)
+            prof_begin(DCMA_B200_STAGE_WARP);
+            materialise_warped();
+            prof_end();
+            prof_begin(DCMA_B200_STAGE_FORCE);
+            launch_force(2, it, d_hist, it, 1, /*reduce=*/false, /*fused_reduce=*/true);
+            prof_end();
+        } else if (p_.fused) {
             prof_begin(DCMA_B200_STAGE_FORCE);
             launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false, /*fused_reduce=*/true);
             prof_end();
@@ -577,7 +597,7 @@ class Engine final : public EngineBase {
             launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false);
             prof_end();
         }
-        if (!p_.fused) {
+        if (!p_.fused && !p_.use_symmetric_force) {
             prof_begin(DCMA_B200_STAGE_REDUCE);
             launch_reduce(it, d_hist, it, 1);
             prof_end();
@@ -616,7 +636,7 @@ class Engine final : public EngineBase {
 #define DCMA_LAUNCH_FORCE(IX, CH1)                                                                                   \
     k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
                                                                   d_part_cnt_, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
-                                                                  hist_idx, count_iter)
+                                                                  hist_idx, count_iter, (p_.use_symmetric_force && w_src == 2) ? 1 : 0)
         if (small_index_) {
             if (g_.CH == 1) DCMA_LAUNCH_FORCE(int, true); else DCMA_LAUNCH_FORCE(int, false);
         } else {

@@ -38,6 +38,7 @@ class AlignViaDemonsParams:
     pyramid_levels: int = 1
     use_symmetric_force: bool = False
     fused: bool = True
+    pyramid_iterations: tuple = (0, 0, 0)  # iterations at pyramid levels 1..3 (0 = max_iterations)
     n_devices: int = 0   # AlignViaDemons only: > 1 shards the volume into z-slabs over devices 0..n-1 of this process
     halo_planes: int = 0
 
@@ -62,6 +63,8 @@ class AlignViaDemonsParams:
         p.fused = 1 if self.fused else 0
         p.n_devices = int(self.n_devices)
         p.halo_planes = int(self.halo_planes)
+        for i in range(3):
+            p.pyramid_iterations[i] = int(self.pyramid_iterations[i]) if i < len(self.pyramid_iterations) else 0
         return p
 
 
@@ -222,6 +225,29 @@ class DemonsEngine:
         self._stage(capi.STAGE_WARP)
 
 
+def restrict_image(image: demons_volume, device: int = -1) -> demons_volume:
+    """Next-coarser pyramid level of an image (extension a12; definition in csrc/pyramid.cu)."""
+    lib = capi.lib()
+    img = _as_f32(image)
+    g, gc = image.geom(), capi.Geom()
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_restrict_image(C.byref(g), None, C.byref(gc), None, device, err, len(err)), err)
+    out = np.empty((gc.slices, gc.rows, gc.cols, gc.channels), dtype=np.float32)
+    capi.check(lib.dcma_b200_restrict_image(C.byref(g), img.ctypes.data, C.byref(gc), out.ctypes.data, device, err, len(err)), err)
+    return demons_volume(out, gc.pxl_dx, gc.pxl_dy, gc.pxl_dz)
+
+
+def prolong_field(coarse_field: np.ndarray, fine: demons_volume, device: int = -1) -> np.ndarray:
+    """Trilinear prolongation of a displacement field from the next-coarser level onto the grid of `fine`."""
+    lib = capi.lib()
+    cf = np.ascontiguousarray(coarse_field, dtype=np.float64)
+    out = np.empty(fine.data.shape[:3] + (3,), dtype=np.float64)
+    g = fine.geom()
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_prolong_field(C.byref(g), cf.ctypes.data, out.ctypes.data, device, err, len(err)), err)
+    return out
+
+
 def slab_partition(slices: int, world: int, rank: int, halo_planes: int):
     """(zoff, local, own0, own1) of one z-slab: pure host arithmetic of the library (no GPU needed)."""
     v = [C.c_int64(0) for _ in range(4)]
@@ -340,7 +366,12 @@ def AlignViaDemons(params: AlignViaDemonsParams, moving: demons_volume, stationa
         geom = stationary.geom()
         cp = params.to_c()
         D = np.empty(stationary.data.shape[:3] + (3,), dtype=np.float64)
-        hist = np.full(max(int(params.max_iterations), 1), np.nan, dtype=np.float64)
+        # one entry per iteration of every pyramid level (coarse levels first)
+        n_hist = int(params.max_iterations)
+        for l in range(1, int(params.pyramid_levels)):
+            extra = int(params.pyramid_iterations[l - 1]) if l - 1 < len(params.pyramid_iterations) else 0
+            n_hist += extra if extra > 0 else int(params.max_iterations)
+        hist = np.full(max(n_hist, 1), np.nan, dtype=np.float64)
         stats = capi.RunStats()
         err = C.create_string_buffer(512)
         capi.check(lib.dcma_b200_demons_register(C.byref(geom), f.ctypes.data, m.ctypes.data, C.byref(cp),

@@ -175,6 +175,10 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
         p.device = params.device;
         p.pyramid_levels = params.pyramid_levels;
         p.use_symmetric_force = params.use_symmetric_force ? 1 : 0;
+        for (int i = 0; i < 3; ++i) p.pyramid_iterations[i] = params.pyramid_iterations[i];
+        p.n_devices = params.n_devices;
+        if (const char *e = std::getenv("DCMA_B200_DEVICES")) p.n_devices = std::atoi(e);  // site policy: GPUs to shard over
+        p.halo_planes = params.halo_planes;
 
         demons_volume<double> def;
         def.slices = fixed_vol.slices;

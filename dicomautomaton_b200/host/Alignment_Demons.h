@@ -44,6 +44,9 @@ struct AlignViaDemonsParams {
     int32_t device = -1;              // CUDA device ordinal, -1 = current
     int32_t pyramid_levels = 1;       // multi-resolution levels (1 = single resolution, as the reference)
     bool use_symmetric_force = false; // (grad F + grad W)/2 in the force (false = fixed-image gradient, as the reference)
+    int32_t pyramid_iterations[3] = {0, 0, 0};  // iterations at pyramid levels 1..3 (0 = max_iterations)
+    int32_t n_devices = 0;            // > 1: shard the volume into z-slabs over GPUs 0..n_devices-1 of this process
+    int32_t halo_planes = 0;          // z-slab halo (0 = default)
 };
 
 // Dense proxy of a regular image stack (reference :64-74).

@@ -72,13 +72,16 @@ typedef struct {
     int32_t field_mode;          /* dcma_b200_field_mode; default DCMA_B200_FIELD_FP64 */
     int32_t device;              /* CUDA device ordinal; -1 = current device */
     int32_t check_every;         /* iterations between host polls of the device-side convergence flag; 0 = auto */
-    int32_t pyramid_levels;      /* 1 = reference behaviour (single resolution) */
-    int32_t use_symmetric_force; /* 0 = reference behaviour (fixed-image gradient only) */
+    int32_t pyramid_levels;      /* 1 = reference behaviour (single resolution); 2..4: dcma_b200_demons_register runs a
+                                    coarse-to-fine pyramid (definition: dicomautomaton_b200/csrc/pyramid.cu) */
+    int32_t use_symmetric_force; /* 0 = reference behaviour (fixed-image gradient only); 1: the force uses
+                                    J = (grad F + grad W) / 2, grad W by the rule of cc:232-265 applied to the warped image */
     int32_t fused;               /* 1 (default) = fused loop kernels; 0 = one kernel per reference stage */
     int32_t n_devices;           /* dcma_b200_demons_register only: > 1 shards the volume into z-slabs over devices
                                     0..n_devices-1 of this process (0/1 = single device, reference-like) */
     int32_t halo_planes;         /* z-slab halo; 0 = default */
-    int32_t reserved[4];
+    int32_t pyramid_iterations[3]; /* iterations at pyramid levels 1..3 (coarser than the finest); 0 = max_iterations */
+    int32_t reserved[1];
 } dcma_b200_demons_params;
 
 /* Timing/launch statistics of one run (all device-timed with CUDA events on the engine's stream). */
@@ -124,7 +127,8 @@ DCMA_B200_API void dcma_b200_demons_params_default(dcma_b200_demons_params *p); 
 /* Replaces, inside AlignViaDemons, the block  `sycl_demons_engine engine(fixed_vol, moving_vol, params); for(iter...)
  * { engine.compute_single_iteration(); ... } engine.export_deformation_volume()`  (src/Alignment_Demons.cc:977-997).
  * `moving_on_fixed_grid` is the moving image after resample_image_to_reference_grid / histogram_match (cc:964-972).
- * deformation_out: N*3 doubles (AoS z,y,x,c).  mse_history: max_iterations doubles or NULL.  stats may be NULL.
+ * deformation_out: N*3 doubles (AoS z,y,x,c).  mse_history: max_iterations doubles (with pyramid_levels > 1: the sum of
+ * the levels' iteration limits, coarse levels first) or NULL.  stats may be NULL.
  * Blocking; H2D and D2H copies happen inside the call. */
 DCMA_B200_API int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, const float *moving_on_fixed_grid,
                               const dcma_b200_demons_params *params, double *deformation_out, double *mse_history,
@@ -197,6 +201,15 @@ DCMA_B200_API int dcma_b200_slab_group_run(dcma_b200_slab_group *g, int64_t max_
 DCMA_B200_API int dcma_b200_slab_group_range(dcma_b200_slab_group *g, int64_t *z0, int64_t *z1);
 DCMA_B200_API int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deformation_out);
 DCMA_B200_API int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g); /* bytes exchanged by the last run */
+
+/* ---- pyramid building blocks (extension; host buffers) ------------------------------------------------------- */
+/* Next-coarser level of `image`: every axis with extent >= 8 is halved (mean of the finite voxels of each block).
+ * *coarse receives the coarse geometry; `out` may be NULL to query the geometry only. */
+DCMA_B200_API int dcma_b200_restrict_image(const dcma_b200_geom *fine, const float *image, dcma_b200_geom *coarse, float *out,
+                                           int device, char *errbuf, size_t errbuf_len);
+/* Trilinear prolongation of a displacement field (AoS doubles, mm) from the next-coarser level onto `fine`. */
+DCMA_B200_API int dcma_b200_prolong_field(const dcma_b200_geom *fine, const double *coarse_field, double *out, int device,
+                                          char *errbuf, size_t errbuf_len);
 
 /* ---- warp an image with a deformation field on the same grid (warp_moving semantics, cc:467-550) ------------ */
 /* out[p] = image(p + D(p)) with the reference's strict validity rule; `oob_value` replaces NaN when finite

@@ -1,0 +1,163 @@
+"""TEST INFRASTRUCTURE ONLY: CPU restatement (numpy, fp64) of the two EXTENSIONS that have no counterpart in the
+reference -- the symmetric Demons force and the multi-resolution pyramid (row a12).
+
+**Parity unpinned**: `AlignViaDemonsParams` (/root/reference/src/Alignment_Demons.h:20-61) has neither option and the
+reference's tests hold nothing for them, so there is no reference output to compare with.  What IS pinned: every stage
+these loops are assembled from (gradient rule, smoothing, composition, warp) is the pinned oracle engine of
+`oracle/__init__.py`; only the few lines below (mean of two gradients; block mean; trilinear prolongation) are ours, and
+they restate the definitions documented in dicomautomaton_b200/csrc/pyramid.cu and demons_kernels.cuh.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import OracleEngine, make_params
+
+
+def gradient_rule(img: np.ndarray) -> np.ndarray:
+    """compute_gradient's rule (reference src/Alignment_Demons.cc:232-265) applied to a (S,R,C) float image:
+    (v[+1] - v[-1]) / (index distance) with clamped neighbours, 0 where a neighbour is non-finite or the extent is 1."""
+    v = img.astype(np.float64)
+    out = np.zeros(v.shape + (3,), dtype=np.float64)
+    for comp, axis in ((0, 2), (1, 1), (2, 0)):  # x <-> columns, y <-> rows, z <-> slices
+        n = v.shape[axis]
+        if n <= 1:
+            continue
+        idx = np.arange(n)
+        lo, hi = np.maximum(idx - 1, 0), np.minimum(idx + 1, n - 1)
+        a, b = np.take(v, hi, axis=axis), np.take(v, lo, axis=axis)
+        shape = [1, 1, 1]
+        shape[axis] = n
+        dist = (hi - lo).astype(np.float64).reshape(shape)
+        with np.errstate(invalid="ignore"):
+            g = (a - b) / dist
+        g[~(np.isfinite(a) & np.isfinite(b))] = 0.0
+        out[..., comp] = g
+    return out
+
+
+def symmetric_force(fixed, warped, grad_fixed, normalization_factor=1.0, max_update_magnitude=2.0):
+    """compute_update_and_mse (cc:291-330) with J = (grad F + grad W) / 2 in place of grad F.  Returns (U, mse, n)."""
+    f, w = fixed.astype(np.float64), warped.astype(np.float64)
+    valid = np.isfinite(fixed) & np.isfinite(warped)
+    J = (grad_fixed + gradient_rule(warped)) * 0.5
+    with np.errstate(invalid="ignore", over="ignore"):
+        diff = np.where(valid, f - w, 0.0)
+        gmag = J[..., 0] * J[..., 0] + J[..., 1] * J[..., 1] + J[..., 2] * J[..., 2]
+        denom = gmag + (diff * diff) / (normalization_factor + 1.0e-10)
+        ok = valid & (denom > 1.0e-10)
+        safe = np.where(ok, denom, 1.0)
+        U = np.where(ok[..., None], diff[..., None] * J / safe[..., None], 0.0)
+        mag = np.sqrt(U[..., 0] * U[..., 0] + U[..., 1] * U[..., 1] + U[..., 2] * U[..., 2])
+        scale = np.where(mag > max_update_magnitude, max_update_magnitude / np.where(mag > 0, mag, 1.0), 1.0)
+        U = np.where((mag > max_update_magnitude)[..., None], U * scale[..., None], U)
+    n = int(valid.sum())
+    mse = float((diff * diff)[valid].sum() / n) if n > 0 else 0.0
+    return U, mse, n
+
+
+def run_level(fixed, moving, spacing, iters, sigma_d, sigma_u, diffeo, symmetric, D0=None, normalization_factor=1.0,
+              max_update_magnitude=2.0):
+    """The loop of one level (threshold 0) assembled from the pinned oracle stages; D0 = warm start (mm)."""
+    par = make_params(max_iterations=iters, convergence_threshold=0.0, deformation_field_smoothing_sigma=sigma_d,
+                      update_field_smoothing_sigma=sigma_u, use_diffeomorphic=diffeo,
+                      normalization_factor=normalization_factor, max_update_magnitude=max_update_magnitude)
+    E = OracleEngine(fixed, moving, par, spacing, kind="port")
+    hist = []
+    try:
+        if D0 is not None:
+            E.set("deformation", D0)
+            E.warp_moving()  # W := warp(M, D0); W := M only holds for D = 0
+        G = E.get("gradient")
+        for _ in range(iters):
+            if symmetric:
+                U, mse, _ = symmetric_force(E.get("fixed")[..., 0], E.get("warped")[..., 0], G, normalization_factor,
+                                            max_update_magnitude)
+                E.set("update", U)
+            else:
+                mse, _ = E.compute_update_and_mse()
+            hist.append(mse)
+            if diffeo and sigma_u > 0:
+                E.smooth_update(sigma_u)
+            if diffeo:
+                E.add_update_diffeomorphic()
+            else:
+                E.add_update()
+            if sigma_d > 0:
+                E.smooth_deformation(sigma_d)
+            E.warp_moving()
+        return E.get("deformation"), np.array(hist)
+    finally:
+        E.close()
+
+
+def coarsen(shape, spacing):
+    """(coarse shape, coarse spacing (dx,dy,dz), halved flags (z,y,x)): axes with extent >= 8 are halved."""
+    s, r, c = shape
+    hz, hy, hx = s >= 8, r >= 8, c >= 8
+    cs = ((s + 1) // 2 if hz else s, (r + 1) // 2 if hy else r, (c + 1) // 2 if hx else c)
+    sp = (spacing[0] * (2.0 if hx else 1.0), spacing[1] * (2.0 if hy else 1.0), spacing[2] * (2.0 if hz else 1.0))
+    return cs, sp, (hz, hy, hx)
+
+
+def restrict(img: np.ndarray):
+    """Mean of the finite voxels of each 2x2x2 block (2 or 1 along kept axes), double accumulation in z,y,x order."""
+    s, r, c = img.shape
+    (cs, cr, cc), _, (hz, hy, hx) = coarsen(img.shape, (1, 1, 1))
+    acc = np.zeros((cs, cr, cc), dtype=np.float64)
+    cnt = np.zeros((cs, cr, cc), dtype=np.int64)
+    for dz in range(2 if hz else 1):
+        for dy in range(2 if hy else 1):
+            for dx in range(2 if hx else 1):
+                sub = img[dz::2 if hz else 1, dy::2 if hy else 1, dx::2 if hx else 1].astype(np.float64)
+                fin = np.isfinite(sub)
+                a = np.zeros_like(acc)
+                k = np.zeros_like(cnt)
+                a[:sub.shape[0], :sub.shape[1], :sub.shape[2]] = np.where(fin, sub, 0.0)
+                k[:sub.shape[0], :sub.shape[1], :sub.shape[2]] = fin
+                acc = acc + a
+                cnt = cnt + k
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = np.where(cnt > 0, acc / cnt, np.nan)
+    return out.astype(np.float32)
+
+
+def prolong(coarse_field: np.ndarray, fine_shape):
+    """Trilinear sampling of the coarse field at u = x/2 - 1/4 (halved axes) clamped to the coarse grid."""
+    _, _, (hz, hy, hx) = coarsen(fine_shape, (1, 1, 1))
+
+    def axis(n_f, n_c, halved):
+        x = np.arange(n_f, dtype=np.float64)
+        u = 0.5 * x - 0.25 if halved else x
+        u = np.minimum(np.maximum(u, 0.0), float(n_c - 1))
+        f = np.floor(u)
+        i0 = f.astype(np.int64)
+        return i0, np.minimum(i0 + 1, n_c - 1), u - f
+
+    z0, z1, tz = axis(fine_shape[0], coarse_field.shape[0], hz)
+    y0, y1, ty = axis(fine_shape[1], coarse_field.shape[1], hy)
+    x0, x1, tx = axis(fine_shape[2], coarse_field.shape[2], hx)
+    tz, ty, tx = tz[:, None, None, None], ty[None, :, None, None], tx[None, None, :, None]
+    g = lambda zz, yy, xx: coarse_field[zz][:, yy][:, :, xx]
+    c00 = g(z0, y0, x0) * (1.0 - tx) + g(z0, y0, x1) * tx
+    c10 = g(z0, y1, x0) * (1.0 - tx) + g(z0, y1, x1) * tx
+    c01 = g(z1, y0, x0) * (1.0 - tx) + g(z1, y0, x1) * tx
+    c11 = g(z1, y1, x0) * (1.0 - tx) + g(z1, y1, x1) * tx
+    c0 = c00 * (1.0 - ty) + c10 * ty
+    c1 = c01 * (1.0 - ty) + c11 * ty
+    return c0 * (1.0 - tz) + c1 * tz
+
+
+def pyramid_run(fixed, moving, spacing, levels, iters_per_level, sigma_d, sigma_u, diffeo, symmetric):
+    """iters_per_level[l] for level l (0 = finest).  Returns (D at the finest level, concatenated MSE history)."""
+    F, M, SP = [fixed], [moving], [tuple(spacing)]
+    for _ in range(1, levels):
+        F.append(restrict(F[-1]))
+        M.append(restrict(M[-1]))
+        SP.append(coarsen(F[-2].shape, SP[-1])[1])
+    D, hist = None, []
+    for l in range(levels - 1, -1, -1):
+        D0 = prolong(D, F[l].shape) if D is not None else None
+        D, h = run_level(F[l], M[l], SP[l], iters_per_level[l], sigma_d, sigma_u, diffeo, symmetric, D0)
+        hist.extend(h.tolist())
+    return D, np.array(hist)

@@ -1,0 +1,112 @@
+"""The two EXTENSIONS (no reference counterpart, "parity unpinned"): symmetric force (row a11) and the multi-resolution
+pyramid (row a12).  Checked against oracle/extensions.py -- our own CPU restatement assembled from the pinned oracle
+stages -- and by properties: the defaults reproduce the reference path exactly, the pyramid recovers a large warp that
+the single-resolution loop does not, and the result then warps a co-registered dose grid (BASELINE config 3)."""
+import numpy as np
+import pytest
+
+from _helpers import phantom_pair, random_smooth_field
+
+pytestmark = pytest.mark.gpu
+
+
+def _par(mode, iters, sigma, diffeo, **kw):
+    from dicomautomaton_b200.demons import AlignViaDemonsParams
+    return AlignViaDemonsParams(max_iterations=iters, convergence_threshold=0.0, deformation_field_smoothing_sigma=sigma,
+                                update_field_smoothing_sigma=sigma, use_diffeomorphic=diffeo, verbosity=0, field_mode=mode, **kw)
+
+
+def _run(par, F, M, sp):
+    from dicomautomaton_b200.demons import AlignViaDemons, demons_volume
+    out, hist, st = AlignViaDemons(par, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
+    assert out is not None
+    return out.data, hist, st
+
+
+@pytest.mark.parametrize("diffeo", [False, True])
+@pytest.mark.parametrize("shape,sp", [((14, 24, 28), (1.0, 1.0, 1.0)), ((1, 24, 28), (1.0, 1.0, 1.0)), ((9, 21, 19), (0.9, 1.1, 2.5))])
+def test_symmetric_force_matches_the_cpu_restatement(oracle_mod, diffeo, shape, sp):
+    from oracle import extensions as ext
+    F, M = phantom_pair(shape, sp)
+    iters, sigma = 8, 1.5
+    Do, ho = ext.run_level(F, M, sp, iters, sigma, sigma, diffeo, symmetric=True)
+    for mode, tol in (("fp64_strict", 1e-12), ("fp64", 1e-9), ("fp32", 1e-4)):
+        D, h, st = _run(_par(mode, iters, sigma, diffeo, use_symmetric_force=True), F, M, sp)
+        assert st.iterations_done == iters
+        assert np.array_equal(np.isnan(D), np.isnan(Do))
+        assert np.nanmax(np.abs(D - Do)) <= tol, (mode, np.nanmax(np.abs(D - Do)))
+        assert np.max(np.abs(h - ho) / ho) <= (1e-4 if mode == "fp32" else 1e-10)
+
+
+def test_symmetric_force_changes_the_result_and_default_is_off():
+    shape, sp = (12, 24, 28), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp)
+    a, _, _ = _run(_par("fp64", 6, 1.5, True), F, M, sp)
+    b, _, _ = _run(_par("fp64", 6, 1.5, True, use_symmetric_force=False, pyramid_levels=1), F, M, sp)
+    c, _, _ = _run(_par("fp64", 6, 1.5, True, use_symmetric_force=True), F, M, sp)
+    assert np.array_equal(a, b)
+    assert np.abs(a - c).max() > 1e-3
+
+
+@pytest.mark.parametrize("shape", [(16, 24, 40), (7, 33, 18), (1, 20, 26), (9, 9, 9)])
+def test_restrict_and_prolong_match_the_cpu_restatement(shape):
+    from dicomautomaton_b200.demons import demons_volume, prolong_field, restrict_image
+    from oracle import extensions as ext
+    sp = (0.8, 1.0, 2.0)
+    F, _ = phantom_pair(shape, sp)
+    F = F.copy()
+    F[0, 0, :3] = np.nan  # non-finite voxels are left out of the block mean
+    c = restrict_image(demons_volume(F, *sp))
+    cs, csp, _ = ext.coarsen(shape, sp)
+    assert c.data.shape[:3] == cs
+    assert (c.pxl_dx, c.pxl_dy, c.pxl_dz) == csp
+    assert np.array_equal(c.data[..., 0], ext.restrict(F), equal_nan=True)
+    Dc = random_smooth_field(cs, 3.0, seed=2)
+    got = prolong_field(Dc, demons_volume(F, *sp))
+    assert np.abs(got - ext.prolong(Dc, shape)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_pyramid_matches_the_cpu_restatement(oracle_mod, symmetric):
+    from oracle import extensions as ext
+    shape, sp = (24, 40, 48), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp, amplitude_mm=4.0)
+    iters = (5, 7, 9)  # finest, level 1, level 2
+    Do, ho = ext.pyramid_run(F, M, sp, 3, iters, 1.5, 1.5, True, symmetric)
+    for mode, tol in (("fp64_strict", 1e-11), ("fp64", 1e-8)):
+        D, h, st = _run(_par(mode, iters[0], 1.5, True, pyramid_levels=3, pyramid_iterations=(iters[1], iters[2], 0),
+                             use_symmetric_force=symmetric), F, M, sp)
+        assert st.iterations_done == sum(iters)
+        assert np.nanmax(np.abs(D - Do)) <= tol, (mode, np.nanmax(np.abs(D - Do)))
+        assert np.max(np.abs(h - ho) / ho) <= 1e-9
+
+
+def test_pyramid_recovers_a_large_warp_and_the_field_warps_a_dose_grid():
+    """BASELINE config 3 in small: 3-level pyramid + symmetric force on a pair whose warp (6 mm) is beyond the capture
+    range of the single-resolution loop, then the result warps a co-registered dose grid (out-of-bounds -> 0.0, the
+    WarpImages rule, reference src/Operations/WarpImages.cc:197,452)."""
+    import torch
+    from dicomautomaton_b200 import phantom
+    from dicomautomaton_b200.demons import demons_volume, warp_image_with_field
+    shape, sp = (48, 64, 64), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp, amplitude_mm=6.0)
+    single, hs, _ = _run(_par("fp32", 60, 1.5, True), F, M, sp)
+    pyr, hp, st = _run(_par("fp32", 20, 1.5, True, pyramid_levels=3, pyramid_iterations=(20, 20, 0), use_symmetric_force=True), F, M, sp)
+    assert st.iterations_done == 60
+    z = torch.arange(shape[0], dtype=torch.float64).view(-1, 1, 1)
+    y = torch.arange(shape[1], dtype=torch.float64).view(1, -1, 1)
+    x = torch.arange(shape[2], dtype=torch.float64).view(1, 1, -1)
+    w = torch.stack(torch.broadcast_tensors(*phantom.known_warp_mm(x, y, z, shape, amplitude_mm=6.0)), -1).numpy()
+    core = (slice(8, -8),) * 3
+    err_single = np.sqrt(((single + w)[core] ** 2).mean())
+    err_pyr = np.sqrt(((pyr + w)[core] ** 2).mean())
+    # better match of the images for the same number of iterations, with a field at least as close to the first-order
+    # estimate -w of the known warp (for a 6 mm warp -w is only an approximation of the ideal field D(p) = -w(p + D(p)))
+    assert hp[-1] < hs[-1]
+    assert err_pyr <= 1.02 * err_single
+    zz, yy, xx = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), np.arange(shape[2]), indexing="ij")
+    dose = (70.0 * np.exp(-(((zz - 24) / 10.0) ** 2 + ((yy - 32) / 12.0) ** 2 + ((xx - 30) / 14.0) ** 2))).astype(np.float32)
+    warped = warp_image_with_field(demons_volume(dose, *sp), pyr, oob_value=0.0)[..., 0]
+    assert np.isfinite(warped).all() and warped.min() >= 0.0 and warped.max() <= 70.0 + 1e-3
+    assert abs(float(warped.sum()) / float(dose.sum()) - 1.0) < 0.1   # a smooth warp roughly preserves the integral
+    assert np.abs(warped - dose).max() > 1.0                           # and it did move the dose

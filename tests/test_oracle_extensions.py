@@ -1,0 +1,65 @@
+"""CPU checks of oracle/extensions.py (the restatement of OUR extension definitions; parity unpinned): with the
+extensions switched off it must reduce to the pinned oracle loop bit for bit, and its helpers obey their definitions."""
+import numpy as np
+
+from _helpers import phantom_pair, random_smooth_field
+
+
+def test_level_loop_without_extensions_equals_the_pinned_oracle(oracle_mod):
+    from oracle import extensions as ext
+    shape, sp = (10, 20, 24), (1.0, 1.2, 2.0)
+    F, M = phantom_pair(shape, sp)
+    for diffeo in (False, True):
+        op = oracle_mod.make_params(max_iterations=6, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
+                                    update_field_smoothing_sigma=1.5, use_diffeomorphic=diffeo)
+        Do, ho, _ = oracle_mod.demons_run(F, M, op, sp, kind="port")
+        D, h = ext.run_level(F, M, sp, 6, 1.5, 1.5, diffeo, symmetric=False)
+        assert np.array_equal(D, Do, equal_nan=True)
+        assert np.array_equal(h, ho[:6])
+
+
+def test_gradient_rule_equals_the_oracle_gradient(oracle_mod):
+    from oracle import extensions as ext
+    shape, sp = (6, 9, 11), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp)
+    F = F.copy()
+    F[2, 3, 4] = np.nan
+    E = oracle_mod.OracleEngine(F, M, oracle_mod.make_params(max_iterations=1), sp, kind="port")
+    try:
+        G = E.get("gradient")
+    finally:
+        E.close()
+    assert np.array_equal(ext.gradient_rule(F), G)
+
+
+def test_symmetric_force_with_equal_gradients_is_the_reference_force(oracle_mod):
+    """J = (g + g)/2 = g exactly: the symmetric force of (F, W = F shifted copy with the same gradient) cannot be
+    built in general, so check the algebra instead: symmetric_force(F, W, 2*gradF - gradW) equals the oracle's force."""
+    from oracle import extensions as ext
+    shape, sp = (5, 12, 14), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp)
+    E = oracle_mod.OracleEngine(F, M, oracle_mod.make_params(max_iterations=1), sp, kind="port")
+    try:
+        mse, n = E.compute_update_and_mse()
+        U_ref, G = E.get("update"), E.get("gradient")
+    finally:
+        E.close()
+    U, mse2, n2 = ext.symmetric_force(F, M, 2.0 * G - ext.gradient_rule(M))
+    assert n2 == n and abs(mse2 - mse) <= 1e-12 * mse
+    assert np.abs(U - U_ref).max() <= 1e-12
+
+
+def test_restrict_prolong_definitions():
+    from oracle import extensions as ext
+    img = np.arange(4 * 10 * 12, dtype=np.float32).reshape(4, 10, 12)   # 4 slices: z is kept, y and x are halved
+    c = ext.restrict(img)
+    assert c.shape == (4, 5, 6)
+    assert c[1, 2, 3] == np.float32(img[1, 4:6, 6:8].astype(np.float64).mean())
+    img[0, 0, 0] = np.nan
+    assert ext.restrict(img)[0, 0, 0] == np.float32(np.mean([img[0, 0, 1], img[0, 1, 0], img[0, 1, 1]], dtype=np.float64))
+    const = np.full((4, 5, 6, 3), 1.25)
+    assert np.array_equal(ext.prolong(const, (4, 10, 12)), np.full((4, 10, 12, 3), 1.25))
+    ramp = np.zeros((4, 5, 6, 3))
+    ramp[..., 0] = np.arange(6)[None, None, :] * 2.0 + 0.5   # value = coarse-centre position in fine index units
+    p = ext.prolong(ramp, (4, 10, 12))
+    assert np.allclose(p[2, 3, 1:-1, 0], np.arange(12)[1:-1])  # linear functions are reproduced away from the clamped ends
