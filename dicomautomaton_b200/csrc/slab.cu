@@ -112,6 +112,7 @@ struct SlabGroup::Local {
     std::unique_ptr<EngineBase> eng;
     int rank = 0, device = 0;
     double *d_mse2 = nullptr;    // this slab's (sum, count)
+    double *d_mse_hist = nullptr;  // per iteration (sum, count) of this slab, when no per-iteration gather is needed
     double *d_gather = nullptr;  // world x (sum, count)
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
@@ -121,6 +122,7 @@ SlabGroup::~SlabGroup() {
         cudaSetDevice(l->device);
         if (l->eng) cudaStreamSynchronize(static_cast<cudaStream_t>(l->eng->stream_handle()));
         cudaFree(l->d_mse2);
+        cudaFree(l->d_mse_hist);
         cudaFree(l->d_gather);
         if (l->ev_ready) cudaEventDestroy(l->ev_ready);
         if (l->ev_done) cudaEventDestroy(l->ev_done);
@@ -312,9 +314,27 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
     const bool can_converge = (params_.convergence_threshold > 0.0);
     const int64_t poll = (params_.check_every > 0) ? params_.check_every : 4;
     for (auto &l : locals_) l->eng->begin_run(max_iterations);
+    // With threshold <= 0 the stop rule can never fire (|prev - mse| < threshold is false), so the slabs' MSE terms are
+    // only needed for the history: they are kept per iteration on each device and combined once, after the loop,
+    // instead of one all-gather per iteration.
+    if (!can_converge) {
+        for (auto &l : locals_) {
+            DCMA_CUDA(cudaSetDevice(l->device));
+            cudaFree(l->d_mse_hist);
+            l->d_mse_hist = nullptr;
+            DCMA_CUDA(cudaMalloc(&l->d_mse_hist, 2 * sizeof(double) * max_iterations));
+        }
+    }
     for (int64_t it = 0; it < max_iterations; ++it) {
         for (auto &l : locals_) l->eng->iter_stage(IterStage::Force, it, /*global_mse=*/true);
-        gather_mse_and_stop_rule(it);
+        if (can_converge) {
+            gather_mse_and_stop_rule(it);
+        } else {
+            for (auto &l : locals_) {
+                l->eng->publish_mse(l->d_mse_hist + 2 * it);
+                l->eng->stop_rule(l->d_mse_hist + 2 * it, 1, it);  // counts the iteration; history is rebuilt below
+            }
+        }
         if (rz_u > 0) {
             exchange(DCMA_B200_BUF_UPDATE, rz_u);
             for (auto &l : locals_) l->eng->iter_stage(IterStage::SmoothU, it, true);
@@ -339,6 +359,36 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
         first = false;
     }
     if (stats) *stats = st0;
+    if (!can_converge && mse_history_host && st0.iterations_done > 0) {
+        // global MSE history: sum the slabs' terms in rank order (the order of k_stop_rule)
+        const int64_t n = st0.iterations_done;
+        std::vector<double> all(static_cast<size_t>(2 * n) * world_, 0.0);
+        if (comm_) {
+            Local &l = *locals_[0];
+            DCMA_CUDA(cudaSetDevice(l.device));
+            double *d_all = nullptr;
+            DCMA_CUDA(cudaMalloc(&d_all, sizeof(double) * all.size()));
+            cudaStream_t st = static_cast<cudaStream_t>(l.eng->stream_handle());
+            DCMA_NCCL(nccl().AllGather(l.d_mse_hist, d_all, 2 * n, ncclDouble, static_cast<ncclComm_t>(comm_), st));
+            DCMA_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, st));
+            DCMA_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d_all);
+        } else {
+            for (auto &l : locals_) {
+                DCMA_CUDA(cudaSetDevice(l->device));
+                DCMA_CUDA(cudaMemcpy(all.data() + static_cast<size_t>(2 * n) * l->rank, l->d_mse_hist, sizeof(double) * 2 * n,
+                                     cudaMemcpyDeviceToHost));
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            double sum = 0.0, cnt = 0.0;
+            for (int r = 0; r < world_; ++r) {
+                sum += all[static_cast<size_t>(2 * n) * r + 2 * i];
+                cnt += all[static_cast<size_t>(2 * n) * r + 2 * i + 1];
+            }
+            mse_history_host[i] = (cnt > 0.0) ? sum / cnt : sum;
+        }
+    }
     for (auto &l : locals_)
         if (l->eng->halo_overflowed())
             throw std::logic_error("a composition gather left the slab halo (|D_z| too large for halo_planes = " +
