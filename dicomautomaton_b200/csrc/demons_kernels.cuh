@@ -414,13 +414,13 @@ __device__ __forceinline__ void apply_stop_rule(Ctrl *ctrl, double sum, long lon
     }
 }
 
-template <typename T, bool STRICT, typename IX, bool CH1>
+template <typename T, bool STRICT, typename IX, bool CH1, bool SYM>
 __global__ void __launch_bounds__(kTileX *kTileY)
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
                  const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
                  const ForceK fk, double *part_sum, long long *part_cnt, Ctrl *ctrl, const long long it,
-                 const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter,
-                 const int symmetric /* extension a11: J = (grad F + grad W)/2; needs w_src == 2 */) {
+                 const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter) {
+    constexpr bool symmetric = SYM;  // extension a11: J = (grad F + grad W)/2; needs w_src == 2
     using CT = T;  // compute type of coordinates / interpolation / force == field storage type
     if (it > ctrl->converged_at) return;
     CT acc = 0;

@@ -633,15 +633,23 @@ class Engine final : public EngineBase {
         fk.max_update = p_.max_update_magnitude;
         fk.mu2_lo = (fk.max_update >= 0.0) ? fk.max_update * fk.max_update * (1.0 - 8.881784197001252e-16) : -1.0;
         const dim3 blk(kTileX, kTileY);
-#define DCMA_LAUNCH_FORCE(IX, CH1)                                                                                   \
-    k_warp_force<T, STRICT, IX, CH1><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
-                                                                  d_part_cnt_, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
-                                                                  hist_idx, count_iter, (p_.use_symmetric_force && w_src == 2) ? 1 : 0)
+#define DCMA_LAUNCH_FORCE2(IX, CH1, SYM)                                                                             \
+    k_warp_force<T, STRICT, IX, CH1, SYM><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
+                                                                       d_part_cnt_, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
+                                                                       hist_idx, count_iter)
+#define DCMA_LAUNCH_FORCE(IX, CH1)                            \
+    do {                                                      \
+        if (p_.use_symmetric_force && w_src == 2)             \
+            DCMA_LAUNCH_FORCE2(IX, CH1, true);                \
+        else                                                  \
+            DCMA_LAUNCH_FORCE2(IX, CH1, false);               \
+    } while (0)
         if (small_index_) {
             if (g_.CH == 1) DCMA_LAUNCH_FORCE(int, true); else DCMA_LAUNCH_FORCE(int, false);
         } else {
             if (g_.CH == 1) DCMA_LAUNCH_FORCE(long long, true); else DCMA_LAUNCH_FORCE(long long, false);
         }
+#undef DCMA_LAUNCH_FORCE2
 #undef DCMA_LAUNCH_FORCE
         DCMA_CUDA(cudaGetLastError());
         ++launches_;

@@ -42,6 +42,9 @@ constexpr int kMaxFastRadius = 6;
 #ifndef DCMA_SMOOTH_XPRELOAD
 #define DCMA_SMOOTH_XPRELOAD 0
 #endif
+#ifndef DCMA_SMOOTH_YBATCH
+#define DCMA_SMOOTH_YBATCH 0
+#endif
 #ifndef DCMA_SMOOTH_PF
 #define DCMA_SMOOTH_PF 0  // slices ahead of the cp.async stage that are requested into L2 (0 = off)
 #endif
@@ -514,6 +517,9 @@ __global__ void __launch_bounds__(NT, MINB)
                 // (ascending k: the reference's order); OY adjacent rows share their taps.
 #pragma unroll
                 for (int m = 0; m < OY + 2 * R; ++m) {
+                    // DCMA_SMOOTH_YBATCH > 0: at most that many row vectors are in flight (a compiler-level fence
+                    // keeps the shared-memory loads from all being hoisted to the front) -- fewer live registers
+                    if (DCMA_SMOOTH_YBATCH > 0 && m > 0 && (m % DCMA_SMOOTH_YBATCH) == 0) asm volatile("" ::: "memory");
                     const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
 #pragma unroll
                     for (int j = 0; j < OY; ++j) {
