@@ -20,6 +20,10 @@
 #include "engine.h"
 #include "smooth_kernels.cuh"
 
+#ifndef DCMA_FUSED_REDUCE
+#define DCMA_FUSED_REDUCE 1  // 1: the force kernel's last block reduces the MSE partials; 0: k_reduce_final as its own launch
+#endif
+
 namespace DCMA_NS {
 using namespace ::dcma;
 
@@ -584,8 +588,13 @@ class Engine final : public EngineBase {
             prof_end();
         } else if (p_.fused) {
             prof_begin(DCMA_B200_STAGE_FORCE);
-            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false, /*fused_reduce=*/true);
+            launch_force(w_src_, it, d_hist, it, 1, /*reduce=*/false, /*fused_reduce=*/DCMA_FUSED_REDUCE != 0);
             prof_end();
+            if (!DCMA_FUSED_REDUCE) {
+                prof_begin(DCMA_B200_STAGE_REDUCE);
+                launch_reduce(it, d_hist, it, 1);
+                prof_end();
+            }
         } else {
             if (w_src_ == 1) {
                 prof_begin(DCMA_B200_STAGE_WARP);
