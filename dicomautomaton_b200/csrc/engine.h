@@ -30,6 +30,7 @@ class EngineBase {
     virtual bool update_smoothed() const = 0, deformation_smoothed() const = 0, diffeomorphic() const = 0;
     virtual int smoothing_radius_z(bool update_field) const = 0;
     virtual void *field_base(int buffer) = 0;     // DCMA_B200_BUF_UPDATE / _DEFORMATION: device pointer of component 0
+    virtual void *field_allocation(int i) = 0;    // the three field allocations (fixed identity; their roles rotate)
     virtual int64_t field_elem_size() const = 0;  // 4 or 8
     virtual int64_t field_comp_stride() const = 0, plane_elems() const = 0;
     virtual void *stream_handle() = 0;

@@ -120,6 +120,9 @@ class Engine final : public EngineBase {
         dD_ = alloc<T>(3 * N);
         dU_ = alloc<T>(3 * N);
         dTmp_ = alloc<T>(3 * N);
+        field_alloc_[0] = dD_;
+        field_alloc_[1] = dU_;
+        field_alloc_[2] = dTmp_;
         d_part_sum_ = alloc<double>(grid_vox_);
         d_part_cnt_ = alloc<long long>(grid_vox_);
         d_ctrl_ = alloc<Ctrl>(1);
@@ -300,6 +303,7 @@ class Engine final : public EngineBase {
     bool diffeomorphic() const override { return p_.use_diffeomorphic != 0; }
     int smoothing_radius_z(bool update_field) const override { return update_field ? plan_u_.r[2] : plan_d_.r[2]; }
     void *field_base(int buffer) override { return buffer == DCMA_B200_BUF_UPDATE ? static_cast<void *>(dU_) : static_cast<void *>(dD_); }
+    void *field_allocation(int i) override { return field_alloc_[i]; }
     int64_t field_elem_size() const override { return static_cast<int64_t>(sizeof(T)); }
     int64_t field_comp_stride() const override { return g_.N; }
     int64_t plane_elems() const override { return static_cast<int64_t>(g_.R) * g_.C; }
@@ -828,6 +832,7 @@ class Engine final : public EngineBase {
     int grid_vox_ = 1, grid_lin_ = 1;
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
     T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;
+    void *field_alloc_[3] = {nullptr, nullptr, nullptr};
     double *d_part_sum_ = nullptr;
     long long *d_part_cnt_ = nullptr;
     Ctrl *d_ctrl_ = nullptr, *h_ctrl_ = nullptr;

@@ -128,6 +128,11 @@ SlabGroup::~SlabGroup() {
         if (l->ev_done) cudaEventDestroy(l->ev_done);
         l->eng.reset();
     }
+    for (int i = 0; i < 3; ++i) {
+        if (peer_lo_[i]) cudaIpcCloseMemHandle(peer_lo_[i]);
+        if (peer_hi_[i]) cudaIpcCloseMemHandle(peer_hi_[i]);
+    }
+    cudaFree(d_token_);
     if (comm_) {
         try {
             nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
@@ -189,6 +194,80 @@ SlabGroup::SlabGroup(const dcma_b200_geom &g, const dcma_b200_demons_params &p, 
     ncclComm_t c = nullptr;
     DCMA_NCCL(nccl().CommInitRank(&c, world, u, rank));
     comm_ = c;
+    const char *no_ipc = std::getenv("DCMA_B200_SLAB_NO_IPC");
+    if (world > 1 && !(no_ipc && *no_ipc == '1')) setup_ipc();
+}
+
+// Exchange the CUDA IPC handles of the three field allocations with every rank (all-gather over NCCL) and open the two
+// z-neighbours'.  Any failure (IPC not permitted in this environment, no peer access) leaves ipc_ok_ false on ALL ranks
+// and the exchange falls back to ncclSend/ncclRecv.
+void SlabGroup::setup_ipc() {
+    Local &l = *locals_[0];
+    EngineBase *e = l.eng.get();
+    DCMA_CUDA(cudaSetDevice(l.device));
+    cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
+    struct Rec {
+        cudaIpcMemHandle_t h[3];
+        int ok;
+        int pad[3];
+    };
+    Rec mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.ok = 1;
+    for (int i = 0; i < 3; ++i)
+        if (cudaIpcGetMemHandle(&mine.h[i], e->field_allocation(i)) != cudaSuccess) {
+            cudaGetLastError();
+            mine.ok = 0;
+        }
+    Rec *d_all = nullptr, *d_mine = nullptr;
+    DCMA_CUDA(cudaMalloc(&d_all, sizeof(Rec) * world_));
+    DCMA_CUDA(cudaMalloc(&d_mine, sizeof(Rec)));
+    DCMA_CUDA(cudaMalloc(&d_token_, 4 * sizeof(int)));
+    DCMA_CUDA(cudaMemsetAsync(d_token_, 0, 4 * sizeof(int), st));
+    DCMA_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st));
+    DCMA_NCCL(nccl().AllGather(d_mine, d_all, sizeof(Rec), ncclChar, static_cast<ncclComm_t>(comm_), st));
+    std::vector<Rec> all(world_);
+    DCMA_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * world_, cudaMemcpyDeviceToHost, st));
+    DCMA_CUDA(cudaStreamSynchronize(st));
+    int ok = 1;
+    for (auto &r : all) ok &= r.ok;
+    auto open_peer = [&](int peer, void *out[3]) {
+        for (int i = 0; i < 3 && ok; ++i)
+            if (cudaIpcOpenMemHandle(&out[i], all[peer].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
+    };
+    if (ok && l.rank > 0) open_peer(l.rank - 1, peer_lo_);
+    if (ok && l.rank + 1 < world_) open_peer(l.rank + 1, peer_hi_);
+    // every rank must take the same path: agree on the outcome
+    mine.ok = ok;
+    DCMA_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st));
+    DCMA_NCCL(nccl().AllGather(d_mine, d_all, sizeof(Rec), ncclChar, static_cast<ncclComm_t>(comm_), st));
+    DCMA_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * world_, cudaMemcpyDeviceToHost, st));
+    DCMA_CUDA(cudaStreamSynchronize(st));
+    ok = 1;
+    for (auto &r : all) ok &= r.ok;
+    ipc_ok_ = (ok != 0);
+    cudaFree(d_all);
+    cudaFree(d_mine);
+}
+
+// A 4-byte send/recv with each z-neighbour in stream order: when it completes on this stream, the neighbours' streams
+// have reached the same point (their kernels enqueued before it are done as far as their own stream order goes).
+void SlabGroup::token_sync() {
+    Local &l = *locals_[0];
+    cudaStream_t st = static_cast<cudaStream_t>(l.eng->stream_handle());
+    DCMA_NCCL(nccl().GroupStart());
+    if (l.rank > 0) {
+        DCMA_NCCL(nccl().Send(d_token_ + 0, 1, ncclInt32, l.rank - 1, static_cast<ncclComm_t>(comm_), st));
+        DCMA_NCCL(nccl().Recv(d_token_ + 1, 1, ncclInt32, l.rank - 1, static_cast<ncclComm_t>(comm_), st));
+    }
+    if (l.rank + 1 < world_) {
+        DCMA_NCCL(nccl().Send(d_token_ + 2, 1, ncclInt32, l.rank + 1, static_cast<ncclComm_t>(comm_), st));
+        DCMA_NCCL(nccl().Recv(d_token_ + 3, 1, ncclInt32, l.rank + 1, static_cast<ncclComm_t>(comm_), st));
+    }
+    DCMA_NCCL(nccl().GroupEnd());
 }
 
 void SlabGroup::load(const float *fixed, const float *moving, bool on_device) {
@@ -206,6 +285,40 @@ static inline char *plane_ptr(EngineBase *e, int buffer, int c, int64_t l0) {
 void SlabGroup::exchange(int buffer, int64_t n) {
     if (world_ == 1 || n <= 0) return;
     if (n > halo_) throw std::logic_error("exchange wider than the halo");
+    if (comm_ && ipc_ok_) {
+        // ---- NVLink copy engines: PULL the neighbours' boundary planes out of their (IPC-mapped) field buffers into my
+        // halo.  The tokens order the streams: before -- the neighbours have produced the planes; after -- they may
+        // overwrite them again (nobody is still reading).
+        Local &l = *locals_[0];
+        EngineBase *e = l.eng.get();
+        const SlabSpec s = e->slab();
+        const int64_t pe = e->plane_elems(), es = e->field_elem_size();
+        const size_t bytes = static_cast<size_t>(n) * pe * es;
+        cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
+        DCMA_CUDA(cudaSetDevice(l.device));
+        int idx = -1;  // which of the three allocations currently plays `buffer` (the roles rotate identically on all ranks)
+        for (int i = 0; i < 3; ++i)
+            if (e->field_allocation(i) == e->field_base(buffer)) idx = i;
+        if (idx < 0) throw std::logic_error("field buffer is not one of the engine's allocations");
+        token_sync();
+        if (l.rank > 0) {
+            const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank - 1, halo_);
+            for (int c = 0; c < 3; ++c)
+                DCMA_CUDA(cudaMemcpyAsync(plane_ptr(e, buffer, c, s.own0 - n),
+                                          static_cast<const char *>(peer_lo_[idx]) + (c * p.local * pe + (p.own1 - n) * pe) * es, bytes,
+                                          cudaMemcpyDefault, st));
+        }
+        if (l.rank + 1 < world_) {
+            const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank + 1, halo_);
+            for (int c = 0; c < 3; ++c)
+                DCMA_CUDA(cudaMemcpyAsync(plane_ptr(e, buffer, c, s.own1),
+                                          static_cast<const char *>(peer_hi_[idx]) + (c * p.local * pe + p.own0 * pe) * es, bytes,
+                                          cudaMemcpyDefault, st));
+        }
+        token_sync();
+        halo_bytes_ += 3 * bytes * ((l.rank > 0 ? 1 : 0) + (l.rank + 1 < world_ ? 1 : 0));
+        return;
+    }
     if (comm_) {
         // ---- NCCL: one grouped send/recv set with both z-neighbours, on the engine's stream
         Local &l = *locals_[0];

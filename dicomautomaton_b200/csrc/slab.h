@@ -40,6 +40,13 @@ class SlabGroup {
     int64_t halo_ = 0;
     int64_t halo_bytes_ = 0;
     void *comm_ = nullptr;  // ncclComm_t
+    // NCCL groups on NVLink: the neighbours' field allocations opened through CUDA IPC, so that the halo planes move
+    // by copy-engine transfers (no SMs, full NVLink bandwidth) and NCCL only carries 4-byte ordering tokens
+    void setup_ipc();
+    void token_sync();
+    bool ipc_ok_ = false;
+    void *peer_lo_[3] = {nullptr, nullptr, nullptr}, *peer_hi_[3] = {nullptr, nullptr, nullptr};
+    int *d_token_ = nullptr;
     std::vector<std::unique_ptr<Local>> locals_;
 };
 
