@@ -35,6 +35,7 @@ UNITS = {
     "engine_f32.cu": [],
     "slab.cu": [],
     "pyramid.cu": [],
+    "warp_grid.cu": [],
     "c_api.cu": [],
 }
 

@@ -26,6 +26,12 @@ class Geom(C.Structure):
                 ("pxl_dx", C.c_double), ("pxl_dy", C.c_double), ("pxl_dz", C.c_double)]
 
 
+class Grid(C.Structure):
+    """dcma_b200_grid: a regular grid in world space (geom + origin + unit axes)."""
+    _fields_ = [("geom", Geom), ("origin", C.c_double * 3), ("ex", C.c_double * 3), ("ey", C.c_double * 3),
+                ("ez", C.c_double * 3)]
+
+
 class Params(C.Structure):
     _fields_ = [("max_iterations", C.c_int64), ("convergence_threshold", C.c_double),
                 ("deformation_field_smoothing_sigma", C.c_double), ("update_field_smoothing_sigma", C.c_double),
@@ -67,6 +73,8 @@ SYMBOLS = {
     "dcma_b200_warp_image": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_restrict_image": (C.c_int, [C.POINTER(Geom), _vp, C.POINTER(Geom), _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_prolong_field": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_int, _cp, C.c_size_t]),
+    "dcma_b200_warp_image_grid": (C.c_int, [C.POINTER(Grid), _vp, C.POINTER(Grid), _vp, _vp, C.c_float, _vp, C.c_int, _cp,
+                                            C.c_size_t]),
     "dcma_b200_slab_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, _ip, _ip, _ip, _ip]),
     "dcma_b200_slab_group_create_local": (C.c_int, [C.POINTER(_vp), C.POINTER(Geom), C.POINTER(Params),
                                                     C.POINTER(C.c_int32), C.c_int32, C.c_int64, _cp, C.c_size_t]),

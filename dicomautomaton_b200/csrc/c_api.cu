@@ -337,4 +337,13 @@ int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const d
         errbuf_len);
 }
 
+int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, const double *deformation, const dcma_b200_grid *image_grid,
+                              const float *image, const unsigned char *mask, float oob_value, float *out, int device,
+                              char *errbuf, size_t errbuf_len) {
+    if (!field_grid || !deformation || !image_grid || !image || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded(
+        [&]() { dcma::warp_image_grid_host(*field_grid, deformation, *image_grid, image, mask, oob_value, out, device); }, errbuf,
+        errbuf_len);
+}
+
 }  // extern "C"

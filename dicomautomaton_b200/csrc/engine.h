@@ -61,4 +61,8 @@ EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &
 void warp_image_host(const dcma_b200_geom &g, const float *image, const double *deformation_aos, bool use_oob,
                      float oob_value, float *out, int device);
 
+// WarpImages' voxel body for a field and an image on different regular grids (warp_grid.cu)
+void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &image_grid,
+                          const float *image, const unsigned char *mask, float oob_value, float *out, int device);
+
 }  // namespace dcma

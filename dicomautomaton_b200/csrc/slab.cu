@@ -151,6 +151,8 @@ int64_t SlabGroup::default_halo(const dcma_b200_geom &g, const dcma_b200_demons_
 }
 
 void SlabGroup::add_local(const dcma_b200_geom &g, const dcma_b200_demons_params &p, int rank, int device) {
+    // the fixed-image gradient reads the z neighbours of every owned slice (cc:254-265): at least one halo plane
+    if (world_ > 1 && halo_ < 1) throw std::invalid_argument("halo_planes must be >= 1 when the volume is sharded");
     auto l = std::make_unique<Local>();
     l->rank = rank;
     dcma_b200_demons_params pp = p;

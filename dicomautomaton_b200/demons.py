@@ -225,6 +225,33 @@ class DemonsEngine:
         self._stage(capi.STAGE_WARP)
 
 
+def make_grid(shape, spacing, origin=(0.0, 0.0, 0.0), channels=1, ex=(1.0, 0.0, 0.0), ey=(0.0, 1.0, 0.0),
+              ez=(0.0, 0.0, 1.0)) -> capi.Grid:
+    """A regular grid in world space: voxel (z, y, x) at origin + x*dx*ex + y*dy*ey + z*dz*ez; spacing = (dx, dy, dz)."""
+    g = capi.Grid()
+    g.geom = capi.Geom(int(shape[0]), int(shape[1]), int(shape[2]), int(channels), float(spacing[0]), float(spacing[1]),
+                       float(spacing[2]))
+    for i in range(3):
+        g.origin[i], g.ex[i], g.ey[i], g.ez[i] = float(origin[i]), float(ex[i]), float(ey[i]), float(ez[i])
+    return g
+
+
+def warp_image_on_grid(field_grid: capi.Grid, deformation: np.ndarray, image_grid: capi.Grid, image: np.ndarray,
+                       mask: Optional[np.ndarray] = None, oob_value: float = 0.0, device: int = -1) -> np.ndarray:
+    """WarpImages' voxel body for a deformation_field transform when the image (e.g. an RT dose grid) lives on another
+    regular grid than the field (reference src/Operations/WarpImages.cc:418-456)."""
+    lib = capi.lib()
+    D = np.ascontiguousarray(deformation, dtype=np.float64)
+    img = np.ascontiguousarray(image, dtype=np.float32)
+    out = np.empty_like(img)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_warp_image_grid(C.byref(field_grid), D.ctypes.data, C.byref(image_grid), img.ctypes.data,
+                                             None if m is None else m.ctypes.data, float(oob_value), out.ctypes.data,
+                                             device, err, len(err)), err)
+    return out
+
+
 def restrict_image(image: demons_volume, device: int = -1) -> demons_volume:
     """Next-coarser pyramid level of an image (extension a12; definition in csrc/pyramid.cu)."""
     lib = capi.lib()

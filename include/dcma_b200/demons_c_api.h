@@ -217,6 +217,24 @@ DCMA_B200_API int dcma_b200_prolong_field(const dcma_b200_geom *fine, const doub
 DCMA_B200_API int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
                          int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* ---- warp an image that lives on ANOTHER regular grid than the field (WarpImages with a deformation_field) ----- */
+/* A regular grid in world space: voxel (z, y, x) sits at origin + x*pxl_dx*ex + y*pxl_dy*ey + z*pxl_dz*ez, with ex, ey,
+ * ez unit vectors (the reference's row_unit, col_unit and ortho_unit of a planar_image stack; origin = position(0,0) of
+ * the first image). */
+typedef struct {
+    dcma_b200_geom geom;
+    double origin[3];
+    double ex[3], ey[3], ez[3];
+} dcma_b200_grid;
+/* The per-voxel body of WarpImages for a deformation_field transform (src/Operations/WarpImages.cc:418-456,
+ * src/Alignment_Field.cc:138-153): out(p) = image(p + D(p)) with p running over `image_grid`, D sampled trilinearly
+ * from the field on `field_grid` (displacement components along the field's axes, mm), the image sampled trilinearly at
+ * the displaced position; `oob_value` (WarpImages: 0.0, cc:197) wherever either lookup leaves its grid or is non-finite.
+ * `mask` (image_grid voxels, may be NULL): 0 = voxel outside the region of interest, copied unchanged.  All HOST. */
+DCMA_B200_API int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, const double *deformation,
+                                            const dcma_b200_grid *image_grid, const float *image, const unsigned char *mask,
+                                            float oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,57 @@ def pyramid_run(fixed, moving, spacing, levels, iters_per_level, sigma_d, sigma_
         D, h = run_level(F[l], M[l], SP[l], iters_per_level[l], sigma_d, sigma_u, diffeo, symmetric, D0)
         hist.extend(h.tolist())
     return D, np.array(hist)
+
+
+# ---- row f1: WarpImages' voxel body for a field and an image on different regular grids ------------------------
+# (reference src/Operations/WarpImages.cc:418-456 + src/Alignment_Field.cc:138-153; the trilinear lookups there are
+#  Ygor's planar_image_adjacency, which is not vendored: the definition below is ours -- parity unpinned -- and is the
+#  one documented in dicomautomaton_b200/csrc/warp_grid.cu)
+def _axis(u, n):
+    if n == 1:
+        ok = np.abs(u) <= 0.5
+        z = np.zeros(u.shape, dtype=np.int64)
+        return ok, z, z, np.zeros(u.shape)
+    ok = (u >= 0.0) & (u <= float(n - 1))
+    us = np.where(ok, u, 0.0)
+    i0 = np.minimum(np.floor(us).astype(np.int64), n - 2)
+    return ok, i0, i0 + 1, us - i0
+
+
+def _trilinear(data, u):
+    """data (S,R,C); u = (ux, uy, uz) index coordinates, arrays of one shape.  Returns (value, ok)."""
+    S, R, C = data.shape
+    okx, x0, x1, tx = _axis(u[0], C)
+    oky, y0, y1, ty = _axis(u[1], R)
+    okz, z0, z1, tz = _axis(u[2], S)
+    d = data.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        c00 = d[z0, y0, x0] * (1.0 - tx) + d[z0, y0, x1] * tx
+        c10 = d[z0, y1, x0] * (1.0 - tx) + d[z0, y1, x1] * tx
+        c01 = d[z1, y0, x0] * (1.0 - tx) + d[z1, y0, x1] * tx
+        c11 = d[z1, y1, x0] * (1.0 - tx) + d[z1, y1, x1] * tx
+        c0 = c00 * (1.0 - ty) + c10 * ty
+        c1 = c01 * (1.0 - ty) + c11 * ty
+        v = c0 * (1.0 - tz) + c1 * tz
+    ok = okx & oky & okz & np.isfinite(v)
+    return v, ok
+
+
+def warp_image_on_grid(field, f_spacing, f_origin, image, i_spacing, i_origin, oob_value=0.0, mask=None):
+    """Axis-aligned grids (ex, ey, ez = unit axes).  field (S,R,C,3) mm; image (S,R,C) float32."""
+    S, R, C = image.shape
+    z, y, x = np.meshgrid(np.arange(S, dtype=np.float64), np.arange(R, dtype=np.float64), np.arange(C, dtype=np.float64),
+                          indexing="ij")
+    p = [i_origin[0] + x * i_spacing[0], i_origin[1] + y * i_spacing[1], i_origin[2] + z * i_spacing[2]]
+    uf = [(p[k] - f_origin[k]) / f_spacing[k] for k in range(3)]
+    d, okd = [], np.ones(image.shape, dtype=bool)
+    for c in range(3):
+        v, ok = _trilinear(field[..., c], uf)
+        d.append(v)
+        okd &= ok
+    ui = [(p[k] + np.where(okd, d[k], 0.0) - i_origin[k]) / i_spacing[k] for k in range(3)]
+    val, ok = _trilinear(image, ui)
+    out = np.where(okd & ok, val, oob_value).astype(np.float32)
+    if mask is not None:
+        out = np.where(mask.astype(bool), out, image)
+    return out

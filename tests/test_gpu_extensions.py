@@ -110,3 +110,44 @@ def test_pyramid_recovers_a_large_warp_and_the_field_warps_a_dose_grid():
     assert np.isfinite(warped).all() and warped.min() >= 0.0 and warped.max() <= 70.0 + 1e-3
     assert abs(float(warped.sum()) / float(dose.sum()) - 1.0) < 0.1   # a smooth warp roughly preserves the integral
     assert np.abs(warped - dose).max() > 1.0                           # and it did move the dose
+
+
+def test_warp_on_another_grid_matches_the_cpu_restatement_and_the_reference_properties():
+    """Row f1: the dose grid (coarser, shifted, smaller than the CT grid the field was estimated on).  Checked against
+    oracle/extensions.py and against what the reference's own tests pin for this transform: a zero field is the
+    identity, a uniform field is a shift (src/Alignment_Field_Tests.cc:291-427), out of bounds gives 0.0
+    (src/Operations/WarpImages.cc:197)."""
+    from dicomautomaton_b200.demons import make_grid, warp_image_on_grid
+    from oracle import extensions as ext
+    fshape, fsp, forg = (20, 32, 36), (1.0, 1.0, 2.0), (-10.0, 5.0, 0.0)
+    ishape, isp, iorg = (12, 14, 13), (2.5, 2.0, 3.0), (-8.0, 7.5, 1.0)   # partly outside the field's grid
+    D = random_smooth_field(fshape, 3.0, seed=7)
+    rng = np.random.default_rng(3)
+    img = rng.uniform(0.0, 70.0, size=ishape).astype(np.float32)
+    fg, ig = make_grid(fshape, fsp, forg), make_grid(ishape, isp, iorg)
+    got = warp_image_on_grid(fg, D, ig, img, oob_value=0.0)
+    ref = ext.warp_image_on_grid(D, fsp, forg, img, isp, iorg, 0.0)
+    assert np.abs(got - ref).max() <= 1e-4 * 70.0 and np.array_equal(got == 0.0, ref == 0.0)
+    assert (got == 0.0).any() and (got != 0.0).any()
+    # region of interest: voxels outside the mask are left untouched
+    mask = np.zeros(ishape, dtype=np.uint8)
+    mask[3:9, 4:10, 2:11] = 1
+    gm = warp_image_on_grid(fg, D, ig, img, mask=mask, oob_value=0.0)
+    assert np.array_equal(gm[mask == 0], img[mask == 0]) and np.array_equal(gm[mask == 1], got[mask == 1])
+    # zero field on a grid that covers the image: identity
+    big = make_grid((40, 60, 60), (1.0, 1.0, 1.0), (-12.0, 0.0, -2.0))
+    ident = warp_image_on_grid(big, np.zeros((40, 60, 60, 3)), ig, img)
+    assert np.array_equal(ident, img)
+    # uniform field of exactly one image voxel along x: a shift by one column, zeros where the source leaves the image
+    U = np.zeros((40, 60, 60, 3))
+    U[..., 0] = isp[0]
+    sh = warp_image_on_grid(big, U, ig, img)
+    assert np.allclose(sh[:, :, :-1], img[:, :, 1:], rtol=0, atol=1e-4) and np.all(sh[:, :, -1] == 0.0)
+    # the same grid as the field and an in-grid field: equals the loop's own warp kernel wherever that one is defined
+    from dicomautomaton_b200.demons import demons_volume, warp_image_with_field
+    F, M = phantom_pair(fshape, (1.0, 1.0, 1.0))
+    same = make_grid(fshape, (1.0, 1.0, 1.0))
+    a = warp_image_on_grid(same, D, same, M, oob_value=0.0)
+    b = warp_image_with_field(demons_volume(M), D, oob_value=0.0)[..., 0]
+    inside = b != 0.0
+    assert np.abs(a - b)[inside].max() <= 2e-3   # float rounding of the two code paths (HU)
