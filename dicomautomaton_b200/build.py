@@ -36,6 +36,7 @@ UNITS = {
     "slab.cu": [],
     "pyramid.cu": [],
     "warp_grid.cu": [],
+    "histmatch.cu": ["-fmad=false"],
     "c_api.cu": [],
 }
 

@@ -73,6 +73,8 @@ SYMBOLS = {
     "dcma_b200_warp_image": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_restrict_image": (C.c_int, [C.POINTER(Geom), _vp, C.POINTER(Geom), _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_prolong_field": (C.c_int, [C.POINTER(Geom), _vp, _vp, C.c_int, _cp, C.c_size_t]),
+    "dcma_b200_histogram_match": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_double, _vp, C.POINTER(C.c_int32),
+                                            C.c_int, _cp, C.c_size_t]),
     "dcma_b200_warp_image_grid": (C.c_int, [C.POINTER(Grid), _vp, C.POINTER(Grid), _vp, _vp, C.c_float, _vp, C.c_int, _cp,
                                             C.c_size_t]),
     "dcma_b200_slab_partition": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, _ip, _ip, _ip, _ip]),

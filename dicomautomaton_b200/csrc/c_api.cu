@@ -337,6 +337,18 @@ int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const d
         errbuf_len);
 }
 
+int dcma_b200_histogram_match(const float *source, int64_t n_source, const float *reference, int64_t n_reference,
+                              int64_t num_bins, double outlier_fraction, float *out, int32_t *mapped, int device, char *errbuf,
+                              size_t errbuf_len) {
+    if (!source || !reference || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded(
+        [&]() {
+            const int m = dcma::histogram_match_host(source, n_source, reference, n_reference, num_bins, outlier_fraction, out, device);
+            if (mapped) *mapped = m;
+        },
+        errbuf, errbuf_len);
+}
+
 int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, const double *deformation, const dcma_b200_grid *image_grid,
                               const float *image, const unsigned char *mask, float oob_value, float *out, int device,
                               char *errbuf, size_t errbuf_len) {

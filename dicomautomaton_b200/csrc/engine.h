@@ -61,6 +61,10 @@ EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &
 void warp_image_host(const dcma_b200_geom &g, const float *image, const double *deformation_aos, bool use_oob,
                      float oob_value, float *out, int device);
 
+// histogram_match (cc:760-891) on the GPU, bit-identical (histmatch.cu); returns 1 if mapped, 0 if returned unchanged
+int histogram_match_host(const float *source, long long n_src, const float *reference, long long n_ref, long long num_bins,
+                         double outlier_fraction, float *out, int device);
+
 // WarpImages' voxel body for a field and an image on different regular grids (warp_grid.cu)
 void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &image_grid,
                           const float *image, const unsigned char *mask, float oob_value, float *out, int device);

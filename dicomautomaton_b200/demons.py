@@ -225,6 +225,24 @@ class DemonsEngine:
         self._stage(capi.STAGE_WARP)
 
 
+def histogram_match(source: np.ndarray, reference: np.ndarray, num_bins: int = 256, outlier_fraction: float = 0.01,
+                    device: int = -1):
+    """AlignViaDemonsHelpers::histogram_match (reference src/Alignment_Demons.cc:760-891) on the GPU, bit-identical.
+    Returns (matched array shaped like `source`, mapped flag)."""
+    lib = capi.lib()
+    src = np.ascontiguousarray(source, dtype=np.float32)
+    ref = np.ascontiguousarray(reference, dtype=np.float32)
+    if src.size == 0 or ref.size == 0:
+        raise ValueError("Cannot perform histogram matching: image collection is empty")
+    out = np.empty_like(src)
+    mapped = C.c_int32(0)
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_histogram_match(src.ctypes.data, src.size, ref.ctypes.data, ref.size, int(num_bins),
+                                             float(outlier_fraction), out.ctypes.data, C.byref(mapped), device, err,
+                                             len(err)), err)
+    return out, bool(mapped.value)
+
+
 def make_grid(shape, spacing, origin=(0.0, 0.0, 0.0), channels=1, ex=(1.0, 0.0, 0.0), ey=(0.0, 1.0, 0.0),
               ez=(0.0, 0.0, 1.0)) -> capi.Grid:
     """A regular grid in world space: voxel (z, y, x) at origin + x*dx*ex + y*dy*ey + z*dz*ez; spacing = (dx, dy, dz)."""

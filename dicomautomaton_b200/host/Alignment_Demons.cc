@@ -137,12 +137,24 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
     try {
         if (params.verbosity >= 1) YLOGINFO("Resampling moving image to reference grid");
         auto moving = resample_image_to_reference_grid(moving_in, stationary);
-        if (params.use_histogram_matching) {
-            if (params.verbosity >= 1) YLOGINFO("Applying histogram matching");
-            moving = histogram_match(moving, stationary, params.histogram_bins, params.histogram_outlier_fraction);
-        }
         const auto fixed_vol = marshal_collection_to_volume(stationary);
-        const auto moving_vol = marshal_collection_to_volume(moving);
+        auto moving_vol = marshal_collection_to_volume(moving);
+        if (params.use_histogram_matching) {
+            // reference: histogram_match(moving, stationary, ...) on the collections (cc:967-972).  Here the same
+            // algorithm runs on the GPU over the dense volumes (bit-identical result; the public helper above stays a
+            // host function, as in the reference)
+            if (params.verbosity >= 1) YLOGINFO("Applying histogram matching");
+            std::vector<float> matched(moving_vol.data.size());
+            char herr[512] = {0};
+            int32_t mapped = 0;
+            if (dcma_b200_histogram_match(moving_vol.data.data(), static_cast<int64_t>(moving_vol.data.size()),
+                                          fixed_vol.data.data(), static_cast<int64_t>(fixed_vol.data.size()),
+                                          params.histogram_bins, params.histogram_outlier_fraction, matched.data(), &mapped,
+                                          params.device, herr, sizeof herr) != DCMA_B200_OK)
+                throw std::runtime_error(herr);
+            if (!mapped) YLOGWARN("Histogram matching not applicable (no finite values or constant intensity), moving image unchanged");
+            moving_vol.data.swap(matched);
+        }
 
         dcma_b200_geom g;
         g.slices = fixed_vol.slices;

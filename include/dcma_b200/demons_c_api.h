@@ -217,6 +217,16 @@ DCMA_B200_API int dcma_b200_prolong_field(const dcma_b200_geom *fine, const doub
 DCMA_B200_API int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
                          int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* ---- histogram matching (AlignViaDemonsHelpers::histogram_match, src/Alignment_Demons.cc:760-891) ------------- */
+/* out := source with its intensity distribution matched to `reference` (num_bins-bin CDFs between the
+ * outlier_fraction / 1-outlier_fraction percentiles, first-bin->=quantile lookup, clamping outside the source range).
+ * Same double arithmetic as the reference: bit-identical output.  *mapped (may be NULL) is set to 0 when the source is
+ * returned unchanged (no finite values, or a degenerate intensity range: cc:791-794, 812-815).  All pointers HOST;
+ * the two images need not have the same size. */
+DCMA_B200_API int dcma_b200_histogram_match(const float *source, int64_t n_source, const float *reference, int64_t n_reference,
+                                            int64_t num_bins, double outlier_fraction, float *out, int32_t *mapped, int device,
+                                            char *errbuf, size_t errbuf_len);
+
 /* ---- warp an image that lives on ANOTHER regular grid than the field (WarpImages with a deformation_field) ----- */
 /* A regular grid in world space: voxel (z, y, x) sits at origin + x*pxl_dx*ex + y*pxl_dy*ey + z*pxl_dz*ez, with ex, ey,
  * ez unit vectors (the reference's row_unit, col_unit and ortho_unit of a planar_image stack; origin = position(0,0) of

@@ -215,3 +215,45 @@ def warp_image_on_grid(field, f_spacing, f_origin, image, i_spacing, i_origin, o
     if mask is not None:
         out = np.where(mask.astype(bool), out, image)
     return out
+
+
+# ---- row a14 / f4: histogram_match, reference src/Alignment_Demons.cc:760-891 (pure std:: code, no Ygor arithmetic) ----
+# PINNED: tests/test_oracle_extensions.py checks the reference's own known answers (10, 17.5, 25, 32.5 for a 2x2 ramp
+# with 4 bins, constants returned unchanged: src/Alignment_Demons_Tests.cc:204-236).
+def histogram_match(source: np.ndarray, reference: np.ndarray, num_bins: int, outlier_fraction: float):
+    """Returns (matched float32 array shaped like source, mapped flag)."""
+    if source.size == 0 or reference.size == 0:
+        raise ValueError("Cannot perform histogram matching: image collection is empty")
+    src = source.astype(np.float32)
+    sv = np.sort(src[np.isfinite(src)].astype(np.float64))                      # cc:772-798
+    rv = np.sort(reference[np.isfinite(reference)].astype(np.float64))
+    if sv.size == 0 or rv.size == 0:
+        return src.copy(), False                                                  # cc:791-794
+    pct = lambda v, p: v[int(p * (v.size - 1))]                                   # cc:801-804
+    smin, smax = pct(sv, outlier_fraction), pct(sv, 1.0 - outlier_fraction)
+    rmin, rmax = pct(rv, outlier_fraction), pct(rv, 1.0 - outlier_fraction)
+    if smax <= smin or rmax <= rmin:
+        return src.copy(), False                                                  # cc:812-815
+
+    def cdf(v, lo, hi):                                                           # cc:818-851
+        inside = v[(v >= lo) & (v <= hi)]
+        b = np.minimum(num_bins - 1, ((inside - lo) / (hi - lo) * num_bins).astype(np.int64))
+        c = np.bincount(b, minlength=num_bins).astype(np.float64)
+        c = np.cumsum(c)
+        return c / c[-1] if c[-1] > 0 else c
+
+    sc, rc = cdf(sv, smin, smax), cdf(rv, rmin, rmax)
+    lut = np.empty(num_bins)
+    for sb in range(num_bins):                                                    # cc:854-869
+        hit = np.nonzero(rc >= sc[sb])[0]
+        rb = int(hit[0]) if hit.size else 0
+        lut[sb] = rmin + (rmax - rmin) * rb / num_bins
+    out = src.copy()
+    fin = np.isfinite(src)
+    v = src.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        b = np.minimum(num_bins - 1, np.where(fin, (v - smin) / (smax - smin) * num_bins, 0.0).astype(np.int64))
+    b = np.clip(b, 0, num_bins - 1)
+    mapped = np.where(v < smin, rmin, np.where(v > smax, rmax, lut[b]))          # cc:875-886
+    out[fin] = mapped[fin].astype(np.float32)
+    return out, True

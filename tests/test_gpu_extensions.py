@@ -151,3 +151,33 @@ def test_warp_on_another_grid_matches_the_cpu_restatement_and_the_reference_prop
     b = warp_image_with_field(demons_volume(M), D, oob_value=0.0)[..., 0]
     inside = b != 0.0
     assert np.abs(a - b)[inside].max() <= 2e-3   # float rounding of the two code paths (HU)
+
+
+def test_gpu_histogram_match_is_bit_identical_to_the_reference_algorithm():
+    """dcma_b200_histogram_match vs the pinned restatement of src/Alignment_Demons.cc:760-891: the reference's known
+    answers, then random CT-like volumes with NaNs, outliers, different sizes and bin counts -- bit for bit."""
+    from dicomautomaton_b200.demons import histogram_match
+    from oracle import extensions as ext
+    src = np.array([[0, 1], [2, 3]], dtype=np.float32)
+    ref = np.array([[10, 20], [30, 40]], dtype=np.float32)
+    out, mapped = histogram_match(src, ref, 4, 0.0)
+    assert mapped and np.array_equal(out, np.array([[10.0, 17.5], [25.0, 32.5]], dtype=np.float32))
+    c10 = np.full((2, 2), 10.0, np.float32)
+    o, m = histogram_match(src, c10, 8, 0.0)
+    assert not m and np.array_equal(o, src)
+    o, m = histogram_match(np.full((2, 2), np.nan, np.float32), ref, 8, 0.0)
+    assert not m and np.isnan(o).all()
+    rng = np.random.default_rng(11)
+    for shape_s, shape_r, bins, frac in (((20, 40, 48), (20, 40, 48), 256, 0.01), ((9, 33, 17), (12, 20, 31), 64, 0.05),
+                                         ((6, 50, 50), (6, 50, 50), 5000, 0.0), ((3, 7, 5), (2, 4, 9), 1, 0.0)):
+        F, _ = phantom_pair(shape_r)
+        _, M = phantom_pair(shape_s, case=2)
+        M = (M * 0.8 + 35.0 + rng.normal(0, 5, size=shape_s)).astype(np.float32)
+        M[0, 0, :3] = np.nan
+        M[1, 2, 3] = np.inf
+        F = F.copy()
+        F[-1, -1, -1] = -np.inf
+        want, wm = ext.histogram_match(M, F, bins, frac)
+        got, gm = histogram_match(M, F, bins, frac)
+        assert gm == wm
+        assert np.array_equal(got, want, equal_nan=True), (shape_s, bins, np.nanmax(np.abs(got - want)))

@@ -63,3 +63,18 @@ def test_restrict_prolong_definitions():
     ramp[..., 0] = np.arange(6)[None, None, :] * 2.0 + 0.5   # value = coarse-centre position in fine index units
     p = ext.prolong(ramp, (4, 10, 12))
     assert np.allclose(p[2, 3, 1:-1, 0], np.arange(12)[1:-1])  # linear functions are reproduced away from the clamped ends
+
+
+def test_histogram_match_restatement_reproduces_the_reference_known_answers():
+    """src/Alignment_Demons_Tests.cc:204-236: a 2x2 ramp 0..3 matched to 10..40 with 4 bins and no outliers gives exactly
+    10, 17.5, 25, 32.5; constant source or constant reference return the source unchanged."""
+    from oracle import extensions as ext
+    src = np.array([[0, 1], [2, 3]], dtype=np.float32)
+    ref = np.array([[10, 20], [30, 40]], dtype=np.float32)
+    out, mapped = ext.histogram_match(src, ref, 4, 0.0)
+    assert mapped and np.array_equal(out, np.array([[10.0, 17.5], [25.0, 32.5]], dtype=np.float32))
+    c5, c10 = np.full((2, 2), 5.0, np.float32), np.full((2, 2), 10.0, np.float32)
+    o, m = ext.histogram_match(c5, c10, 8, 0.0)
+    assert not m and np.array_equal(o, c5)
+    o, m = ext.histogram_match(src, c10, 8, 0.0)
+    assert not m and np.array_equal(o, src)
