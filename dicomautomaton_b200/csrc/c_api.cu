@@ -358,4 +358,10 @@ int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, const double *de
         errbuf_len);
 }
 
+int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *image, const dcma_b200_grid *dst_grid, float oob_value,
+                               float *out, int device, char *errbuf, size_t errbuf_len) {
+    if (!src_grid || !image || !dst_grid || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded([&]() { dcma::resample_to_grid_host(*src_grid, image, *dst_grid, oob_value, out, device); }, errbuf, errbuf_len);
+}
+
 }  // extern "C"

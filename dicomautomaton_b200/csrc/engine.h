@@ -69,4 +69,7 @@ int histogram_match_host(const float *source, long long n_src, const float *refe
 void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &image_grid,
                           const float *image, const unsigned char *mask, float oob_value, float *out, int device);
 
+void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
+                           float *out, int device);
+
 }  // namespace dcma

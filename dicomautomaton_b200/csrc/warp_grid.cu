@@ -104,6 +104,28 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// resample_image_to_reference_grid (src/Alignment_Demons.cc:709-755): every voxel of the destination grid takes the
+// trilinear sample of the source image at its own position, `oob_value` (the reference: NaN, cc:743) outside.
+__global__ void __launch_bounds__(256)
+    k_resample_grid(const GridK sg, const float *__restrict__ image, const GridK dg, const float oob_value, float *__restrict__ out) {
+    const long long nvox = static_cast<long long>(dg.S) * dg.R * dg.C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+        const int x = static_cast<int>(v % dg.C);
+        const long long r = v / dg.C;
+        const int y = static_cast<int>(r % dg.R);
+        const int z = static_cast<int>(r / dg.R);
+        double p[3], u[3];
+        for (int k = 0; k < 3; ++k) p[k] = dg.o[k] + x * dg.dx * dg.ex[k] + y * dg.dy * dg.ey[k] + z * dg.dz * dg.ez[k];
+        to_index(sg, p, u);
+        for (int c = 0; c < sg.CH; ++c) {
+            bool ok = false;
+            const double val = trilinear(image, sg, sg.CH, c, u, ok);
+            out[v * sg.CH + c] = ok ? static_cast<float>(val) : oob_value;
+        }
+    }
+}
+
 GridK make_gridk(const dcma_b200_grid &g) {
     if (g.geom.slices < 1 || g.geom.rows < 1 || g.geom.cols < 1 || g.geom.channels < 1)
         throw std::invalid_argument("grid extents and channel count must be >= 1");
@@ -168,6 +190,33 @@ void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deform
         throw;
     }
     cleanup();
+}
+
+void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
+                           float *out, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw CudaError(cudaErrorNoDevice, "no CUDA device is available (dcma_b200 has no CPU fallback)");
+    if (device >= 0) DCMA_CUDA(cudaSetDevice(device));
+    const GridK sg = make_gridk(src_grid);
+    const GridK dg = make_gridk(dst_grid);
+    const long long ns = static_cast<long long>(sg.S) * sg.R * sg.C * sg.CH, nd = static_cast<long long>(dg.S) * dg.R * dg.C * sg.CH;
+    float *dI = nullptr, *dO = nullptr;
+    try {
+        DCMA_CUDA(cudaMalloc(&dI, sizeof(float) * ns));
+        DCMA_CUDA(cudaMalloc(&dO, sizeof(float) * nd));
+        DCMA_CUDA(cudaMemcpy(dI, image, sizeof(float) * ns, cudaMemcpyHostToDevice));
+        const long long nv = static_cast<long long>(dg.S) * dg.R * dg.C;
+        k_resample_grid<<<static_cast<int>(std::min<long long>((nv + 255) / 256, 148LL * 16)), 256>>>(sg, dI, dg, oob_value, dO);
+        DCMA_CUDA(cudaGetLastError());
+        DCMA_CUDA(cudaMemcpy(out, dO, sizeof(float) * nd, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cudaFree(dI);
+        cudaFree(dO);
+        throw;
+    }
+    cudaFree(dI);
+    cudaFree(dO);
 }
 
 }  // namespace dcma

@@ -270,6 +270,19 @@ def warp_image_on_grid(field_grid: capi.Grid, deformation: np.ndarray, image_gri
     return out
 
 
+def resample_to_grid(src_grid: capi.Grid, image: np.ndarray, dst_grid: capi.Grid, oob_value: float = float("nan"),
+                     device: int = -1) -> np.ndarray:
+    """resample_image_to_reference_grid (reference src/Alignment_Demons.cc:709-755) for regular grids."""
+    lib = capi.lib()
+    img = np.ascontiguousarray(image, dtype=np.float32)
+    ch = int(src_grid.geom.channels)
+    out = np.empty((dst_grid.geom.slices, dst_grid.geom.rows, dst_grid.geom.cols) + ((ch,) if img.ndim == 4 else ()), dtype=np.float32)
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_resample_to_grid(C.byref(src_grid), img.ctypes.data, C.byref(dst_grid), float(oob_value),
+                                              out.ctypes.data, device, err, len(err)), err)
+    return out
+
+
 def restrict_image(image: demons_volume, device: int = -1) -> demons_volume:
     """Next-coarser pyramid level of an image (extension a12; definition in csrc/pyramid.cu)."""
     lib = capi.lib()

@@ -245,6 +245,12 @@ DCMA_B200_API int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, co
                                             const dcma_b200_grid *image_grid, const float *image, const unsigned char *mask,
                                             float oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* resample_image_to_reference_grid (src/Alignment_Demons.cc:709-755): the source image sampled trilinearly at the
+ * positions of the destination grid's voxels, `oob_value` (the reference passes NaN, cc:743) outside the source grid.
+ * out: dst voxels x src channels.  The reference's lookup is Ygor's (unpinned); definition as dcma_b200_warp_image_grid. */
+DCMA_B200_API int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *image, const dcma_b200_grid *dst_grid,
+                                             float oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,3 +257,14 @@ def histogram_match(source: np.ndarray, reference: np.ndarray, num_bins: int, ou
     mapped = np.where(v < smin, rmin, np.where(v > smax, rmax, lut[b]))          # cc:875-886
     out[fin] = mapped[fin].astype(np.float32)
     return out, True
+
+
+def resample_to_grid(image, s_spacing, s_origin, d_shape, d_spacing, d_origin, oob_value=np.nan):
+    """Row f2 (axis-aligned grids): trilinear sample of `image` at the destination voxels' positions (parity unpinned)."""
+    S, R, C = d_shape
+    z, y, x = np.meshgrid(np.arange(S, dtype=np.float64), np.arange(R, dtype=np.float64), np.arange(C, dtype=np.float64),
+                          indexing="ij")
+    p = [d_origin[0] + x * d_spacing[0], d_origin[1] + y * d_spacing[1], d_origin[2] + z * d_spacing[2]]
+    u = [(p[k] - s_origin[k]) / s_spacing[k] for k in range(3)]
+    val, ok = _trilinear(image, u)
+    return np.where(ok, val, oob_value).astype(np.float32)

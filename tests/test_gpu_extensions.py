@@ -181,3 +181,22 @@ def test_gpu_histogram_match_is_bit_identical_to_the_reference_algorithm():
         got, gm = histogram_match(M, F, bins, frac)
         assert gm == wm
         assert np.array_equal(got, want, equal_nan=True), (shape_s, bins, np.nanmax(np.abs(got - want)))
+
+
+def test_resample_to_grid_matches_the_restatement_and_the_reference_properties():
+    """Row f2: identity on the same grid, NaN outside a smaller source (src/Alignment_Demons_Tests.cc:171-202), and the
+    CPU restatement on a shifted, anisotropic destination grid."""
+    from dicomautomaton_b200.demons import make_grid, resample_to_grid
+    from oracle import extensions as ext
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-1000.0, 1000.0, size=(7, 9, 11)).astype(np.float32)
+    g = make_grid(img.shape, (1.0, 2.0, 3.0), (4.0, -2.0, 1.0))
+    assert np.array_equal(resample_to_grid(g, img, g), img)
+    bigger = make_grid((9, 11, 13), (1.0, 2.0, 3.0), (3.0, -4.0, -2.0))   # one voxel more on every side
+    out = resample_to_grid(g, img, bigger)
+    assert np.array_equal(out[1:-1, 1:-1, 1:-1], img) and np.isnan(out[0]).all() and np.isnan(out[:, :, -1]).all()
+    dshape, dsp, dorg = (10, 12, 9), (0.7, 1.3, 2.2), (5.1, -1.0, 2.5)
+    got = resample_to_grid(g, img, make_grid(dshape, dsp, dorg))
+    want = ext.resample_to_grid(img, (1.0, 2.0, 3.0), (4.0, -2.0, 1.0), dshape, dsp, dorg)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.nanmax(np.abs(got - want)) <= 1e-3
