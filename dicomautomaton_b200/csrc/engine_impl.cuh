@@ -32,6 +32,7 @@ struct SmoothPlan {
     bool active = false;  // sigma > 0 (cc:564-566)
     bool fast = false;    // fused k_smooth3d usable (equal radii <= kMaxFastRadius)
     int r[3] = {0, 0, 0};
+    int rk = 0;                // radius the fused kernel is instantiated for: max of r[]
     std::vector<double> w[3];  // normalised weights per axis (cc:587-597)
     SmoothWeights<T> W;
     T *tab[3] = {nullptr, nullptr, nullptr};        // per-position wsum (STRICT) or 1/wsum
@@ -529,19 +530,26 @@ class Engine final : public EngineBase {
             pl.dw[a] = alloc<double>(2 * rad + 1);
             DCMA_CUDA(cudaMemcpy(pl.dw[a], k.data(), sizeof(double) * k.size(), cudaMemcpyHostToDevice));
         }
-        pl.fast = (p_.fused != 0) && (pl.r[0] == pl.r[1]) && (pl.r[1] == pl.r[2]) && (pl.r[0] <= kMaxFastRadius);
+        // The fused kernel serves any per-axis radii up to kMaxFastRadius (anisotropic clinical spacing included): it
+        // is instantiated for rk = the largest of the three and the other axes' weights are zero-padded.
+        pl.rk = std::max(pl.r[0], std::max(pl.r[1], pl.r[2]));
+        pl.fast = (p_.fused != 0) && (pl.rk <= kMaxFastRadius);
         if (pl.fast) {
+            const int rk = pl.rk;
             for (int a = 0; a < 3; ++a) {
                 const int rad = pl.r[a];
-                for (int k = 0; k < 2 * rad + 1; ++k) pl.W.w[a][k] = static_cast<T>(pl.w[a][k]);
+                pl.W.r[a] = rad;
+                for (int k = 0; k < 2 * kMaxFastRadius + 1; ++k) pl.W.w[a][k] = T(0);
+                for (int k = -rad; k <= rad; ++k) pl.W.w[a][k + rk] = static_cast<T>(pl.w[a][k + rad]);
                 const int padded = ((extent[a] + 127) / 128) * 128 + 128;  // whole tiles: the kernel never tests bounds
                 std::vector<T> tab(padded, T(1));
                 for (int pos = 0; pos < extent[a]; ++pos) {
-                    // in-order accumulation over the in-grid taps, in the kernel's own type (cc:620-631)
+                    // in-order accumulation over the in-grid taps, in the kernel's own type (cc:620-631); the padded
+                    // zero weights leave the sum unchanged
                     T wsum = 0;
-                    for (int k = -rad; k <= rad; ++k) {
+                    for (int k = -rk; k <= rk; ++k) {
                         const int q = pos + k;
-                        if (q >= 0 && q < extent[a]) wsum += pl.W.w[a][k + rad];
+                        if (q >= 0 && q < extent[a]) wsum += pl.W.w[a][k + rk];
                     }
                     tab[pos] = STRICT ? wsum : static_cast<T>(1.0 / static_cast<double>(wsum));
                 }
@@ -800,7 +808,7 @@ class Engine final : public EngineBase {
     }
 
     void launch_smooth3d(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
-        switch (pl.r[0]) {
+        switch (pl.rk) {
             case 1: launch_smooth3d_r<1>(in, out, pl, it); break;
             case 2: launch_smooth3d_r<2>(in, out, pl, it); break;
             case 3: launch_smooth3d_r<3>(in, out, pl, it); break;

@@ -50,9 +50,13 @@ constexpr int kMaxFastRadius = 6;
 #endif
 
 // Per-launch constants of one smoothing call (kernel parameter space => uniform/constant-bank reads).
+// The fused kernel is instantiated for ONE radius R = max(r_x, r_y, r_z); an axis with a smaller radius gets its
+// weights zero-padded around the centre (w[a][k], k - R = tap offset).  A zero-weight tap adds exactly 0 to the sum and
+// to the weight sum, so the arithmetic of the true taps, order included, is unchanged.
 template <typename T>
 struct SmoothWeights {
-    T w[3][2 * kMaxFastRadius + 1];  // [axis: 0=x,1=y,2=z][k + r]
+    T w[3][2 * kMaxFastRadius + 1];  // [axis: 0=x,1=y,2=z][k + R]
+    int r[3];                        // true radii per axis (cc:574-576), for the literal fallback
 };
 
 // STRICT: table holds wsum (divide, as the reference does); otherwise it holds 1/wsum (multiply).
@@ -202,27 +206,27 @@ struct Smooth3dCfg {
 
 // The literal definition for ONE output voxel, straight from global memory (cc:609-693): used only when the fast path
 // produced a non-finite value, i.e. when some tap in the (2r+1)^3 support is non-finite.  Deliberately not inlined.
-template <typename T, int R>
+template <typename T>
 __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g, const double *__restrict__ dwx,
-                                         const double *__restrict__ dwy, const double *__restrict__ dwz, int x, int y,
-                                         int z) {
+                                         const double *__restrict__ dwy, const double *__restrict__ dwz, const int rx,
+                                         const int ry, const int rz, int x, int y, int z) {
     const long long plane = static_cast<long long>(g.R) * g.C;
     T zs = 0, zw = 0, z_centre = 0;
-    for (int kz = -R; kz <= R; ++kz) {
+    for (int kz = -rz; kz <= rz; ++kz) {
         const int zz = z + kz;  // local slice; in-grid test on the global index
         if (zz + g.zoff < 0 || zz + g.zoff >= g.Sg || zz < 0 || zz >= g.S) continue;
         T ys = 0, yw = 0, y_centre = 0;
-        for (int ky = -R; ky <= R; ++ky) {
+        for (int ky = -ry; ky <= ry; ++ky) {
             const int yy = y + ky;
             if (yy < 0 || yy >= g.R) continue;
             const T *row = src + zz * plane + static_cast<long long>(yy) * g.C;
             T xs = 0, xw = 0;
-            for (int kx = -R; kx <= R; ++kx) {
+            for (int kx = -rx; kx <= rx; ++kx) {
                 const int xx = x + kx;
                 if (xx < 0 || xx >= g.C) continue;
                 const T val = row[xx];
                 if (isfinite(val)) {
-                    const T wk = static_cast<T>(dwx[kx + R]);
+                    const T wk = static_cast<T>(dwx[kx + rx]);
                     xs += wk * val;
                     xw += wk;
                 }
@@ -230,7 +234,7 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
             const T xv = (xw > T(0)) ? (xs / xw) : row[x];
             if (ky == 0) y_centre = xv;
             if (isfinite(xv)) {
-                const T wk = static_cast<T>(dwy[ky + R]);
+                const T wk = static_cast<T>(dwy[ky + ry]);
                 ys += wk * xv;
                 yw += wk;
             }
@@ -238,7 +242,7 @@ __device__ __noinline__ T smooth_literal(const T *__restrict__ src, const Geo g,
         const T yv = (yw > T(0)) ? (ys / yw) : y_centre;
         if (kz == 0) z_centre = yv;
         if (isfinite(yv)) {
-            const T wk = static_cast<T>(dwz[kz + R]);
+            const T wk = static_cast<T>(dwz[kz + rz]);
             zs += wk * yv;
             zw += wk;
         }
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
                     for (int i = 0; i < VW; ++i)
                         if (!isfinite(o.v[i]) && gy < g.R && gx_out + i < g.C)
-                            o.v[i] = smooth_literal<T, R>(src, g, dwx, dwy, dwz, gx_out + i, gy, zo);
+                            o.v[i] = smooth_literal<T>(src, g, dwx, dwy, dwz, W.r[0], W.r[1], W.r[2], gx_out + i, gy, zo);
                 }
                 if (gy < g.R) {
                     T *p = dst + zo * plane + static_cast<long long>(gy) * g.C + gx_out;
