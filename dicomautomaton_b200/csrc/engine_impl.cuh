@@ -752,11 +752,13 @@ class Engine final : public EngineBase {
     template <int R, int TX, int TY, int NT, int MINB, bool VEC>
     void launch_smooth3d_cfg(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
         using Cfg = Smooth3dCfg<T, R, TX, TY, NT>;
-        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, MINB, VEC>;
+        constexpr bool WS = (DCMA_SMOOTH_WS < 0) ? (sizeof(T) == 8) : (DCMA_SMOOTH_WS != 0);
+        constexpr int NTL = WS ? 2 * NT : NT;  // threads per CTA at launch
+        constexpr size_t SMEM = WS ? Cfg::smem_bytes_ws : Cfg::smem_bytes;
+        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, (WS ? 2 : MINB), VEC, WS>;
         static thread_local bool attr_set[64] = {false};
         if (!attr_set[dev_ & 63]) {
-            DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(Cfg::smem_bytes)));
+            DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM)));
             // without this the driver picks the smallest L1/shared split that fits ONE block (ncu: 1 block/SM)
             DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                            cudaSharedmemCarveoutMaxShared));
@@ -766,7 +768,7 @@ class Engine final : public EngineBase {
         // z chunks: score = (fraction of slice steps that produce output) x (wave efficiency); every chunk re-stages
         // 2R slices of warm-up, and a partially filled last wave idles SMs.
         int blocks_per_sm = 1;
-        DCMA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NT, Cfg::smem_bytes));
+        DCMA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NTL, SMEM));
         const double slots = static_cast<double>(std::max(1, blocks_per_sm)) * sms_;
         const long long nxy = static_cast<long long>(gx) * gy * 3;
         int best_nz = 1;
@@ -786,7 +788,7 @@ class Engine final : public EngineBase {
         const int zchunk = (So + best_nz - 1) / best_nz;
         const int nz = (So + zchunk - 1) / zchunk;
         if (3LL * nz > 65535 || gy > 65535) throw std::invalid_argument("volume exceeds the smoothing kernel's grid limits");
-        kern<<<dim3(gx, gy, 3 * nz), NT, Cfg::smem_bytes, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2] + g_.zoff,
+        kern<<<dim3(gx, gy, 3 * nz), NTL, SMEM, stream_>>>(in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2] + g_.zoff,
                                                                      pl.dw[0], pl.dw[1], pl.dw[2], zchunk, nz, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;

@@ -42,6 +42,10 @@ constexpr int kMaxFastRadius = 6;
 #ifndef DCMA_SMOOTH_XPRELOAD
 #define DCMA_SMOOTH_XPRELOAD 0
 #endif
+#ifndef DCMA_SMOOTH_WS
+#define DCMA_SMOOTH_WS -1  // warp-specialised CTAs (producer/consumer warpgroups): 1 on, 0 off, -1 = per type (fp64 on:
+                           // measured -8 % per launch at 512x512x256; fp32 off: no gain)
+#endif
 #ifndef DCMA_SMOOTH_YBATCH
 #define DCMA_SMOOTH_YBATCH 0
 #endif
@@ -185,6 +189,12 @@ __device__ __forceinline__ void cp_async_small(void *smem_dst, const void *gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+// named barriers (ids 1..15; 0 is __syncthreads): `count` threads must arrive (bar.sync also waits)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <typename T, int R, int TX, int TY, int NT>
 struct Smooth3dCfg {
     static constexpr int VW = 16 / sizeof(T);             // elements per 16-byte vector
@@ -201,6 +211,8 @@ struct Smooth3dCfg {
     static constexpr int CPR = PW / VW;                   // 16-byte copies per staged row
     static constexpr int NCP = (PH * CPR + NT - 1) / NT;  // 16-byte copies per thread per slice
     static constexpr size_t smem_bytes = (size_t(2) * PH * PW + size_t(PH) * TX) * sizeof(T);
+    // warp-specialised variant: 3 staged input tiles (two slice steps of lead) + 2 x-pass output tiles (hand-off)
+    static constexpr size_t smem_bytes_ws = (size_t(3) * PH * PW + size_t(2) * PH * TX) * sizeof(T);
     static_assert(TX % VW == 0 && NT % QX == 0 && TY % RG == 0 && (QX & (QX - 1)) == 0, "tile/thread shape");
 };
 
@@ -291,8 +303,12 @@ __device__ __forceinline__ void dispatch_phase(const int phase, F &f) {
 
 // grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks.
 // tab_x / tab_y / tab_z are padded by the host to whole tiles (no bounds tests here).
-template <typename T, bool STRICT, int R, int TX, int TY, int NT, int MINB, bool VEC>
-__global__ void __launch_bounds__(NT, MINB)
+// WS (warp-specialised, DCMA_SMOOTH_WS): the CTA has 2*NT threads; threads [0, NT) are PRODUCERS (cp.async staging + x
+// pass, ~56 registers after setmaxnreg.dec), threads [NT, 2*NT) CONSUMERS (y pass into the register ring, z pass, stores;
+// ~200 registers after setmaxnreg.inc).  Hand-off through two x-pass tiles and named barriers: full[b] (producers
+// arrive, consumers wait) and empty[b] (consumers arrive, producers wait).
+template <typename T, bool STRICT, int R, int TX, int TY, int NT, int MINB, bool VEC, bool WS = false>
+__global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
     k_smooth3d(const T *__restrict__ in, T *__restrict__ out, const Geo g, const SmoothWeights<T> W,
                const T *__restrict__ tab_x, const T *__restrict__ tab_y, const T *__restrict__ tab_z,
                const double *__restrict__ dwx, const double *__restrict__ dwy, const double *__restrict__ dwz,
@@ -309,10 +325,11 @@ __global__ void __launch_bounds__(NT, MINB)
     if (it > ctrl->converged_at) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *s_in = reinterpret_cast<T *>(smem_raw);  // [2][PH][PW]
-    T *s_x = s_in + 2 * PH * PW;                // [PH][TX]
+    T *s_in = reinterpret_cast<T *>(smem_raw);  // [2 (WS: 3)][PH][PW]
+    T *s_x = s_in + (WS ? 3 : 2) * PH * PW;     // [1 (WS: 2)][PH][TX]
 
-    const int tid = threadIdx.x;
+    const bool producer = WS && (threadIdx.x < NT);
+    const int tid = WS ? (threadIdx.x % NT) : threadIdx.x;
     const int comp = blockIdx.z / nzchunks;
     const int chunk = blockIdx.z - comp * nzchunks;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
@@ -410,25 +427,12 @@ __global__ void __launch_bounds__(NT, MINB)
             for (int k = 0; k < TAPS; ++k) win[j][i][k] = LG::zero();
 
     const int zp_first = z_begin - R, zp_last = z_end - 1 + R;
-    stage(zp_first, 0);
-    cp_async_commit();
+    const auto in_grid = [&](int zp) { return zp + g.zoff >= 0 && zp + g.zoff < g.Sg && zp >= 0 && zp < g.S; };
 
-    // One slice step = xstep(zp) [staging + x pass, phase independent] followed by ring(P) [y pass into ring slot
-    // P = (zp - zp_first) % TAPS, then the z pass].
-    bool slice_in = false;
-    int zo = 0;  // output slice completed by the current step
-    auto xstep = [&](const int zp) {
-        const int buf = (zp - zp_first) & 1;
-        cp_async_wait_all();
-        __syncthreads();  // s_in[buf] complete; everyone is done with s_x and s_in[buf^1] of the previous step
-        if (zp + 1 <= zp_last) stage(zp + 1, buf ^ 1);
-        cp_async_commit();
-        if (zp + 1 + DCMA_SMOOTH_PF <= zp_last) l2_prefetch(zp + 1 + DCMA_SMOOTH_PF);
-
-        slice_in = (zp + g.zoff >= 0 && zp + g.zoff < g.Sg && zp >= 0 && zp < g.S);
-        zo = zp - R;
-        if (slice_in) {
-            const T *sb = s_in + buf * PH * PW;
+    // ---- x pass of one staged slice tile: sb -> sx
+    const T *sxr = s_x;  // the x-pass tile the y pass of the current step reads
+    auto xpass = [&](const T *__restrict__ sb, T *__restrict__ sx) {
+        {
             // ---- x pass: s_in -> s_x.  Task = one vector of VW outputs; q == qx for every task of this thread.
             // fp32: the operands of ALL x tasks are requested before the first task computes (the three shared-memory
             // latencies overlap instead of adding up; fp64 has no registers to spare for that)
@@ -505,8 +509,29 @@ __global__ void __launch_bounds__(NT, MINB)
                         o.v[i] = normalise<T, STRICT>(sum, nx[i]);
                     }
                 }
-                *reinterpret_cast<Vec *>(s_x + row * TX + qx * VW) = o;
+                *reinterpret_cast<Vec *>(sx + row * TX + qx * VW) = o;
             }
+        }
+    };
+
+    // One slice step (not WS) = xstep(zp) [staging + x pass, phase independent] followed by ring(P) [y pass into ring
+    // slot P = (zp - zp_first) % TAPS, then the z pass].
+    T nz_next = tab_z[z_begin < z_end ? z_begin : 0];
+    bool slice_in = false;
+    int zo = 0;               // output slice completed by the current step
+    int ws_b2 = 0;            // WS: index of the x-pass tile of the current step
+    bool ws_release = false;  // WS: whether the producers will wait for this tile's release
+    auto xstep = [&](const int zp) {
+        const int buf = (zp - zp_first) & 1;
+        cp_async_wait_all();
+        __syncthreads();  // s_in[buf] complete; everyone is done with s_x and s_in[buf^1] of the previous step
+        if (zp + 1 <= zp_last) stage(zp + 1, buf ^ 1);
+        cp_async_commit();
+        if (zp + 1 + DCMA_SMOOTH_PF <= zp_last) l2_prefetch(zp + 1 + DCMA_SMOOTH_PF);
+        slice_in = in_grid(zp);
+        zo = zp - R;
+        if (slice_in) {
+            xpass(s_in + buf * PH * PW, s_x);
             __syncthreads();
         }
     };
@@ -524,7 +549,7 @@ __global__ void __launch_bounds__(NT, MINB)
                     // DCMA_SMOOTH_YBATCH > 0: at most that many row vectors are in flight (a compiler-level fence
                     // keeps the shared-memory loads from all being hoisted to the front) -- fewer live registers
                     if (DCMA_SMOOTH_YBATCH > 0 && m > 0 && (m % DCMA_SMOOTH_YBATCH) == 0) asm volatile("" ::: "memory");
-                    const Vec t = *reinterpret_cast<const Vec *>(s_x + (yl0 + m) * TX + qx * VW);
+                    const Vec t = *reinterpret_cast<const Vec *>(sxr + (yl0 + m) * TX + qx * VW);
 #pragma unroll
                     for (int j = 0; j < OY; ++j) {
                         const int k = m - j;
@@ -555,8 +580,17 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
                     for (int i = 0; i < NG; ++i) win[j][i][P] = LG::zero();
             }
+            if constexpr (WS) {  // the y pass has the tile in registers: the producers may overwrite it
+                if (ws_release) named_bar_arrive(4 + ws_b2, 2 * NT);
+            }
+            // z normaliser of this output slice, requested one step ago (its L2 latency would otherwise sit on the
+            // critical path of every step); the next one is requested now
+            // (not in the plain fp64 kernel: it sits at its 168-register cap and the extra value would spill)
+            constexpr bool NZ_AHEAD = WS || PACKED;
+            T nz = nz_next;
+            if constexpr (NZ_AHEAD) nz_next = tab_z[min(max(zo + 1, z_begin), z_end - 1)];
             if (zo < z_begin) return;  // warm-up slices of this chunk; zo < z_end holds by construction of zp_last
-            const T nz = tab_z[zo];
+            if constexpr (!NZ_AHEAD) nz = tab_z[zo];
             // JB rows advance together, tap-major: independent FMA chains back to back (fp32: all rows; fp64 keeps
             // one row at a time, its register file has no room for more accumulators)
             constexpr int JB = PACKED ? OY : 1;
@@ -611,6 +645,61 @@ __global__ void __launch_bounds__(NT, MINB)
         }
     };
 
+    if constexpr (WS) {
+        constexpr int kBarProd = 1, kBarFull = 2, kBarEmpty = 4;  // named barrier ids (+ tile index for full/empty)
+        const int n_steps = zp_last - zp_first + 1;
+        if (producer) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            stage(zp_first, 0);
+            cp_async_commit();
+            if (zp_first + 1 <= zp_last) stage(zp_first + 1, 1);
+            cp_async_commit();
+            int b3 = 0;
+            for (int it2 = 0; it2 < n_steps; ++it2) {
+                const int zp = zp_first + it2, b2 = it2 & 1;
+                cp_async_wait_pending<1>();    // this thread's chunks of slice zp have landed (one newer group may fly)
+                named_bar_sync(kBarProd, NT);  // ... and every producer's; all are done with the x pass of slice zp-1
+                const int n3 = (b3 == 0) ? 2 : b3 - 1;  // (it2 + 2) % 3: the tile the x pass of slice zp-1 has just left
+                if (zp + 2 <= zp_last) stage(zp + 2, n3);
+                cp_async_commit();
+                if (it2 >= 2) named_bar_sync(kBarEmpty + b2, 2 * NT);  // consumers are done with the tile of slice zp-2
+                if (in_grid(zp)) xpass(s_in + b3 * PH * PW, s_x + b2 * PH * TX);
+                named_bar_arrive(kBarFull + b2, 2 * NT);
+                b3 = (b3 == 2) ? 0 : b3 + 1;
+            }
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        if constexpr (PACKED) {
+            int phase = 0;
+            for (int it2 = 0; it2 < n_steps; ++it2) {
+                const int zp = zp_first + it2;
+                ws_b2 = it2 & 1;
+                ws_release = (it2 + 2 < n_steps);  // the last two tiles are never reused: nobody waits for their release
+                named_bar_sync(kBarFull + ws_b2, 2 * NT);
+                sxr = s_x + ws_b2 * PH * TX;
+                slice_in = in_grid(zp);
+                zo = zp - R;
+                dispatch_phase<TAPS>(phase, ring);
+                phase = (phase + 1 == TAPS) ? 0 : phase + 1;
+            }
+        } else {
+            auto step = [&](auto ph, const int zp) {
+                const int it2 = zp - zp_first;
+                ws_b2 = it2 & 1;
+                ws_release = (it2 + 2 < n_steps);
+                named_bar_sync(kBarFull + ws_b2, 2 * NT);
+                sxr = s_x + ws_b2 * PH * TX;
+                slice_in = in_grid(zp);
+                zo = zp - R;
+                ring(ph);
+            };
+            for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
+        }
+        return;
+    }
+    stage(zp_first, 0);
+    cp_async_commit();
     if constexpr (PACKED) {
         // fp32: one copy of the step; a uniform jump per slice selects the ring phase (small code, fits the I-cache)
         int phase = 0;
