@@ -46,6 +46,9 @@ constexpr int kMaxFastRadius = 6;
 #define DCMA_SMOOTH_WS -1  // warp-specialised CTAs (producer/consumer warpgroups): 1 on, 0 off, -1 = per type (fp64 on:
                            // measured -8 % per launch at 512x512x256; fp32 off: no gain)
 #endif
+#ifndef DCMA_SMOOTH_WS_JB
+#define DCMA_SMOOTH_WS_JB 0  // warp-specialised fp64: advance all rows' z chains together (consumers have the registers)
+#endif
 #ifndef DCMA_SMOOTH_YBATCH
 #define DCMA_SMOOTH_YBATCH 0
 #endif
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
             if constexpr (!NZ_AHEAD) nz = tab_z[zo];
             // JB rows advance together, tap-major: independent FMA chains back to back (fp32: all rows; fp64 keeps
             // one row at a time, its register file has no room for more accumulators)
-            constexpr int JB = PACKED ? OY : 1;
+            constexpr int JB = (PACKED || (WS && DCMA_SMOOTH_WS_JB)) ? OY : 1;
 #pragma unroll
             for (int jb = 0; jb < OY; jb += JB) {
                 GV zs[JB][NG];
