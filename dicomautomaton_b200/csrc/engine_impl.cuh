@@ -30,7 +30,7 @@ using namespace ::dcma;
 template <typename T>
 struct SmoothPlan {
     bool active = false;  // sigma > 0 (cc:564-566)
-    bool fast = false;    // fused k_smooth3d usable (equal radii <= kMaxFastRadius)
+    bool fast = false;    // fused k_smooth3d usable (every radius <= kMaxFastRadius)
     int r[3] = {0, 0, 0};
     int rk = 0;                // radius the fused kernel is instantiated for: max of r[]
     std::vector<double> w[3];  // normalised weights per axis (cc:587-597)
@@ -796,8 +796,9 @@ class Engine final : public EngineBase {
 
     template <int R>
     void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
-        // 128-thread CTAs, 2 adjacent output rows x one 16-byte vector per thread; the register z window (72 regs)
-        // puts the kernel at ~165 registers, so 3 CTAs/SM.  float: 64x16 tile; double: 32x16 tile.
+        // NT = 128 threads per role, 2 adjacent output rows x one 16-byte vector per thread; the register z window
+        // (72 registers) puts the one-role kernel at ~165 registers, so 3 CTAs/SM (fp32); the warp-specialised form
+        // (fp64) launches 2*NT threads, 2 CTAs/SM.  float: 64x16 tile; double: 32x16 tile.
         constexpr int TX = (sizeof(T) == 4) ? 64 : 32;
         constexpr int TY = DCMA_SMOOTH_TY;
         constexpr int NT = DCMA_SMOOTH_NT;

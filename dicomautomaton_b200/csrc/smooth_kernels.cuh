@@ -8,11 +8,15 @@
 //
 // Two implementations with identical results:
 //  * k_smooth_axis   -- one axis per launch, runtime radius, per-tap bounds+finite tests (the literal restatement;
-//                       used for anisotropic/large radii and as the `fused=0` path).
+//                       used for radii above kMaxFastRadius and as the `fused=0` path).
 //  * k_smooth3d      -- ONE launch for all three passes: a CTA owns an x-y tile, marches along z, stages each input
-//                       slice tile (+halo) in shared memory with cp.async (double buffered), does the x and y passes
-//                       in shared memory and keeps the last 2r+1 xy-smoothed values of its voxels in REGISTERS for the
-//                       z pass.  Every field element is read from HBM once (+halo, served by L2) and written once.
+//                       slice tile (+halo) in shared memory with cp.async, does the x and y passes in shared memory and
+//                       keeps the last 2r+1 xy-smoothed values of its voxels in REGISTERS (a ring with compile-time
+//                       indices) for the z pass.  Every field element is read from HBM once (+halo, served by L2) and
+//                       written once.  Per-axis radii may differ (zero-padded weights, see SmoothWeights).
+//                       fp32: packed FFMA2 lanes, one 128-thread role per CTA, 3 CTAs/SM.
+//                       fp64: warp-specialised CTAs -- a producer warpgroup (staging + x pass) and a consumer warpgroup
+//                       (y pass, ring, z pass, stores) with setmaxnreg and named barriers, 2 CTAs/SM.
 //    Out-of-grid taps are staged as 0 and the per-position weight sums come from host tables built by in-order
 //    accumulation, so for finite fields the arithmetic (order included) equals the reference's; a non-finite result
 //    re-runs that output through the literal per-tap path, which makes the two implementations agree on any input.
