@@ -414,8 +414,11 @@ __device__ __forceinline__ void apply_stop_rule(Ctrl *ctrl, double sum, long lon
     }
 }
 
+#ifndef DCMA_FORCE_MINB64
+#define DCMA_FORCE_MINB64 4  // fp64: 64 registers, 4 blocks/SM measured 16 % faster than 80 registers, 3 blocks/SM
+#endif
 template <typename T, bool STRICT, typename IX, bool CH1, bool SYM>
-__global__ void __launch_bounds__(kTileX *kTileY)
+__global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_MINB64 : 4))
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
                  const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
                  const ForceK fk, double *part_sum, long long *part_cnt, Ctrl *ctrl, const long long it,
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(256)
 // fp64: 24 gathered doubles per voxel put the kernel at ~100 registers (2 blocks/SM); capping it at 85 (3 blocks/SM)
 // measured 3 % faster.  fp32 needs no cap (48 registers).
 template <typename T, bool STRICT, typename IX>
-__global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 1))
+__global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
     k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int zlen, Ctrl *__restrict__ ctrl,
               const long long it) {
     using CT = T;
