@@ -50,6 +50,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         "dcma_b200_geom": (capi.Geom, [f[0] for f in capi.Geom._fields_]),
         "dcma_b200_demons_params": (capi.Params, [f[0] for f in capi.Params._fields_]),
         "dcma_b200_run_stats": (capi.RunStats, [f[0] for f in capi.RunStats._fields_]),
+        "dcma_b200_grid": (capi.Grid, [f[0] for f in capi.Grid._fields_]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dcma_b200/demons_c_api.h"', 'int main(void){']
     for name, (_, fl) in fields.items():
@@ -146,3 +147,25 @@ def test_empty_input_returns_none_like_the_reference():
     full = demons_volume(np.zeros((2, 4, 4), np.float32))
     assert AlignViaDemons(AlignViaDemonsParams(verbosity=0), empty, full) is None
     assert AlignViaDemons(AlignViaDemonsParams(verbosity=0), full, empty) is None
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 with warnings as errors, and examples/register_from_c.c links
+    against libdcma_b200.so; without a device it reports DCMA_B200_ENODEVICE and exits 0 (no CPU fallback)."""
+    from dicomautomaton_b200 import capi
+    hdr = tmp_path / "only_header.c"
+    hdr.write_text('#include "dcma_b200/demons_c_api.h"\nint main(void){return DCMA_B200_ABI_VERSION == 1 ? 0 : 1;}\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-fsyntax-only", str(hdr)])
+    exe = tmp_path / "register_from_c"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "register_from_c.c"), "-L", libdir, "-ldcma_b200",
+                           f"-Wl,-rpath,{libdir}", "-lm", "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dcma_b200 ABI 1" in r.stdout
+    if capi.lib().dcma_b200_device_count() == 0:
+        assert "registration failed (-2)" in r.stdout
+    else:
+        assert "MSE" in r.stdout
