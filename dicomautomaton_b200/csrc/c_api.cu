@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <new>
@@ -226,6 +227,7 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
                 }
                 return;
             }
+            const auto tc = clk::now();
             h.p = make(*geom, *params, nullptr);
             const auto t0 = clk::now();
             h.p->load(fixed, moving, false);
@@ -235,6 +237,11 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
             const auto t2 = clk::now();
             h.p->get(DCMA_B200_BUF_DEFORMATION, deformation_out);
             const auto t3 = clk::now();
+            if (std::getenv("DCMA_B200_TRACE")) {  // host-side phase times of the one-shot call (diagnostics)
+                auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                std::fprintf(stderr, "[dcma_b200] create %.2f ms, load(H2D) %.2f ms, run %.2f ms (device loop %.2f ms), get(D2H) %.2f ms\n",
+                             ms(tc, t0), ms(t0, t1), ms(t1, t2), local.loop_ms, ms(t2, t3));
+            }
             if (stats) {
                 *stats = local;
                 const long long n = geom->slices * geom->rows * geom->cols;
