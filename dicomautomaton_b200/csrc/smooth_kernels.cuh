@@ -50,6 +50,17 @@ constexpr int kMaxFastRadius = 6;
 #define DCMA_SMOOTH_WS -1  // warp-specialised CTAs (producer/consumer warpgroups): 1 on, 0 off, -1 = per type (fp64 on:
                            // measured -8 % per launch at 512x512x256; fp32 off: no gain)
 #endif
+#ifndef DCMA_SMOOTH_XW
+#define DCMA_SMOOTH_XW 1  // warp-specialised fp64 only: output vectors per x-pass task (1, 2 or 4).  Wider tasks read each
+                          // staged value fewer times (shared-memory wavefronts of the x pass: 288 -> 192 -> 144 per step)
+                          // but keep fewer producer threads busy: measured 4.11 / 4.29 / 4.62 ms per iteration for 1 / 2 / 4
+#endif
+#ifndef DCMA_SMOOTH_WS_PREG
+#define DCMA_SMOOTH_WS_PREG 56   // registers per producer thread after setmaxnreg.dec
+#endif
+#ifndef DCMA_SMOOTH_WS_CREG
+#define DCMA_SMOOTH_WS_CREG 200  // registers per consumer thread after setmaxnreg.inc (PREG + CREG <= 256)
+#endif
 #ifndef DCMA_SMOOTH_WS_JB
 #define DCMA_SMOOTH_WS_JB 0  // warp-specialised fp64: advance all rows' z chains together (consumers have the registers)
 #endif
@@ -422,6 +433,18 @@ __global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
 #pragma unroll
             for (int i = 0; i < NG; ++i) nxy[j][i] = LG::pack(nx[2 * i] * ny[j], nx[2 * i + 1] * ny[j]);
     }
+    // wide x-pass tasks (producers of the warp-specialised fp64 kernel): XW adjacent output vectors per task; a thread
+    // keeps its column group, so the x normalisers of its XW*VW outputs are loop invariants
+    constexpr int XW = (WS && !PACKED) ? DCMA_SMOOTH_XW : 1;
+    static_assert(XW >= 1 && QX % XW == 0 && NT % (QX / XW) == 0, "x-pass task width");
+    constexpr int XCG = QX / XW;   // column groups per staged row
+    constexpr int XRPP = NT / XCG;  // rows covered per pass of the role's NT threads
+    const int xcg = tid % XCG, xr0 = tid / XCG;
+    T nxw[XW * VW];
+    if constexpr (XW > 1) {
+#pragma unroll
+        for (int j = 0; j < XW * VW; ++j) nxw[j] = tab_x[x0 + xcg * XW * VW + j];
+    }
 
     // z window: the last TAPS xy-smoothed values of each owned output, in registers, used as a RING: the ring insert
     // and the z pass exist once per ring phase so that every ring index is a compile-time constant.
@@ -443,6 +466,34 @@ __global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
             // ---- x pass: s_in -> s_x.  Task = one vector of VW outputs; q == qx for every task of this thread.
             // fp32: the operands of ALL x tasks are requested before the first task computes (the three shared-memory
             // latencies overlap instead of adding up; fp64 has no registers to spare for that)
+            if constexpr (XW > 1) {
+                constexpr int NVX = XW + 2 * HX / VW;  // vectors read per task
+#pragma unroll
+                for (int pass = 0; pass < (PH + XRPP - 1) / XRPP; ++pass) {
+                    const int row = xr0 + pass * XRPP;
+                    if (row >= PH) break;
+                    T a[VW * NVX];
+#pragma unroll
+                    for (int m = 0; m < NVX; ++m) {
+                        const Vec t = *reinterpret_cast<const Vec *>(sb + row * PW + (xcg * XW + m) * VW);
+#pragma unroll
+                        for (int i = 0; i < VW; ++i) a[m * VW + i] = t.v[i];
+                    }
+#pragma unroll
+                    for (int v = 0; v < XW; ++v) {
+                        Vec o;
+#pragma unroll
+                        for (int i = 0; i < VW; ++i) {
+                            T sum = DCMA_WX(0) * a[HX - R + v * VW + i];  // the same taps in the same order as the narrow task
+#pragma unroll
+                            for (int k = 1; k < TAPS; ++k) sum += DCMA_WX(k) * a[HX - R + v * VW + i + k];
+                            o.v[i] = normalise<T, STRICT>(sum, nxw[v * VW + i]);
+                        }
+                        *reinterpret_cast<Vec *>(sx + row * TX + (xcg * XW + v) * VW) = o;
+                    }
+                }
+                return;
+            }
             constexpr bool PRELOAD = PACKED && (DCMA_SMOOTH_XPRELOAD != 0);
             Vec pre[PRELOAD ? XN : 1][PRELOAD ? NV : 1];
             if constexpr (PRELOAD) {
@@ -656,7 +707,7 @@ __global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
         constexpr int kBarProd = 1, kBarFull = 2, kBarEmpty = 4;  // named barrier ids (+ tile index for full/empty)
         const int n_steps = zp_last - zp_first + 1;
         if (producer) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCMA_SMOOTH_WS_PREG));
             stage(zp_first, 0);
             cp_async_commit();
             if (zp_first + 1 <= zp_last) stage(zp_first + 1, 1);
@@ -676,7 +727,8 @@ __global__ void __launch_bounds__(WS ? 2 * NT : NT, MINB)
             }
             return;
         }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCMA_SMOOTH_WS_CREG));
+        static_assert(DCMA_SMOOTH_WS_PREG + DCMA_SMOOTH_WS_CREG <= 256, "register split exceeds the CTA's allocation");
         if constexpr (PACKED) {
             int phase = 0;
             for (int it2 = 0; it2 < n_steps; ++it2) {
