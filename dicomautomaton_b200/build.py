@@ -37,6 +37,7 @@ UNITS = {
     "pyramid.cu": [],
     "warp_grid.cu": [],
     "histmatch.cu": ["-fmad=false"],
+    "text_io.cu": [],
     "c_api.cu": [],
 }
 
@@ -52,7 +53,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(INCLUDE, "dcma_b200")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h", ".inc")):
                 h.update(name.encode())
                 h.update(open(os.path.join(root, name), "rb").read())
     h.update(json.dumps([ARCH, COMMON, UNITS], sort_keys=True).encode())

@@ -371,4 +371,23 @@ int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *imag
     return guarded([&]() { dcma::resample_to_grid_host(*src_grid, image, *dst_grid, oob_value, out, device); }, errbuf, errbuf_len);
 }
 
+int dcma_b200_format_doubles(const double *values, int64_t n, char *text, int64_t capacity, int64_t *text_len, int device,
+                             char *errbuf, size_t errbuf_len) {
+    if ((n > 0 && (!values || !text)) || !text_len) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    *text_len = 0;
+    return guarded([&]() { *text_len = dcma::format_doubles_host(values, n, text, capacity, device); }, errbuf, errbuf_len);
+}
+
+int dcma_b200_parse_doubles(const char *text, int64_t text_len, int64_t n, double *values, int64_t *consumed, int device,
+                            char *errbuf, size_t errbuf_len) {
+    if (n > 0 && (!values || (!text && text_len > 0))) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    if (consumed) *consumed = 0;
+    return guarded(
+        [&]() {
+            const long long used = dcma::parse_doubles_host(text, text_len, n, values, device);
+            if (consumed) *consumed = used;
+        },
+        errbuf, errbuf_len);
+}
+
 }  // extern "C"

@@ -72,4 +72,8 @@ void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deform
 void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
                            float *out, int device);
 
+// the numeric payload of deformation_field::write_to / read_from (src/Alignment_Field.cc:322-436) on the GPU (text_io.cu)
+long long format_doubles_host(const double *values, long long n, char *out, long long capacity, int device);
+long long parse_doubles_host(const char *text, long long nbytes, long long n, double *out, int device);
+
 }  // namespace dcma

@@ -1,15 +1,21 @@
 // Stand-in for the reference's src/Alignment_Field.h, used ONLY to build the host-side tests in this container, where
 // the real file cannot compile (it needs Ygor, Structs.h, Boost...).  Inside the reference tree the drop-in uses the
 // reference's own deformation_field unchanged.  Mirrors src/Alignment_Field.h:34-77 / .cc:45-153 for the members the
-// Demons path touches: construction from a 3-channel regular stack, the two accessors and transform().
+// Demons path touches: construction from a 3-channel regular stack, the two accessors, transform() and the text
+// (de)serialisation, which defers to host/Alignment_Field_IO.{h,cc} the way INTEGRATION.md installs it in the reference.
 #pragma once
 #include <functional>
 #include <limits>
 #include <optional>
 #include <stdexcept>
 
+#include <istream>
+#include <ostream>
+
 #include "YgorImages.h"
 #include "YgorMath.h"
+
+#include "Alignment_Field_IO.h"
 
 class deformation_field {
     planar_image_collection<double, double> field;
@@ -31,6 +37,17 @@ class deformation_field {
         if (!Images_Form_Regular_Grid(sel)) throw std::invalid_argument("Images do not form a rectilinear grid. Cannot continue");
         field.Swap(in);
         rebuild();
+    }
+    deformation_field(std::istream &is) {  // .cc:45-49: defers to read_from(), throws on errors
+        if (!read_from(is)) throw std::invalid_argument("Unable to read deformation field from stream");
+    }
+    bool write_to(std::ostream &os) const { return dcma_b200_io::write_field_text(field, os); }  // .cc:322-357
+    bool read_from(std::istream &is) {                                                           // .cc:359-436
+        planar_image_collection<double, double> f;
+        if (!dcma_b200_io::read_field_text(is, f)) return false;
+        field.Swap(f);
+        rebuild();
+        return true;
     }
     deformation_field(const deformation_field &o) : field(o.field) { rebuild(); }
     deformation_field(deformation_field &&o) : field(std::move(o.field)) { rebuild(); }

@@ -33,6 +33,13 @@ template <class T>
 std::ostream &operator<<(std::ostream &os, const vec3<T> &v) { return os << "(" << v.x << ", " << v.y << ", " << v.z << ")"; }
 
 template <class T>
+std::istream &operator>>(std::istream &is, vec3<T> &v) {  // "(x, y, z)"
+    char c = 0;
+    is >> c >> v.x >> c >> v.y >> c >> v.z >> c;
+    return is;
+}
+
+template <class T>
 class point_set {
   public:
     std::list<vec3<T>> points;

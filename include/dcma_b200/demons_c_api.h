@@ -251,6 +251,25 @@ DCMA_B200_API int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, co
 DCMA_B200_API int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *image, const dcma_b200_grid *dst_grid,
                                              float oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* ---- the numeric payload of a stored deformation field (the `.trans` text format) --------------------------------- */
+/* deformation_field::write_to (src/Alignment_Field.cc:322-357) emits, after each image's header lines, every double of
+ * the image on its own line at precision max_digits10 (`os << val << '\n'`, :346-348); read_from (:359-436) extracts
+ * them again with `is >> val` (:418-420).  For a 512 x 512 x 256 field that is 2.0e8 numbers, ~4.8 GB of text.  These
+ * two calls do that part on the GPU, byte-for-byte and bit-for-bit what the C library produces (correctly rounded in
+ * both directions); the header lines stay with the caller (host/Alignment_Field_IO.cc shows the whole writer/reader).
+ *
+ * dcma_b200_format_doubles: text := printf("%.17g\n") of values[0..n).  `capacity` bytes are available at `text`
+ *   (25 * n always suffices; DCMA_B200_EINVAL if it turns out too small); *text_len := bytes written.  No terminator.
+ * dcma_b200_parse_doubles:  values[0..n) := the first n white-space separated decimal numbers of text[0..text_len), as
+ *   n stream extractions would read them; *consumed := offset just past the last character of the n-th number.
+ *   DCMA_B200_EINVAL (message as the reference's "Pixel data could not be read") when the text holds fewer than n
+ *   numbers, or a token is not a decimal number ("inf"/"nan" included, which the stream extraction rejects too) or
+ *   overflows a double.  All pointers HOST. */
+DCMA_B200_API int dcma_b200_format_doubles(const double *values, int64_t n, char *text, int64_t capacity, int64_t *text_len,
+                                           int device, char *errbuf, size_t errbuf_len);
+DCMA_B200_API int dcma_b200_parse_doubles(const char *text, int64_t text_len, int64_t n, double *values, int64_t *consumed,
+                                          int device, char *errbuf, size_t errbuf_len);
+
 #ifdef __cplusplus
 }
 #endif
