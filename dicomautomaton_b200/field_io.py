@@ -118,3 +118,39 @@ def read_field_text(fileobj, device: int = -1):
                            row_unit=row_unit, col_unit=col_unit, metadata=meta))
     same = all(p.shape == planes[0].shape for p in planes)
     return (np.stack(planes) if same else planes), images
+
+
+_MAGIC = b"DCMA_TRANSFORM"
+_VARIANT = b"TRANSFORM_VARIANT_DEFORMATION_FIELD_3"
+
+
+def write_trans_file(path, deformation: np.ndarray, grid: capi.Grid, metadata: Optional[Dict[str, str]] = None,
+                     device: int = -1) -> None:
+    """A `.trans` file as `ExportWarps` -> `WriteTransform3` writes it for a deformation field (reference
+    src/Transformation_File_Loader.cc:112-149): magic line, variant line, then the field text.  The transform-level
+    `# key = value` comment lines are omitted (their encoding is Ygor's; `ReadTransform3` treats them as optional)."""
+    with open(path, "wb") as f:
+        f.write(_MAGIC + b"\n" + _VARIANT + b"\n")
+        write_field_text(f, deformation, grid, metadata, device)
+
+
+def read_trans_file(path, device: int = -1):
+    """Inverse of `write_trans_file`; follows `ReadTransform3` (src/Transformation_File_Loader.cc:23-100): comment lines
+    and blank lines are skipped, the first other line must be the magic phrase, the second names the variant."""
+    with open(path, "rb") as f:
+        magic = variant = None
+        while variant is None:
+            line = f.readline()
+            if not line:
+                raise ValueError("not a DCMA_TRANSFORM file")
+            if b"#" in line or not line.strip():
+                continue
+            if magic is None:
+                magic = line.strip()
+                if magic != _MAGIC:
+                    raise ValueError("not a DCMA_TRANSFORM file")
+            else:
+                variant = line.strip()
+        if variant != _VARIANT:
+            raise ValueError("transform variant %r is not a deformation field" % variant.decode(errors="replace"))
+        return read_field_text(f, device)

@@ -250,3 +250,46 @@ def test_native_c_and_cpp_callers(tmp_path):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([cc_exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_trans_file_wrapper_and_header_logic_on_cpu(tmp_path, monkeypatch):
+    """Host logic of field_io (headers, metadata, `.trans` wrapper, src/Transformation_File_Loader.cc:23-149) with the two
+    GPU calls replaced by the oracle's conversions: the file equals the oracle's text and reads back."""
+    from dicomautomaton_b200 import demons, field_io
+    from oracle import field_text as ft
+
+    def fake_parse(text, n, device=-1):
+        toks, pos, vals = 0, 0, []
+        while toks < n:
+            while text[pos:pos + 1].isspace():
+                pos += 1
+            b = pos
+            while pos < len(text) and not text[pos:pos + 1].isspace():
+                pos += 1
+            vals.append(float(text[b:pos]))
+            toks += 1
+        return np.array(vals), pos
+
+    monkeypatch.setattr(field_io, "format_doubles", lambda v, device=-1: ft.format_doubles(np.asarray(v).reshape(-1)))
+    monkeypatch.setattr(field_io, "parse_doubles", fake_parse)
+    shape, spacing, origin = (2, 3, 4), (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)
+    D = np.zeros(shape + (3,))
+    for s in range(2):
+        for r in range(3):
+            for c in range(4):
+                D[s, r, c] = (0.1 * c, -0.2 * r, 0.05 * s)   # src/Alignment_Field_Tests.cc:197-200
+    meta = {"PatientID": "test_patient_001", "key with spaces": "value;with@special=chars"}
+    path = tmp_path / "field.trans"
+    field_io.write_trans_file(str(path), D, demons.make_grid(shape, spacing, origin), meta)
+    raw = path.read_bytes()
+    imgs = [dict(rows=3, cols=4, pxl_dx=1.0, pxl_dy=1.0, pxl_dz=1.0, anchor=(0, 0, 0), offset=(0, 0, float(z)), row_unit=(1, 0, 0),
+                 col_unit=(0, 1, 0), metadata=meta, data=D[z].reshape(-1)) for z in range(2)]
+    assert raw == b"DCMA_TRANSFORM\nTRANSFORM_VARIANT_DEFORMATION_FIELD_3\n" + ft.write_field_text(imgs)
+    back, images = field_io.read_trans_file(str(path))
+    assert np.array_equal(back, D) and images[1]["metadata"] == meta and images[1]["offset"] == (0.0, 0.0, 1.0)
+    # comment and blank lines before the magic / variant lines are skipped; anything else is rejected
+    path.write_bytes(b"# a = b\n\n" + raw)
+    assert np.array_equal(field_io.read_trans_file(str(path))[0], D)
+    path.write_bytes(b"SOMETHING_ELSE\n" + raw)
+    with pytest.raises(ValueError):
+        field_io.read_trans_file(str(path))
