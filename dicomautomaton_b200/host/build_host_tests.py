@@ -54,7 +54,59 @@ def build(verbose=True):
     return EXE
 
 
+OP_EXE = os.path.join(OUT, "demons_operation_check")
+
+
+def build_operation(verbose=True):
+    """`host/_build/demons_operation_check`: the reference's OWN operation file, src/Operations/RegisterImagesDemons.cc,
+    compiled in place and unmodified (read through stdin from a scratch directory whose parent holds forwarding headers,
+    so that its `../Structs.h`-style includes resolve to the stand-ins and to our Alignment_Demons.h), linked with the
+    AlignViaDemons drop-in, libdcma_b200.so and the driver tests/native/operation_check.cc."""
+    op_src = os.path.join(REF_SRC, "Operations", "RegisterImagesDemons.cc")
+    if not os.path.isfile(op_src):
+        if verbose:
+            print(f"[host tests] {op_src} not found; {'using prebuilt ' + OP_EXE if os.path.isfile(OP_EXE) else 'nothing to do'}")
+        return OP_EXE if os.path.isfile(OP_EXE) else None
+    ops = os.path.join(OUT, "ops")
+    os.makedirs(ops, exist_ok=True)
+    libdir = os.path.join(os.path.dirname(HERE), "lib")
+    shim = os.path.join(HERE, "shim")
+    inc = ["-I", os.path.join(shim, "dcma_min"), "-I", os.path.join(shim, "ygor_min"), "-I", HERE, "-I", os.path.join(ROOT, "include")]
+    cxx = ["g++", "-std=c++17", "-O2", "-Wno-unused-function", "-Wno-unused-variable"]
+    # forwarding headers: "../X.h" as seen from the scratch directory -> <X.h> on the include path (angle brackets, so that
+    # a forwarder never finds itself)
+    for h in ("Structs.h", "Regex_Selectors.h", "Thread_Pool.h", "Alignment_Rigid.h", "Alignment_Field.h", "Alignment_Demons.h"):
+        with open(os.path.join(OUT, h), "w") as f:
+            f.write(f"#pragma once\n#include <{h}>\n")
+    # the operation's own header declares exactly these two functions (src/Operations/RegisterImagesDemons.h:13-18); the
+    # reference's copy cannot be used because its relative includes would pull in the real Structs.h
+    with open(os.path.join(ops, "RegisterImagesDemons.h"), "w") as f:
+        f.write("#pragma once\n#include <map>\n#include <string>\n#include <Structs.h>\n#include <Regex_Selectors.h>\n"
+                "OperationDoc OpArgDocRegisterImagesDemons();\n"
+                "bool RegisterImagesDemons(Drover &, const OperationArgPkg &, std::map<std::string, std::string> &, const std::string &);\n")
+    objs = []
+    o = os.path.join(OUT, "ref_operation.o")
+    cmd = cxx + inc + ["-x", "c++", "-c", "-", "-o", o]
+    if verbose:
+        print("[host tests]", " ".join(cmd), "<", op_src)
+    with open(op_src, "rb") as f:
+        subprocess.check_call(cmd, stdin=f, cwd=ops)
+    objs.append(o)
+    for src, name in ((os.path.join(ROOT, "tests", "native", "operation_check.cc"), "operation_check.o"),
+                      (os.path.join(HERE, "Alignment_Demons.cc"), "Alignment_Demons.o")):
+        o = os.path.join(OUT, name)
+        subprocess.check_call(cxx + inc + ["-c", src, "-o", o])
+        objs.append(o)
+    cmd = ["g++", "-o", OP_EXE, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    if verbose:
+        print("[host tests]", " ".join(cmd))
+    subprocess.check_call(cmd)
+    return OP_EXE
+
+
 if __name__ == "__main__":
     p = build()
+    q = build_operation()
     print(p if p else "unavailable")
+    print(q if q else "unavailable")
     sys.exit(0 if p else 1)

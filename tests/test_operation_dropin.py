@@ -1,0 +1,67 @@
+"""The drop-in one level up, at the operation: the reference's OWN src/Operations/RegisterImagesDemons.cc is compiled in
+place, unmodified, against our Alignment_Demons.h / AlignViaDemons and stand-ins for Structs.h / Regex_Selectors.h
+(host/build_host_tests.py: build_operation), and driven the way the dispatcher drives it -- arguments as strings,
+defaults from its OperationDoc (tests/native/operation_check.cc).
+
+Checked here: the argument surface (16 arguments, names and defaults) and the error contract without a
+device (AlignViaDemons warns and returns nullopt, the operation throws "Demons registration failed",
+RegisterImagesDemons.cc:337-341).  With a device the same binary runs the registration and checks what the operation
+leaves in the Drover (Transform3 + metadata, KeepDeformedImages) -- that branch has not run on a GPU yet, so it is
+deliberately not part of the `-m gpu` selection this round.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT, has_gpu
+
+sys.path.insert(0, os.path.join(ROOT, "dicomautomaton_b200", "host"))
+
+# SURVEY.md section 8(b), "Argument surface (names, defaults)"; RegisterImagesDemons.cc:84-230
+EXPECTED_ARGS = [("MovingImageSelection", "last"), ("FixedImageSelection", "first"), ("MaxIterations", "100"),
+                 ("ConvergenceThreshold", "0.001"), ("DeformationFieldSmoothingSigma", "1.0"),
+                 ("UpdateFieldSmoothingSigma", "0.5"), ("UseDiffeomorphic", "false"), ("UseHistogramMatching", "false"),
+                 ("HistogramBins", "256"), ("HistogramOutlierFraction", "0.01"), ("NormalizationFactor", "1.0"),
+                 ("MaxUpdateMagnitude", "2.0"), ("Verbosity", "1"), ("TransformName", "demons_registration"),
+                 ("Metadata", ""), ("KeepDeformedImages", "false")]
+
+
+@pytest.fixture(scope="module")
+def exe():
+    import build_host_tests
+    p = build_host_tests.build_operation(verbose=False)
+    if not p:
+        pytest.skip("reference operation source not available and no prebuilt binary")
+    return p
+
+
+def test_operation_argument_surface_is_the_references(exe):
+    r = subprocess.run([exe, "doc"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "operation=RegisterImagesDemons"
+    got = [tuple(l.split("=", 1)) for l in lines[1:]]
+    assert got == EXPECTED_ARGS
+    # the parameter struct behind them has the same defaults (Alignment_Demons.h:20-61 <-> dcma_b200_demons_params_default)
+    from dicomautomaton_b200 import capi
+    p = capi.default_params()
+    d = dict(got)
+    assert p.max_iterations == int(d["MaxIterations"]) and p.convergence_threshold == float(d["ConvergenceThreshold"])
+    assert p.deformation_field_smoothing_sigma == float(d["DeformationFieldSmoothingSigma"])
+    assert p.update_field_smoothing_sigma == float(d["UpdateFieldSmoothingSigma"])
+    assert p.histogram_bins == int(d["HistogramBins"]) and p.histogram_outlier_fraction == float(d["HistogramOutlierFraction"])
+    assert p.normalization_factor == float(d["NormalizationFactor"]) and p.max_update_magnitude == float(d["MaxUpdateMagnitude"])
+    assert not p.use_diffeomorphic and not p.use_histogram_matching
+
+
+def test_operation_fails_like_the_reference_without_a_device_and_registers_with_one(exe):
+    r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    if not has_gpu():
+        # no CPU fallback: nullopt -> std::runtime_error("Demons registration failed") -> the dispatcher returns false
+        assert r.returncode == 3, r.stdout + r.stderr
+        assert "THROW: Demons registration failed" in r.stdout
+        assert "no CUDA device is available" in r.stderr
+    else:
+        assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
