@@ -5,9 +5,9 @@ defaults from its OperationDoc (tests/native/operation_check.cc).
 
 Checked here: the argument surface (16 arguments, names and defaults) and the error contract without a
 device (AlignViaDemons warns and returns nullopt, the operation throws "Demons registration failed",
-RegisterImagesDemons.cc:337-341).  With a device the same binary runs the registration and checks what the operation
-leaves in the Drover (Transform3 + metadata, KeepDeformedImages) -- that branch has not run on a GPU yet, so it is
-deliberately not part of the `-m gpu` selection this round.
+RegisterImagesDemons.cc:337-341).  With a device (`-m gpu`) the same binary runs the registration and checks what the
+operation leaves in the Drover (RegisterImagesDemons.cc:346-381: one Transform3 holding a deformation_field, its
+metadata, the KeepDeformedImages array) and that the warped moving image is close to the fixed one.
 """
 import os
 import subprocess
@@ -56,12 +56,18 @@ def test_operation_argument_surface_is_the_references(exe):
     assert not p.use_diffeomorphic and not p.use_histogram_matching
 
 
-def test_operation_fails_like_the_reference_without_a_device_and_registers_with_one(exe):
+def test_operation_fails_like_the_reference_without_a_device(exe):
+    if has_gpu():
+        pytest.skip("a device is present")
     r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
-    if not has_gpu():
-        # no CPU fallback: nullopt -> std::runtime_error("Demons registration failed") -> the dispatcher returns false
-        assert r.returncode == 3, r.stdout + r.stderr
-        assert "THROW: Demons registration failed" in r.stdout
-        assert "no CUDA device is available" in r.stderr
-    else:
-        assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+    # no CPU fallback: nullopt -> std::runtime_error("Demons registration failed") -> the dispatcher returns false
+    assert r.returncode == 3, r.stdout + r.stderr
+    assert "THROW: Demons registration failed" in r.stdout
+    assert "no CUDA device is available" in r.stderr
+
+
+@pytest.mark.gpu
+def test_operation_registers_through_the_gpu_dropin(exe):
+    """On a B200 (profiles/r1_operation_check.log): MSE before 91.1138 after 0.4843, every check passes."""
+    r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
