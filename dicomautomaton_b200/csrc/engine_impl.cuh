@@ -14,12 +14,17 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <tuple>
 #include <vector>
 
 #include "demons_kernels.cuh"
 #include "engine.h"
 #include "smooth_kernels.cuh"
+#include "smooth_tma.cuh"
 
+#ifndef DCMA_SMOOTH_TMA
+#define DCMA_SMOOTH_TMA 1  // fp64 fields: k_smooth3d_tma (TMA-staged, wide x-pass tasks) whenever its layout rules hold
+#endif
 #ifndef DCMA_FUSED_REDUCE
 #define DCMA_FUSED_REDUCE 1  // 1: the force kernel's last block reduces the MSE partials; 0: k_reduce_final as its own launch
 #endif
@@ -206,6 +211,10 @@ class Engine final : public EngineBase {
         launches_ = 0;
         prof_.clear();
         profiling_ = false;
+        rot_hist_.clear();
+        if (ev_run0_) cudaEventDestroy(ev_run0_);
+        if (ev_run1_) cudaEventDestroy(ev_run1_);
+        ev_run0_ = ev_run1_ = nullptr;
         DCMA_CUDA(cudaEventCreate(&ev_run0_));
         DCMA_CUDA(cudaEventCreate(&ev_run1_));
         DCMA_CUDA(cudaEventRecord(ev_run0_, stream_));
@@ -228,6 +237,17 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaMemcpyAsync(h_ctrl_, d_ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
         DCMA_CUDA(cudaStreamSynchronize(stream_));
         const int64_t done = h_ctrl_->iters_done;
+        // Iterations enqueued after the stop rule fired are skipped ON THE DEVICE (every kernel returns early), but the
+        // host still rotated the field pointers for them: put the roles back to where they stood at the end of the
+        // converging iteration, so that D is the field the reference returns (cc:987-997).
+        if (h_ctrl_->converged_at != kNotConverged && h_ctrl_->converged_at >= 0 &&
+            static_cast<size_t>(h_ctrl_->converged_at) < rot_hist_.size()) {
+            const Rotation &r = rot_hist_[static_cast<size_t>(h_ctrl_->converged_at)];
+            dD_ = r.d;
+            dU_ = r.u;
+            dTmp_ = r.tmp;
+        }
+        rot_hist_.clear();
         if (mse_history_host && done > 0)
             DCMA_CUDA(cudaMemcpy(mse_history_host, d_hist_, sizeof(double) * done, cudaMemcpyDeviceToHost));
         if (p_.verbosity >= 1 && (!is_slab() || g_.zoff + g_.zb == 0)) {
@@ -284,6 +304,7 @@ class Engine final : public EngineBase {
             case IterStage::SmoothD:
                 if (plan_d_.active) smooth(dD_, plan_d_, it);
                 w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
+                record_rotation(it);
                 break;
         }
     }
@@ -643,6 +664,17 @@ class Engine final : public EngineBase {
             prof_end();
         }
         w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
+        record_rotation(it);
+    }
+
+    // which allocation plays D / U / scratch after loop iteration `it` (the smoothing calls swap pointers)
+    struct Rotation {
+        T *d, *u, *tmp;
+    };
+    void record_rotation(long long it) {
+        if (it < 0) return;
+        if (rot_hist_.size() <= static_cast<size_t>(it)) rot_hist_.resize(static_cast<size_t>(it) + 1, Rotation{dD_, dU_, dTmp_});
+        rot_hist_[static_cast<size_t>(it)] = Rotation{dD_, dU_, dTmp_};
     }
 
     void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true,
@@ -794,6 +826,100 @@ class Engine final : public EngineBase {
         ++launches_;
     }
 
+
+    // ---- k_smooth3d_tma (fp64 fields): TMA descriptor per (field allocation, box shape) and the launch ---------------
+    using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode_tiled_fn() {
+        static EncodeTiledFn fn = []() -> EncodeTiledFn {
+            void *p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess)
+                return nullptr;
+            return reinterpret_cast<EncodeTiledFn>(p);
+        }();
+        return fn;
+    }
+    // the field as a 4-D tensor {x, y, z, component}; one box = one staged slice tile (+halo), out-of-grid -> zeros
+    const CUtensorMap *tensor_map(const T *base, int box_x, int box_y) {
+        const auto key = std::make_tuple(static_cast<const void *>(base), box_x, box_y);
+        auto itm = tmaps_.find(key);
+        if (itm != tmaps_.end()) return &itm->second;
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return nullptr;
+        CUtensorMap m;
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(g_.C), static_cast<cuuint64_t>(g_.R), static_cast<cuuint64_t>(g_.S), 3};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g_.C) * sizeof(T),
+                                       static_cast<cuuint64_t>(g_.R) * g_.C * sizeof(T),
+                                       static_cast<cuuint64_t>(g_.N) * sizeof(T)};
+        const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_x), static_cast<cuuint32_t>(box_y), 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<T *>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nullptr;
+        return &tmaps_.emplace(key, m).first->second;
+    }
+    bool tma_usable(const T *in) const {
+        return DCMA_SMOOTH_TMA != 0 && sizeof(T) == 8 && (g_.C % 2) == 0 && (reinterpret_cast<uintptr_t>(in) % 16) == 0 &&
+               (g_.N % 2) == 0 && g_.C >= 2;
+    }
+    template <int R>
+    bool launch_smooth3d_tma(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+        if constexpr (sizeof(T) != 8 || R > 4) {
+            return false;
+        } else {
+            constexpr int TX = 32, TY = DCMA_TMA_TY, OY = DCMA_TMA_OY, NS = DCMA_TMA_NS, NXB = DCMA_TMA_NXB;
+            using Cfg = SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>;
+            if (!tma_usable(in)) return false;
+            const CUtensorMap *tm = tensor_map(in, Cfg::PWP, Cfg::PH);
+            if (!tm) return false;
+            auto kern = k_smooth3d_tma<T, STRICT, R, TX, TY, OY, NS, NXB>;
+            static thread_local bool attr_set[64] = {false};
+            if (!attr_set[dev_ & 63]) {
+                DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::smem_bytes)));
+                DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                attr_set[dev_ & 63] = true;
+            }
+            const int gx = (g_.C + TX - 1) / TX, gy = (g_.R + TY - 1) / TY;
+            int blocks_per_sm = 1;
+            DCMA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, Cfg::NTHREADS, Cfg::smem_bytes));
+            int zchunk = 0, nz = 0;
+            choose_zchunks(gx, gy, R, blocks_per_sm, zchunk, nz);
+            if (3LL * nz > 65535 || gy > 65535) return false;
+            kern<<<dim3(gx, gy, 3 * nz), Cfg::NTHREADS, Cfg::smem_bytes, stream_>>>(*tm, in, out, g_, pl.W, pl.tab[0], pl.tab[1],
+                                                                                    pl.tab[2] + g_.zoff, pl.dw[0], pl.dw[1],
+                                                                                    pl.dw[2], zchunk, nz, d_ctrl_, it);
+            DCMA_CUDA(cudaGetLastError());
+            ++launches_;
+            return true;
+        }
+    }
+    // z chunks: score = (fraction of slice steps that produce output) x (wave efficiency); every chunk re-stages
+    // 2R slices of warm-up, and a partially filled last wave idles SMs.
+    void choose_zchunks(int gx, int gy, int R, int blocks_per_sm, int &zchunk, int &nz) const {
+        const double slots = static_cast<double>(std::max(1, blocks_per_sm)) * sms_;
+        const long long nxy = static_cast<long long>(gx) * gy * 3;
+        int best_nz = 1;
+        double best_score = -1.0;
+        const int So = g_.ze - g_.zb;  // owned slices
+        const int nz_max = std::max(1, std::min(So / std::max(2 * R, 1), static_cast<int>(65535 / 3)));
+        for (int nzc = 1; nzc <= nz_max; ++nzc) {
+            const int zc = (So + nzc - 1) / nzc;
+            const int nz_eff = (So + zc - 1) / zc;
+            const double waves = static_cast<double>(nxy) * nz_eff / slots;
+            const double score = (static_cast<double>(zc) / (zc + 2 * R)) * (waves / std::ceil(waves));
+            if (score > best_score + 1e-9) {
+                best_score = score;
+                best_nz = nz_eff;
+            }
+        }
+        zchunk = (So + best_nz - 1) / best_nz;
+        nz = (So + zchunk - 1) / zchunk;
+    }
+
     template <int R>
     void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
         // NT = 128 threads per role, 2 adjacent output rows x one 16-byte vector per thread; the register z window
@@ -803,6 +929,7 @@ class Engine final : public EngineBase {
         constexpr int TY = DCMA_SMOOTH_TY;
         constexpr int NT = DCMA_SMOOTH_NT;
         constexpr int MINB = DCMA_SMOOTH_MINB;
+        if (launch_smooth3d_tma<R>(in, out, pl, it)) return;
         const bool vec = (g_.C % static_cast<int>(16 / sizeof(T)) == 0);
         if (vec)
             launch_smooth3d_cfg<R, TX, TY, NT, MINB, true>(in, out, pl, it);
@@ -852,12 +979,14 @@ class Engine final : public EngineBase {
     cudaStream_t copy_stream_ = nullptr;
     SmoothPlan<T> plan_u_, plan_d_;
     std::map<double, SmoothPlan<T>> extra_plans_;
+    std::map<std::tuple<const void *, int, int>, CUtensorMap> tmaps_;
     int w_src_ = 0;
     std::vector<void *> allocs_;
     int64_t bytes_ = 0;
     int64_t launches_ = 0, prof_launch_mark_ = 0;
     bool profiling_ = false;
     std::vector<ProfRec> prof_;
+    std::vector<Rotation> rot_hist_;
 };
 
 }  // namespace DCMA_NS

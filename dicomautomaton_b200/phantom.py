@@ -95,3 +95,93 @@ def make_dose_grid(shape, device="cpu", chunk: int = 16):
             + ((zs - 0.5 * nz) / (0.2 * nz)) ** 2
         out[a:b] = (70.0 * torch.exp(-0.5 * r2)).to(torch.float32)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Bit-reproducible variant.  `make_pair` calls sin/exp/sigmoid, whose last bit differs between libm, SLEEF and CUDA, so a
+# pair made on one machine cannot be hashed against one made on another.  `make_pair_exact` builds the same kind of
+# phantom (air, sigmoid-edged ellipsoid, two blobs, a rod, texture everywhere, the same family of sinusoidal warp) from
+# IEEE-exact float64 operations only -- + - * / sqrt floor, one torch kernel per operation, so nothing is contracted into
+# an FMA -- and is therefore bit-identical on any CPU and on the GPU.  Used by the full-size parity fixtures
+# (tests/golden/make_full_size_fixtures.py): the committed sha256 of the reference's result is only meaningful if the
+# GPU box regenerates exactly the same inputs.
+# ----------------------------------------------------------------------------------------------------------------------
+_TWO_PI = 6.283185307179586
+_INV_TWO_PI = 0.15915494309189535
+
+
+def _sin_exact(t):
+    """A sine made of exact operations: reduce to [-pi, pi), then an odd degree-11 polynomial (|error| < 5e-4 at the
+    interval ends, far below what the phantom needs; smooth and periodic is all that matters)."""
+    k = torch.floor(t * _INV_TWO_PI + 0.5)
+    r = t - k * _TWO_PI
+    r2 = r * r
+    p = r2 * (-2.505210838544172e-08) + 2.755731922398589e-06
+    p = p * r2 + (-1.984126984126984e-04)
+    p = p * r2 + 8.333333333333333e-03
+    p = p * r2 + (-1.666666666666667e-01)
+    p = p * r2 + 1.0
+    return r * p
+
+
+def _cos_exact(t):
+    return _sin_exact(t + 1.5707963267948966)
+
+
+def _bump_exact(q):
+    """Stand-in for exp(-q/2): (1 + q/8)^-4, same value/slope at 0, positive, smooth, algebraic tail."""
+    b = 1.0 / (q * 0.125 + 1.0)
+    b = b * b
+    return b * b
+
+
+def _phantom_hu_exact(x, y, z, shape):
+    nz, ny, nx = (float(v) for v in shape)
+    cx, cy, cz = (nx - 1.0) / 2.0, (ny - 1.0) / 2.0, (nz - 1.0) / 2.0
+    small = min(nx, ny, nz)
+    ex, ey, ez = (x - cx) / (0.40 * nx), (y - cy) / (0.32 * ny), (z - cz) / (0.45 * nz)
+    e = torch.sqrt(ex * ex + ey * ey + ez * ez)
+    u = (1.0 - e) / 0.06
+    body = (u / torch.sqrt(u * u + 1.0)) * 0.5 + 0.5  # algebraic sigmoid
+    hu = body * 1000.0 - 1000.0
+
+    def blob(amp, fx, fy, fz, s):
+        bx, by, bz = cx + fx * nx, cy + fy * ny, cz + fz * nz
+        dx, dy, dz = x - bx, y - by, z - bz
+        return _bump_exact((dx * dx + dy * dy + dz * dz) / ((s * small) ** 2)) * amp
+
+    hu = hu + body * blob(300.0, 0.15, -0.05, 0.10, 0.08)
+    hu = hu + body * blob(-700.0, -0.15, 0.08, -0.12, 0.07)
+    rx, ry = x - cx, y - (cy + 0.18 * ny)
+    hu = hu + body * (_bump_exact((rx * rx + ry * ry) / ((0.03 * small) ** 2)) * 900.0)
+    tex = _sin_exact(x * 0.9 + y * 0.3) + _sin_exact(y * 0.7 + z * 0.4) + _sin_exact(z * 0.8 + x * 0.5)
+    return hu + tex * 20.0
+
+
+def known_warp_mm_exact(x, y, z, shape, amplitude_mm: float = 2.0):
+    nz, ny, nx = (float(v) for v in shape)
+    lx, ly, lz = nx / 2.0, ny / 3.0, max(nz / 1.5, 1.0)
+    sx, sy = _sin_exact(x * (_TWO_PI / lx)), _sin_exact(y * (_TWO_PI / ly))
+    czs = _cos_exact(z * (_TWO_PI / lz))
+    return (sy * czs) * amplitude_mm, (sx * czs) * amplitude_mm, (sx * sy) * amplitude_mm
+
+
+def make_pair_exact(shape, spacing=(1.0, 1.0, 1.0), amplitude_mm: float = 2.0, device="cpu", chunk: int = 16):
+    """Bit-reproducible (fixed, moving) float32 pair: identical bytes on every CPU and on the GPU (see above)."""
+    nz, ny, nx = (int(v) for v in shape)
+    dev = torch.device(device)
+    fixed = torch.empty((nz, ny, nx), dtype=torch.float32, device=dev)
+    moving = torch.empty_like(fixed)
+    ys = torch.arange(ny, dtype=torch.float64, device=dev).view(1, ny, 1)
+    xs = torch.arange(nx, dtype=torch.float64, device=dev).view(1, 1, nx)
+    for a in range(0, nz, chunk):
+        b = min(a + chunk, nz)
+        zs = torch.arange(a, b, dtype=torch.float64, device=dev).view(b - a, 1, 1)
+        x, y, z = (t.contiguous() for t in torch.broadcast_tensors(xs, ys, zs))
+        fixed[a:b] = _phantom_hu_exact(x, y, z, shape).to(torch.float32)
+        wx, wy, wz = known_warp_mm_exact(x, y, z, shape, amplitude_mm)
+        if nz == 1:
+            wz = wz * 0.0
+        moving[a:b] = _phantom_hu_exact(x + wx / spacing[0], y + wy / spacing[1], z + wz / spacing[2],
+                                        shape).to(torch.float32)
+    return fixed, moving

@@ -23,3 +23,9 @@ def random_smooth_field(shape, max_mm=3.0, seed=0):
         out[..., comp] = acc
     out *= max_mm / max(np.abs(out).max(), 1e-12)
     return out
+
+
+def ref_kind(oracle_mod):
+    """The compiled reference engine (oracle/_ref, built from /root/reference by oracle/build_ref.py and shipped to the
+    GPU box as a .so) whenever it is present, else the C restatement that tests/test_oracle.py pins to it bit for bit."""
+    return "reference" if oracle_mod.available("reference") else "port"

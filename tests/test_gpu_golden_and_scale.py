@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+from _helpers import ref_kind
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
@@ -115,7 +117,7 @@ def test_full_size_first_iterations_bit_exact_vs_oracle(oracle_mod):
     iters = 2
     op = oracle_mod.make_params(max_iterations=iters, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
                                 update_field_smoothing_sigma=1.5, use_diffeomorphic=True)
-    Do, ho, no = oracle_mod.demons_run(F, M, op, kind="port")
+    Do, ho, no = oracle_mod.demons_run(F, M, op, kind=ref_kind(oracle_mod))
     for mode in ("fp64_strict", "fp64"):
         eng = _engine(mode, iters)
         try:
@@ -144,7 +146,7 @@ def test_config2_parameters_full_200_iterations_at_256x256x128(oracle_mod):
     F, M = phantom_pair(shape)
     kw = dict(max_iterations=200, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
               update_field_smoothing_sigma=1.5, use_diffeomorphic=True)
-    Do, ho, no = oracle_mod.demons_run(F, M, oracle_mod.make_params(**kw), kind="port")
+    Do, ho, no = oracle_mod.demons_run(F, M, oracle_mod.make_params(**kw), kind=ref_kind(oracle_mod))
     report = {}
     for mode in ("fp64_strict", "fp64", "fp32"):
         out, hist, st = AlignViaDemons(AlignViaDemonsParams(verbosity=0, field_mode=mode, **kw), demons_volume(M),

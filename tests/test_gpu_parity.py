@@ -9,7 +9,7 @@ MSE values: the GPU reduces in a tree, the reference serially => 1e-12 relative 
 import numpy as np
 import pytest
 
-from _helpers import phantom_pair, random_smooth_field
+from _helpers import phantom_pair, random_smooth_field, ref_kind
 
 pytestmark = pytest.mark.gpu
 
@@ -17,6 +17,8 @@ TOL_MM = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 1e-4}
 TOL_MSE = {"fp64_strict": 1e-12, "fp64": 1e-12, "fp32": 1e-4}
 # warped intensities (HU): fp32 fields move the sample point by ~1e-7 voxel
 TOL_HU = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 2e-3}
+
+
 
 CASES = [
     # (shape (slices, rows, cols), spacing (dx, dy, dz), sigma)
@@ -57,7 +59,7 @@ def test_stage_level_parity(oracle_mod, mode, fused, case):
     shape, sp, sigma = case
     F, M = phantom_pair(shape, sp)
     op, gp = _params(oracle_mod, mode, 1, sigma, True, fused)
-    O = oracle_mod.OracleEngine(F, M, op, sp, kind="port")
+    O = oracle_mod.OracleEngine(F, M, op, sp, kind=ref_kind(oracle_mod))
     G = DemonsEngine(demons_volume(F, *sp), demons_volume(M, *sp), gp)
     try:
         _check("gradient", G.get("gradient"), O.get("gradient"), mode, tol=0.0)  # fp64 from float inputs: always exact
@@ -111,7 +113,7 @@ def test_loop_parity(oracle_mod, mode, diffeo, case):
     iters = 12
     F, M = phantom_pair(shape, sp)
     op, gp = _params(oracle_mod, mode, iters, sigma, diffeo)
-    Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind="port")
+    Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind=ref_kind(oracle_mod))
     out, hg, st = AlignViaDemons(gp, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
     assert out is not None
     assert st.iterations_done == no == iters
@@ -133,26 +135,39 @@ def test_unfused_equals_fused(oracle_mod, mode):
     _check("fused vs unfused", outs[0], outs[1], mode, tol=0.0 if mode == "fp64_strict" else 1e-12)
 
 
+@pytest.mark.parametrize("diffeo", [False, True], ids=["standard", "diffeomorphic"])
 @pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
-def test_convergence_rule_matches_reference(oracle_mod, mode):
-    """The stop rule (cc:987-993) runs on the device: same number of iterations, same field as the oracle."""
+def test_convergence_rule_matches_reference(oracle_mod, mode, diffeo):
+    """The stop rule (cc:987-993) runs on the device: same number of iterations, same field as the oracle.
+
+    The host enqueues iterations ahead of the device-side stop rule and polls every `check_every` iterations, so
+    1..check_every-1 iterations can be enqueued AFTER the converging one and are skipped on the device.  Each skipped
+    iteration still rotates the field pointers on the host (one swap per smoothing call: period 2 for standard Demons,
+    period 3 for diffeomorphic with both sigmas), so the cadences below are chosen to give skipped counts that are odd
+    and not multiples of 3 -- the returned field must be the one of the converging iteration (cc:987-997)."""
     from dicomautomaton_b200.demons import AlignViaDemons, demons_volume
     shape, sp = (10, 32, 36), (1.0, 1.0, 1.0)
     F, M = phantom_pair(shape, sp, amplitude_mm=1.0)
     # pick a threshold that stops the oracle somewhere in the middle of the run
-    op, _ = _params(oracle_mod, mode, 60, 1.0, False)
-    _, h, _ = oracle_mod.demons_run(F, M, op, sp, kind="port")
+    op, _ = _params(oracle_mod, mode, 60, 1.0, diffeo)
+    _, h, _ = oracle_mod.demons_run(F, M, op, sp, kind=ref_kind(oracle_mod))
     changes = np.abs(np.diff(h))
     k = 20
     thr = float(0.5 * (changes[k - 1] + changes[k]))  # |mse[k]-mse[k+1]| < thr first happens near iteration k+1
-    op, gp = _params(oracle_mod, mode, 60, 1.0, False, threshold=thr)
-    Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind="port")
+    op, gp = _params(oracle_mod, mode, 60, 1.0, diffeo, threshold=thr)
+    Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind=ref_kind(oracle_mod))
     assert 1 < no < 60
-    for check_every in (1, 4, 7):
+    skipped_seen = set()
+    for check_every in (1, 2, 3, 4, 5, 6, 7, 11):
         gp.check_every = check_every
+        # iterations enqueued when the first poll at or after the converging one happens (or the loop ends)
+        enq = min(60, -(-no // check_every) * check_every)
+        skipped_seen.add(enq - no)
         out, hg, st = AlignViaDemons(gp, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
-        assert st.iterations_done == no
-        _check("deformation", out.data, Do, mode)
+        assert st.iterations_done == no, f"check_every={check_every}"
+        _check(f"deformation (check_every={check_every}, {enq - no} skipped)", out.data, Do, mode)
+    # the point of this test: an odd skipped count and one that is not a multiple of 3 have both been exercised
+    assert any(s % 2 == 1 for s in skipped_seen) and any(s % 3 != 0 for s in skipped_seen), skipped_seen
 
 
 @pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
@@ -170,7 +185,7 @@ def test_non_finite_inputs(oracle_mod, mode):
     F[1, 1, 1] = -np.inf
     for diffeo in (False, True):
         op, gp = _params(oracle_mod, mode, 8, 1.5, diffeo)
-        Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind="port")
+        Do, ho, no = oracle_mod.demons_run(F, M, op, sp, kind=ref_kind(oracle_mod))
         out, hg, st = AlignViaDemons(gp, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
         assert st.iterations_done == no
         _check("deformation", out.data, Do, mode)
@@ -189,7 +204,7 @@ def test_non_finite_field_values_take_the_literal_smoothing_path(oracle_mod, mod
     U[0, 0, 0, 1] = np.inf
     U[11, 39, 71, 2] = -np.inf
     U[6, 20:31, 30:41, 1] = np.nan  # a block larger than the kernel support in x and y
-    O = oracle_mod.OracleEngine(F, M, op, sp, kind="port")
+    O = oracle_mod.OracleEngine(F, M, op, sp, kind=ref_kind(oracle_mod))
     G = DemonsEngine(demons_volume(F, *sp), demons_volume(M, *sp), gp)
     try:
         O.set("update", U)
@@ -212,7 +227,7 @@ def test_multichannel_images(oracle_mod, mode):
     F = np.stack([F1, F2], axis=-1)
     M = np.stack([M1, M2], axis=-1)
     op, gp = _params(oracle_mod, mode, 1, 1.0, False)
-    O = oracle_mod.OracleEngine(F, M, op, sp, kind="port")
+    O = oracle_mod.OracleEngine(F, M, op, sp, kind=ref_kind(oracle_mod))
     G = DemonsEngine(demons_volume(F, *sp), demons_volume(M, *sp), gp)
     try:
         for _ in range(3):
@@ -232,7 +247,7 @@ def test_warp_image_entry_point(oracle_mod):
     shape, sp = (7, 18, 22), (1.0, 1.5, 2.0)
     F, M = phantom_pair(shape, sp)
     D = random_smooth_field(shape, 2.5, seed=5)
-    O = oracle_mod.OracleEngine(F, M, oracle_mod.make_params(max_iterations=1), sp, kind="port")
+    O = oracle_mod.OracleEngine(F, M, oracle_mod.make_params(max_iterations=1), sp, kind=ref_kind(oracle_mod))
     try:
         O.set("deformation", D)
         O.warp_moving()
