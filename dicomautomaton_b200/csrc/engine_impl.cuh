@@ -871,7 +871,7 @@ class Engine final : public EngineBase {
         if constexpr (sizeof(T) != 8 || R > 4) {
             return false;
         } else {
-            constexpr int TX = 32, TY = DCMA_TMA_TY, OY = DCMA_TMA_OY, NS = DCMA_TMA_NS, NXB = DCMA_TMA_NXB;
+            constexpr int TX = DCMA_TMA_TX, TY = DCMA_TMA_TY, OY = DCMA_TMA_OY, NS = DCMA_TMA_NS, NXB = DCMA_TMA_NXB;
             using Cfg = SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>;
             if (!tma_usable(in)) return false;
             const CUtensorMap *tm = tensor_map(in, Cfg::PWP, Cfg::PH);

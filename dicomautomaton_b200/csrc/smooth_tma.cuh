@@ -28,11 +28,14 @@
 
 #include "smooth_kernels.cuh"
 
+#ifndef DCMA_TMA_TX
+#define DCMA_TMA_TX 64  // tile columns: TX/8 producer warps (whole warpgroups: 32 or 64)
+#endif
 #ifndef DCMA_TMA_TY
 #define DCMA_TMA_TY 24  // tile rows; TY + 2R = 32 staged rows for R = 4: one x-pass task row per lane
 #endif
 #ifndef DCMA_TMA_OY
-#define DCMA_TMA_OY 3   // rows per consumer thread: TY/OY consumer warps
+#define DCMA_TMA_OY 4   // rows per consumer thread: (TX/32) * (TY/OY) consumer warps
 #endif
 #ifndef DCMA_TMA_NS
 #define DCMA_TMA_NS 3   // TMA stages (slices in flight)
@@ -41,13 +44,16 @@
 #define DCMA_TMA_NXB 2  // x-pass output tiles (producer -> consumer hand-off)
 #endif
 #ifndef DCMA_TMA_PREG
-#define DCMA_TMA_PREG 56
+#define DCMA_TMA_PREG 48  // registers per producer thread after setmaxnreg.dec
 #endif
 #ifndef DCMA_TMA_CREG
-#define DCMA_TMA_CREG 96
+#define DCMA_TMA_CREG 128  // registers per consumer thread after setmaxnreg.inc; see the pool static_assert below
 #endif
 #ifndef DCMA_TMA_MINB
-#define DCMA_TMA_MINB 2
+#define DCMA_TMA_MINB (DCMA_TMA_TX == 32 ? 2 : 1)  // CTAs per SM
+#endif
+#ifndef DCMA_TMA_IDLE_WARPS
+#define DCMA_TMA_IDLE_WARPS 0  // warps that only shrink to 24 registers and exit (pads the CTA to whole warpgroups)
 #endif
 
 namespace DCMA_NS {
@@ -64,18 +70,23 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+// Spin on the phase parity.  A protocol error would otherwise hang the GPU until the driver's watchdog fires, so the spin
+// is bounded (~seconds) and traps: the launch then fails with an error instead of wedging the device.
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "DCMA_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DCMA_MBAR_DONE;\n"
-        "bra DCMA_MBAR_WAIT;\n"
-        "DCMA_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
+    const unsigned addr = smem_addr(bar);
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
 }
 // one box {c0 = x, c1 = y, c2 = z, c3 = component} of the 4-D tensor map -> shared memory, completion on `bar`
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
@@ -117,8 +128,10 @@ struct SmoothTmaCfg {
     static constexpr int SXP = TX + 2;                   // x-pass tile row pitch, same rule
     static constexpr int TAPS = 2 * R + 1;
     static constexpr int NPW = NSEG;                     // producer warps
-    static constexpr int NCW = TY / OY;                  // consumer warps
-    static constexpr int NTHREADS = 32 * (NPW + NCW);
+    static constexpr int NCX = TX / 32;                  // consumer warps side by side (32 columns each)
+    static constexpr int NCW = NCX * (TY / OY);          // consumer warps
+    static constexpr int NIW = DCMA_TMA_IDLE_WARPS;      // idle warps (behind the consumers)
+    static constexpr int NTHREADS = 32 * (NPW + NCW + NIW);
     static constexpr unsigned stage_bytes = PH * PWP * sizeof(T);                    // what one TMA box delivers
     static constexpr unsigned stage_stride = (stage_bytes + 127u) & ~127u;           // TMA destinations: 128-byte aligned
     static constexpr unsigned sx_stride = (PH * SXP * unsigned(sizeof(T)) + 127u) & ~127u;
@@ -126,11 +139,18 @@ struct SmoothTmaCfg {
     static constexpr unsigned off_nx = off_sx + NXB * sx_stride;
     static constexpr unsigned off_bar = off_nx + TX * unsigned(sizeof(T));
     static constexpr size_t smem_bytes = off_bar + (2 * NS + 2 * NXB) * sizeof(unsigned long long);
-    static_assert(TX == 32, "consumer lanes run along the 32 columns of the tile");
-    static_assert(NPW == 4, "the producers are exactly one warpgroup (setmaxnreg)");
-    static_assert(TY % OY == 0 && PH <= 32 && (NPW + NCW) % 4 == 0, "tile/thread shape");
+    static_assert(TX % 32 == 0, "consumer lanes run along 32 columns of the tile");
+    // setmaxnreg.sync.aligned is a WARPGROUP collective: every warpgroup (4 consecutive warps) must be complete and
+    // execute the same instruction -- a partial group, or one split between roles, hangs (measured on B200)
+    static_assert(NPW % 4 == 0 && (NCW + NIW) % 4 == 0 && (NIW == 0 || DCMA_TMA_CREG == 24), "roles must be whole warpgroups");
+    static_assert(TY % OY == 0 && PH <= 32, "tile/thread shape");
     static_assert(((PWP / 2) & 1) == 1 && ((SXP / 2) & 1) == 1, "row pitches must be odd multiples of 16 bytes");
     static_assert(PWP <= 256 && PH <= 256, "TMA box limits");
+    // setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x registers at launch, 8-register
+    // granules); setmaxnreg.inc blocks until the pool can serve it, so an over-subscribed split hangs the kernel.
+    static constexpr int launch_regs = (65536 / (NTHREADS * DCMA_TMA_MINB)) / 8 * 8;
+    static_assert(32 * (NPW * DCMA_TMA_PREG + NCW * DCMA_TMA_CREG + NIW * 24) <= NTHREADS * launch_regs,
+                  "register split exceeds the CTA's launch allocation: setmaxnreg.inc would never return");
 };
 
 // grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks (as k_smooth3d).
@@ -192,6 +212,7 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
 #define DCMA_WY(k) W.w[1][k]
 #define DCMA_WZ(k) W.w[2][k]
 
+    static_assert(DCMA_TMA_IDLE_WARPS == 0, "idle warps cannot share a warpgroup with consumers (setmaxnreg is warpgroup-wide)");
     if (warp < NPW) {
         // =============================================== producers =======================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCMA_TMA_PREG));
@@ -257,11 +278,16 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
         return;
     }
 
+    if (Cfg::NIW > 0 && warp >= NPW + NCW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        return;
+    }
     // ================================================= consumers =========================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCMA_TMA_CREG));
     const int cw = warp - NPW;
-    const int yl0 = cw * OY;        // first owned (local) output row; owned rows are adjacent
-    const int gx = x0 + lane;       // owned column
+    const int xh = cw % Cfg::NCX;          // which 32-column part of the tile
+    const int yl0 = (cw / Cfg::NCX) * OY;  // first owned (local) output row; owned rows are adjacent
+    const int gx = x0 + xh * 32 + lane;    // owned column
     // per-position normalisers (STRICT: weight sums to divide by; otherwise reciprocals, applied once at the end)
     T ny[OY];
 #pragma unroll
@@ -279,6 +305,9 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
     T nz_next = tab_z[z_begin < z_end ? z_begin : 0];
     const bool col_ok = (gx < g.C);
     bool bad = false;  // some output of this thread came out non-finite
+    // running output pointer: row yl0 of the tile, column gx, slice of the next output
+    T *outp = dst + static_cast<long long>(z_begin) * plane + static_cast<long long>(y0 + yl0) * g.C + gx;
+    const int rows_ok = col_ok ? max(0, min(OY, g.R - (y0 + yl0))) : 0;  // owned rows inside the grid
 
     auto step = [&](auto ph, const int zp) {
         constexpr int P = decltype(ph)::value;
@@ -288,7 +317,7 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
             const int b = i % NXB;
             mbar_wait(full_x + b, (i / NXB) & 1);
             const T *sx = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(s_x) + b * Cfg::sx_stride) +
-                          yl0 * SXP + lane;
+                          yl0 * SXP + xh * 32 + lane;
             // y pass: rows streamed once; output j takes row m as its tap k = m - j (ascending k: the reference's order)
 #pragma unroll
             for (int m = 0; m < OY + 2 * R; ++m) {
@@ -326,14 +355,14 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
                 o = zs / nz;
             else
                 o = zs * (ny[j] * nz);
-            const int gy = y0 + yl0 + j;
-            if (gy < g.R && col_ok) {
+            if (j < rows_ok) {
                 // x*0 is 0 for finite x and NaN otherwise.  A non-finite result <=> a non-finite tap somewhere in the
                 // (2r+1)^3 support: such outputs are redone literally after the march (smooth_fix_column)
                 bad |= !(o * T(0) == T(0));
-                dst[zo * plane + static_cast<long long>(gy) * g.C + gx] = o;
+                outp[static_cast<long long>(j) * g.C] = o;
             }
         }
+        outp += plane;
     };
     for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
     if (bad) smooth_fix_column<T>(src, dst, g, dwx, dwy, dwz, W.r[0], W.r[1], W.r[2], gx, y0 + yl0, OY, z_begin, z_end);
