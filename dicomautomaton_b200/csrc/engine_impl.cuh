@@ -886,12 +886,24 @@ class Engine final : public EngineBase {
             const int gx = (g_.C + TX - 1) / TX, gy = (g_.R + TY - 1) / TY;
             int blocks_per_sm = 1;
             DCMA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, Cfg::NTHREADS, Cfg::smem_bytes));
-            int zchunk = 0, nz = 0;
-            choose_zchunks(gx, gy, R, blocks_per_sm, zchunk, nz);
-            if (3LL * nz > 65535 || gy > 65535) return false;
-            kern<<<dim3(gx, gy, 3 * nz), Cfg::NTHREADS, Cfg::smem_bytes, stream_>>>(*tm, in, out, g_, pl.W, pl.tab[0], pl.tab[1],
-                                                                                    pl.tab[2] + g_.zoff, pl.dw[0], pl.dw[1],
-                                                                                    pl.dw[2], zchunk, nz, d_ctrl_, it);
+            // persistent launch, statically balanced (see SmoothWork): every CTA gets the same number of slice steps
+            const long long ncols = 3LL * gx * gy;
+            if (ncols > 0x7fffffffLL) return false;
+            const int So = g_.ze - g_.zb;
+            const int G = static_cast<int>(std::min<long long>(ncols, static_cast<long long>(std::max(1, blocks_per_sm)) * sms_));
+            SmoothWork work;
+            work.ncols = static_cast<int>(ncols);
+            work.tiles_x = gx;
+            work.tiles_y = gy;
+            work.nfull = static_cast<int>(ncols / G);
+            const long long rem = (ncols - static_cast<long long>(work.nfull) * G) * So;
+            work.per = static_cast<int>((rem + G - 1) / G);
+            // pieces shorter than the warm-up are not worth a CTA of their own: fall back to whole columns
+            if (work.per > 0 && work.per < 2 * R) {
+                work.per = So;
+            }
+            kern<<<G, Cfg::NTHREADS, Cfg::smem_bytes, stream_>>>(*tm, in, out, g_, pl.W, pl.tab[0], pl.tab[1], pl.tab[2] + g_.zoff,
+                                                                 pl.dw[0], pl.dw[1], pl.dw[2], work, d_ctrl_, it);
             DCMA_CUDA(cudaGetLastError());
             ++launches_;
             return true;

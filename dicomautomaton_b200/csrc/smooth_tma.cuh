@@ -153,13 +153,54 @@ struct SmoothTmaCfg {
                   "register split exceeds the CTA's launch allocation: setmaxnreg.inc would never return");
 };
 
-// grid: x = tiles along columns, y = tiles along rows, z = 3 components * z-chunks (as k_smooth3d).
+// ---- work decomposition -------------------------------------------------------------------------------------------
+// A "column" is one x-y tile of one component, marched along z.  The launch is PERSISTENT: G = (CTAs per SM) x (SMs)
+// CTAs, and the (columns x owned slices) work is cut so that every CTA gets the same number of slice steps:
+//   rounds 0 .. nfull-1 : CTA b marches the whole column r*G + b (adjacent CTAs -> adjacent tiles: halos are shared in L2);
+//   the remaining columns: their slices, laid end to end, are cut into G equal pieces (a piece may span two columns).
+// With equal tiles a plain grid loses up to a whole tile-time in its last wave (528 columns on 148 SMs: 3.57 -> 4 rounds);
+// here the only overhead is the 2R warm-up slices at the head of each piece of the last round.
+struct SmoothSeg {
+    int col;     // column index = (comp * tiles_y + ty) * tiles_x + tx
+    int z0, z1;  // owned output slices [z0, z1) (local indices)
+};
+struct SmoothWork {
+    int ncols, tiles_x, tiles_y;  // columns = 3 * tiles_y * tiles_x
+    int nfull;                    // whole-column rounds
+    int per;                      // slices per CTA in the last round
+    __device__ __forceinline__ int count(int bid, int G, int So) const {
+        (void)G;
+        const long long rem = static_cast<long long>(ncols - nfull * G) * So;
+        const long long l0 = static_cast<long long>(bid) * per, l1 = min(l0 + per, rem);
+        int n = nfull;
+        if (l0 < l1) n += static_cast<int>((l1 - 1) / So - l0 / So) + 1;
+        return n;
+    }
+    __device__ __forceinline__ SmoothSeg get(int k, int bid, int G, int zb, int So) const {
+        SmoothSeg sg;
+        if (k < nfull) {
+            sg.col = k * G + bid;
+            sg.z0 = zb;
+            sg.z1 = zb + So;
+            return sg;
+        }
+        const long long rem = static_cast<long long>(ncols - nfull * G) * So;
+        const long long l0 = static_cast<long long>(bid) * per, l1 = min(l0 + per, rem);
+        const int c0 = static_cast<int>(l0 / So) + (k - nfull);  // k-th column touched by [l0, l1)
+        const long long a = max(l0, static_cast<long long>(c0) * So), b = min(l1, static_cast<long long>(c0 + 1) * So);
+        sg.col = nfull * G + c0;
+        sg.z0 = zb + static_cast<int>(a - static_cast<long long>(c0) * So);
+        sg.z1 = zb + static_cast<int>(b - static_cast<long long>(c0) * So);
+        return sg;
+    }
+};
+
 template <typename T, bool STRICT, int R, int TX, int TY, int OY, int NS, int NXB>
 __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHREADS), DCMA_TMA_MINB)
     k_smooth3d_tma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ in, T *__restrict__ out, const Geo g,
                    const SmoothWeights<T> W, const T *__restrict__ tab_x, const T *__restrict__ tab_y,
                    const T *__restrict__ tab_z, const double *__restrict__ dwx, const double *__restrict__ dwy,
-                   const double *__restrict__ dwz, const int zchunk, const int nzchunks, const Ctrl *__restrict__ ctrl,
+                   const double *__restrict__ dwz, const SmoothWork work, const Ctrl *__restrict__ ctrl,
                    const long long it) {
     using Cfg = SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>;
     constexpr int HX = Cfg::HX, NA = Cfg::NA, PH = Cfg::PH, PWP = Cfg::PWP, SXP = Cfg::SXP, TAPS = Cfg::TAPS, SEG = Cfg::SEG;
@@ -174,14 +215,10 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
     unsigned long long *full_in = bars, *empty_in = bars + NS, *full_x = bars + 2 * NS, *empty_x = bars + 2 * NS + NXB;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int comp = blockIdx.z / nzchunks;
-    const int chunk = blockIdx.z - comp * nzchunks;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int z_begin = g.zb + chunk * zchunk;
-    const int z_end = min(z_begin + zchunk, g.ze);
+    const int bid = blockIdx.x, G = gridDim.x;
+    const int So = g.ze - g.zb;
     const long long plane = static_cast<long long>(g.R) * g.C;
-    const T *src = in + comp * g.N;
-    T *dst = out + comp * g.N;
+    const int nseg = work.count(bid, G, So);
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -197,175 +234,203 @@ __global__ void __launch_bounds__((SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>::NTHR
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (STRICT && threadIdx.x < TX) s_nx[threadIdx.x] = tab_x[x0 + threadIdx.x];
     __syncthreads();
-
-    // slices this CTA stages: [zp_first, zp_last]; those inside the grid AND inside this engine's buffers form one
-    // contiguous range [zlo, zhi] (a slab's halo planes are inside it); the others contribute zeros and are skipped by
-    // every role alike, so the pipeline indices count in-grid slices only.
-    const int zp_first = z_begin - R, zp_last = z_end - 1 + R;
-    const int zlo = max(zp_first, max(0, -g.zoff));
-    const int zhi = min(zp_last, min(g.S - 1, g.Sg - 1 - g.zoff));
-    const int n_in = zhi - zlo + 1;
 
 #define DCMA_WX(k) W.w[0][k]
 #define DCMA_WY(k) W.w[1][k]
 #define DCMA_WZ(k) W.w[2][k]
+    // Per segment: slices staged = [zp_first, zp_last] = [z0 - R, z1 - 1 + R]; those inside the grid AND inside this
+    // engine's buffers form one contiguous range [zlo, zhi] (a slab's halo planes are inside it); the others contribute
+    // zeros and are skipped by every role alike, so the pipeline counters count in-grid slices only -- and they run on
+    // across segments (the barriers' phases do not know about segments).
 
     static_assert(DCMA_TMA_IDLE_WARPS == 0, "idle warps cannot share a warpgroup with consumers (setmaxnreg is warpgroup-wide)");
     if (warp < NPW) {
         // =============================================== producers =======================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCMA_TMA_PREG));
         const bool tma_thread = (threadIdx.x == 0);
-        auto issue = [&](int i) {  // in-grid slice number i -> stage i % NS
-            const int s = i % NS;
-            mbar_wait(empty_in + s, ((i / NS) & 1) ^ 1);  // first round: passes at once (fresh barrier, opposite parity)
-            mbar_arrive_expect_tx(full_in + s, Cfg::stage_bytes);
-            tma_load_4d(reinterpret_cast<unsigned char *>(s_in) + s * Cfg::stage_stride, &tmap, x0 - HX, y0 - R, zlo + i, comp,
-                        full_in + s);
-        };
-        if (tma_thread) {
-            for (int i = 0; i < NS - 1 && i < n_in; ++i) issue(i);
-        }
         const int seg = warp, row = lane;  // task: outputs [seg*8, seg*8+8) of staged row `row`
-        int s = 0, ph_in = 0;              // stage and its parity
-        for (int i = 0; i < n_in; ++i) {
-            if (tma_thread && i + NS - 1 < n_in) issue(i + NS - 1);
-            __syncwarp();
-            const int b = i % NXB;
-            mbar_wait(full_in + s, ph_in);
-            mbar_wait(empty_x + b, ((i / NXB) & 1) ^ 1);
-            if (PH == 32 || row < PH) {
-                const T *sb = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(s_in) + s * Cfg::stage_stride) +
-                              row * PWP + seg * SEG;
-                T a[NA];
-#pragma unroll
-                for (int m = 0; m < NA / 2; ++m) {
-                    const double2 t = *reinterpret_cast<const double2 *>(sb + 2 * m);
-                    a[2 * m] = t.x;
-                    a[2 * m + 1] = t.y;
+        int si = 0, phi = 1;                // TMA thread: next stage to fill and the parity of its `empty` wait
+        int s = 0, ph_in = 0;               // x pass: stage being read and its `full` parity
+        int b = 0, ph_x = 1;                // x-pass tile being written and the parity of its `empty` wait
+        for (int k = 0; k < nseg; ++k) {
+            const SmoothSeg sg = work.get(k, bid, G, g.zb, So);
+            const int tx = sg.col % work.tiles_x, rest = sg.col / work.tiles_x;
+            const int ty = rest % work.tiles_y, comp = rest / work.tiles_y;
+            const int x0 = tx * TX, y0 = ty * TY;
+            const int zp_first = sg.z0 - R, zp_last = sg.z1 - 1 + R;
+            const int zlo = max(zp_first, max(0, -g.zoff));
+            const int zhi = min(zp_last, min(g.S - 1, g.Sg - 1 - g.zoff));
+            const int n_in = zhi - zlo + 1;
+            if constexpr (STRICT) {  // this warp's 8 x normalisers (read back by this warp only)
+                if (lane < SEG) s_nx[seg * SEG + lane] = tab_x[x0 + seg * SEG + lane];
+                __syncwarp();
+            }
+            auto issue = [&](int z) {
+                mbar_wait(empty_in + si, phi);  // first use of a stage: passes at once (fresh barrier, opposite parity)
+                mbar_arrive_expect_tx(full_in + si, Cfg::stage_bytes);
+                tma_load_4d(reinterpret_cast<unsigned char *>(s_in) + si * Cfg::stage_stride, &tmap, x0 - HX, y0 - R, z, comp,
+                            full_in + si);
+                if (++si == NS) {
+                    si = 0;
+                    phi ^= 1;
                 }
-                T o[SEG];
+            };
+            if (tma_thread) {
+                for (int i = 0; i < NS - 1 && i < n_in; ++i) issue(zlo + i);
+            }
+            for (int i = 0; i < n_in; ++i) {
+                if (tma_thread && i + NS - 1 < n_in) issue(zlo + i + NS - 1);
+                __syncwarp();
+                mbar_wait(full_in + s, ph_in);
+                mbar_wait(empty_x + b, ph_x);
+                if (PH == 32 || row < PH) {
+                    const T *sb = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(s_in) + s * Cfg::stage_stride) +
+                                  row * PWP + seg * SEG;
+                    T a[NA];
 #pragma unroll
-                for (int i2 = 0; i2 < SEG; ++i2) {
-                    T sum = DCMA_WX(0) * a[HX - R + i2];  // taps in ascending order, as the reference (cc:619-631)
-#pragma unroll
-                    for (int k = 1; k < TAPS; ++k) sum += DCMA_WX(k) * a[HX - R + i2 + k];
-                    o[i2] = sum;
-                }
-                if constexpr (STRICT) {
-#pragma unroll
-                    for (int m = 0; m < SEG / 2; ++m) {
-                        const double2 n2 = *reinterpret_cast<const double2 *>(s_nx + seg * SEG + 2 * m);
-                        o[2 * m] = o[2 * m] / n2.x;
-                        o[2 * m + 1] = o[2 * m + 1] / n2.y;
+                    for (int m = 0; m < NA / 2; ++m) {
+                        const double2 t = *reinterpret_cast<const double2 *>(sb + 2 * m);
+                        a[2 * m] = t.x;
+                        a[2 * m + 1] = t.y;
                     }
-                }
-                T *sx = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(s_x) + b * Cfg::sx_stride) + row * SXP + seg * SEG;
+                    T o[SEG];
 #pragma unroll
-                for (int m = 0; m < SEG / 2; ++m) *reinterpret_cast<double2 *>(sx + 2 * m) = make_double2(o[2 * m], o[2 * m + 1]);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(full_x + b);   // this warp's segment column of the x-pass tile is written
-                mbar_arrive(empty_in + s);  // ... and it is done reading the staged slice
-            }
-            if (++s == NS) {
-                s = 0;
-                ph_in ^= 1;
+                    for (int i2 = 0; i2 < SEG; ++i2) {
+                        T sum = DCMA_WX(0) * a[HX - R + i2];  // taps in ascending order, as the reference (cc:619-631)
+#pragma unroll
+                        for (int kk = 1; kk < TAPS; ++kk) sum += DCMA_WX(kk) * a[HX - R + i2 + kk];
+                        o[i2] = sum;
+                    }
+                    if constexpr (STRICT) {
+#pragma unroll
+                        for (int m = 0; m < SEG / 2; ++m) {
+                            const double2 n2 = *reinterpret_cast<const double2 *>(s_nx + seg * SEG + 2 * m);
+                            o[2 * m] = o[2 * m] / n2.x;
+                            o[2 * m + 1] = o[2 * m + 1] / n2.y;
+                        }
+                    }
+                    T *sx = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(s_x) + b * Cfg::sx_stride) + row * SXP + seg * SEG;
+#pragma unroll
+                    for (int m = 0; m < SEG / 2; ++m) *reinterpret_cast<double2 *>(sx + 2 * m) = make_double2(o[2 * m], o[2 * m + 1]);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(full_x + b);    // this warp's segment column of the x-pass tile is written
+                    mbar_arrive(empty_in + s);  // ... and it is done reading the staged slice
+                }
+                if (++s == NS) {
+                    s = 0;
+                    ph_in ^= 1;
+                }
+                if (++b == NXB) {
+                    b = 0;
+                    ph_x ^= 1;
+                }
             }
         }
         return;
     }
 
-    if (Cfg::NIW > 0 && warp >= NPW + NCW) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        return;
-    }
     // ================================================= consumers =========================================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCMA_TMA_CREG));
     const int cw = warp - NPW;
     const int xh = cw % Cfg::NCX;          // which 32-column part of the tile
     const int yl0 = (cw / Cfg::NCX) * OY;  // first owned (local) output row; owned rows are adjacent
-    const int gx = x0 + xh * 32 + lane;    // owned column
-    // per-position normalisers (STRICT: weight sums to divide by; otherwise reciprocals, applied once at the end)
-    T ny[OY];
+    int b = 0, ph_x = 0;                   // x-pass tile being read and its `full` parity
+    for (int k = 0; k < nseg; ++k) {
+        const SmoothSeg sg = work.get(k, bid, G, g.zb, So);
+        const int tx = sg.col % work.tiles_x, rest = sg.col / work.tiles_x;
+        const int ty = rest % work.tiles_y, comp = rest / work.tiles_y;
+        const int x0 = tx * TX, y0 = ty * TY;
+        const int z_begin = sg.z0, z_end = sg.z1;
+        const int zp_first = z_begin - R, zp_last = z_end - 1 + R;
+        const int zlo = max(zp_first, max(0, -g.zoff));
+        const int zhi = min(zp_last, min(g.S - 1, g.Sg - 1 - g.zoff));
+        const T *src = in + comp * g.N;
+        T *dst = out + comp * g.N;
+        const int gx = x0 + xh * 32 + lane;  // owned column
+        // per-position normalisers (STRICT: weight sums to divide by; otherwise reciprocals, applied once at the end)
+        T ny[OY];
 #pragma unroll
-    for (int j = 0; j < OY; ++j) ny[j] = tab_y[y0 + yl0 + j];
-    if constexpr (!STRICT) {
-        const T nxv = tab_x[gx];
+        for (int j = 0; j < OY; ++j) ny[j] = tab_y[y0 + yl0 + j];
+        if constexpr (!STRICT) {
+            const T nxv = tab_x[gx];
 #pragma unroll
-        for (int j = 0; j < OY; ++j) ny[j] *= nxv;
-    }
-    T win[OY][TAPS];  // z ring of xy-smoothed values, compile-time indices (one copy of the step per ring phase)
+            for (int j = 0; j < OY; ++j) ny[j] *= nxv;
+        }
+        T win[OY][TAPS];  // z ring of xy-smoothed values, compile-time indices (one copy of the step per ring phase)
 #pragma unroll
-    for (int j = 0; j < OY; ++j)
+        for (int j = 0; j < OY; ++j)
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) win[j][k] = T(0);
-    T nz_next = tab_z[z_begin < z_end ? z_begin : 0];
-    const bool col_ok = (gx < g.C);
-    bool bad = false;  // some output of this thread came out non-finite
-    // running output pointer: row yl0 of the tile, column gx, slice of the next output
-    T *outp = dst + static_cast<long long>(z_begin) * plane + static_cast<long long>(y0 + yl0) * g.C + gx;
-    const int rows_ok = col_ok ? max(0, min(OY, g.R - (y0 + yl0))) : 0;  // owned rows inside the grid
+            for (int kk = 0; kk < TAPS; ++kk) win[j][kk] = T(0);
+        T nz_next = tab_z[z_begin];
+        const bool col_ok = (gx < g.C);
+        bool bad = false;  // some output of this thread came out non-finite
+        // running output pointer: row yl0 of the tile, column gx, slice of the next output
+        T *outp = dst + static_cast<long long>(z_begin) * plane + static_cast<long long>(y0 + yl0) * g.C + gx;
+        const int rows_ok = col_ok ? max(0, min(OY, g.R - (y0 + yl0))) : 0;  // owned rows inside the grid
 
-    auto step = [&](auto ph, const int zp) {
-        constexpr int P = decltype(ph)::value;
-        const int i = zp - zlo;
-        const int zo = zp - R;  // output slice completed by this step
-        if (i >= 0 && i < n_in) {
-            const int b = i % NXB;
-            mbar_wait(full_x + b, (i / NXB) & 1);
-            const T *sx = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(s_x) + b * Cfg::sx_stride) +
-                          yl0 * SXP + xh * 32 + lane;
-            // y pass: rows streamed once; output j takes row m as its tap k = m - j (ascending k: the reference's order)
+        auto step = [&](auto ph, const int zp) {
+            constexpr int P = decltype(ph)::value;
+            const int zo = zp - R;  // output slice completed by this step
+            if (zp >= zlo && zp <= zhi) {
+                mbar_wait(full_x + b, ph_x);
+                const T *sx = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(s_x) + b * Cfg::sx_stride) +
+                              yl0 * SXP + xh * 32 + lane;
+                // y pass: rows streamed once; output j takes row m as its tap k = m - j (ascending k: the reference's order)
 #pragma unroll
-            for (int m = 0; m < OY + 2 * R; ++m) {
-                const T t = sx[m * SXP];
+                for (int m = 0; m < OY + 2 * R; ++m) {
+                    const T t = sx[m * SXP];
 #pragma unroll
-                for (int j = 0; j < OY; ++j) {
-                    const int k = m - j;
-                    if (k < 0 || k >= TAPS) continue;
-                    if (k == 0)
-                        win[j][P] = DCMA_WY(0) * t;
-                    else
-                        win[j][P] += DCMA_WY(k) * t;
+                    for (int j = 0; j < OY; ++j) {
+                        const int kk = m - j;
+                        if (kk < 0 || kk >= TAPS) continue;
+                        if (kk == 0)
+                            win[j][P] = DCMA_WY(0) * t;
+                        else
+                            win[j][P] += DCMA_WY(kk) * t;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_x + b);  // the tile is in registers: the producers may overwrite it
+                if (++b == NXB) {
+                    b = 0;
+                    ph_x ^= 1;
+                }
+                if constexpr (STRICT) {
+#pragma unroll
+                    for (int j = 0; j < OY; ++j) win[j][P] = win[j][P] / ny[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < OY; ++j) win[j][P] = T(0);
+            }
+            const T nz = nz_next;  // requested one step ago
+            nz_next = tab_z[min(max(zo + 1, z_begin), z_end - 1)];
+            if (zo < z_begin) return;  // warm-up slices of this segment
+#pragma unroll
+            for (int j = 0; j < OY; ++j) {
+                T zs = DCMA_WZ(0) * win[j][(P + 1) % TAPS];  // tap k of the z pass (oldest first) lives in slot (P+1+k) % TAPS
+#pragma unroll
+                for (int kk = 1; kk < TAPS; ++kk) zs += DCMA_WZ(kk) * win[j][(P + 1 + kk) % TAPS];
+                T o;
+                if constexpr (STRICT)
+                    o = zs / nz;
+                else
+                    o = zs * (ny[j] * nz);
+                if (j < rows_ok) {
+                    // x*0 is 0 for finite x and NaN otherwise.  A non-finite result <=> a non-finite tap somewhere in the
+                    // (2r+1)^3 support: such outputs are redone literally after the march (smooth_fix_column)
+                    bad |= !(o * T(0) == T(0));
+                    outp[static_cast<long long>(j) * g.C] = o;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_x + b);  // the tile is in registers: the producers may overwrite it
-            if constexpr (STRICT) {
-#pragma unroll
-                for (int j = 0; j < OY; ++j) win[j][P] = win[j][P] / ny[j];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < OY; ++j) win[j][P] = T(0);
-        }
-        const T nz = nz_next;  // requested one step ago
-        nz_next = tab_z[min(max(zo + 1, z_begin), z_end - 1)];
-        if (zo < z_begin) return;  // warm-up slices of this chunk
-#pragma unroll
-        for (int j = 0; j < OY; ++j) {
-            T zs = DCMA_WZ(0) * win[j][(P + 1) % TAPS];  // tap k of the z pass (oldest first) lives in slot (P+1+k) % TAPS
-#pragma unroll
-            for (int k = 1; k < TAPS; ++k) zs += DCMA_WZ(k) * win[j][(P + 1 + k) % TAPS];
-            T o;
-            if constexpr (STRICT)
-                o = zs / nz;
-            else
-                o = zs * (ny[j] * nz);
-            if (j < rows_ok) {
-                // x*0 is 0 for finite x and NaN otherwise.  A non-finite result <=> a non-finite tap somewhere in the
-                // (2r+1)^3 support: such outputs are redone literally after the march (smooth_fix_column)
-                bad |= !(o * T(0) == T(0));
-                outp[static_cast<long long>(j) * g.C] = o;
-            }
-        }
-        outp += plane;
-    };
-    for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
-    if (bad) smooth_fix_column<T>(src, dst, g, dwx, dwy, dwz, W.r[0], W.r[1], W.r[2], gx, y0 + yl0, OY, z_begin, z_end);
+            outp += plane;
+        };
+        for (int zb = zp_first; zb <= zp_last; zb += TAPS) unroll_phases<TAPS, 0>(step, zb, zp_last);
+        if (bad) smooth_fix_column<T>(src, dst, g, dwx, dwy, dwz, W.r[0], W.r[1], W.r[2], gx, y0 + yl0, OY, z_begin, z_end);
+    }
 #undef DCMA_WX
 #undef DCMA_WY
 #undef DCMA_WZ
