@@ -9,8 +9,12 @@ sigma_d = sigma_u = 1.5 mm, convergence threshold 0 (exactly `iters` iterations 
 (voxels x iterations executed / time).
 
   value     : loop-only throughput, inputs resident in HBM, device-timed (CUDA events on the engine's stream),
-              max over ranks.  N > 1: one independent registration per GPU (BASELINE config 5 style, weak scaling,
-              no data-path collective).
+              max over ranks.
+              N = 1 : BASELINE config 2 (512x512x256, 200 iterations per step).
+              N > 1 : BASELINE config 4 -- ONE registration of 1024^3 sharded into z-slabs over the N ranks (halo
+                      exchange over NVLink every iteration), "scaling": "strong".  The throughput of N independent
+                      config-2 registrations (no data-path collective) is reported beside it as `replicas`, and
+                      `--replicas` makes that the headline instead.
   e2e       : the same metric through the C-ABI one-shot call `dcma_b200_demons_register` with HOST (pinned) buffers:
               H2D of fixed+moving, the loop, and D2H of the fp64 deformation field are all inside the timed region.
   roofline  : dominant kernel (k_smooth3d): algorithmic bytes per launch / mean launch time from CUDA events.
@@ -171,15 +175,36 @@ def run_reference(args):
             vals.append(base["value"])
             ms.append(base["ms_per_iter"])
     v = sum(vals) / len(vals)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg = workload_config(args, "fp64") if world <= 1 or args.replicas else slab_config(args, "fp64", world, SLAB_SHAPE)
+    cfg["reference_sample"] = base["sample"]
     line = {"impl": "reference", "metric": "demons_voxel_updates_per_s", "value": v, "unit": "voxel-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms) * 2,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, "fp64"),
+            "iterations_timed": 2,  # per step: 1 warm-up + 2 timed iterations of the reference engine on the sample
+            "higher_is_better": True, "scaling": "weak" if world <= 1 or args.replicas else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
             "cpu_baseline": {"value": v, "unit": "voxel-updates/s", "cores": base["cores"], "kind": base["kind"],
                              "sample": base["sample"]},
             "e2e": {"value": v, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+SLAB_SHAPE = (1024, 1024, 1024)  # BASELINE config 4
+SLAB_ITERS = 50                   # iterations per step of the sharded run (config 4 asks for >= 20)
+CHECK_SHAPE = (256, 256, 256)     # slab-vs-whole bit-identity check (a size every rank can also run whole)
+
+
+def slab_config(args, mode, world, shape):
+    return {"workload": f"BASELINE config 4: one synthetic CT pair {shape[2]}x{shape[1]}x{shape[0]} (textured phantom + known "
+                        f"sinusoidal warp) sharded into {world} z-slabs, diffeomorphic Demons, sigma_d=sigma_u="
+                        f"{WORKLOAD['sigma_d']} mm (r=4, 9 taps), {args.slab_iters} iterations per step, threshold 0",
+            "iterations_per_step": args.slab_iters, "field_mode": mode,
+            "parallelism": f"z-slabs over {world} GPU(s), one rank per GPU, moving image replicated; per iteration the "
+                           f"z-neighbours exchange r_z planes of U, halo planes of smoothed U and r_z planes of D over "
+                           f"NVLink (IPC-mapped peer buffers, copy engines); MSE terms combined after the loop",
+            "l2": "working set (tens of GB of fields per rank) is far larger than the 126 MB L2; no flush needed"}
 
 
 def workload_config(args, mode):
@@ -188,7 +213,8 @@ def workload_config(args, mode):
                         f"warp), diffeomorphic Demons, sigma_d=sigma_u={WORKLOAD['sigma_d']} mm (r=4, 9 taps), "
                         f"{args.iters} iterations per step, threshold 0",
             "iterations_per_step": args.iters, "field_mode": mode,
-            "parallelism": "single GPU" if args.gpus == 1 else f"{args.gpus} independent registrations, one per GPU",
+            "parallelism": "single GPU" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else
+                           f"{os.environ.get('WORLD_SIZE')} independent registrations, one per GPU (no data-path collective)",
             "l2": "working set (>= 3 GB of fields) is far larger than the 126 MB L2; no flush needed"}
 
 
@@ -379,30 +405,105 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _replicas_throughput(args, dist, dev, rank, world, local, stream):
+    """N independent config-2 registrations, one per GPU, no data-path collective (BASELINE config 5 style): a short
+    device-timed run, max over ranks.  Reported beside the sharded headline."""
+    import torch
+    from dicomautomaton_b200 import phantom
+    from dicomautomaton_b200.demons import AlignViaDemonsParams, DemonsEngine
+    shape, spacing = WORKLOAD["shape"], WORKLOAD["spacing"]
+    n_it = min(args.iters, 50)
+    f, m = phantom.make_pair(shape, spacing=spacing, case=rank, device=dev)
+    par = AlignViaDemonsParams(max_iterations=n_it, convergence_threshold=0.0,
+                               deformation_field_smoothing_sigma=WORKLOAD["sigma_d"],
+                               update_field_smoothing_sigma=WORKLOAD["sigma_u"],
+                               use_diffeomorphic=WORKLOAD["diffeomorphic"], verbosity=0, field_mode=args.field_mode,
+                               device=local)
+    eng = DemonsEngine.empty(shape, spacing, par, stream=stream.cuda_stream)
+    eng.load_device(f.data_ptr(), m.data_ptr())
+    eng.run(5)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.load_device(f.data_ptr(), m.data_ptr())
+    _, st = eng.run(n_it)
+    eng.close()
+    t = torch.tensor([st.loop_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nvox = shape[0] * shape[1] * shape[2]
+    del f, m
+    return {"value": nvox * st.iterations_done * world / (float(t[0]) * 1e-3), "unit": "voxel-updates/s",
+            "workload": f"{world} independent registrations of {shape[2]}x{shape[1]}x{shape[0]} (config-2 parameters), one per "
+                        f"GPU, {int(st.iterations_done)} iterations, no data-path collective", "scaling": "weak"}
+
+
+def _slab_bit_identity(args, dist, dev, rank, world, local):
+    """The sharded run against the whole-volume engine at a size every rank can also run whole: the owned slices of the
+    slab result must equal the whole-volume field BIT FOR BIT (halo exchange must not change any voxel's arithmetic)."""
+    import numpy as np
+    import torch
+    from dicomautomaton_b200 import phantom
+    from dicomautomaton_b200.demons import AlignViaDemonsParams, DemonsEngine, DemonsSlabGroup
+    shape, iters = CHECK_SHAPE, 10
+    f, m = phantom.make_pair(shape, device=dev)
+    par = AlignViaDemonsParams(max_iterations=iters, convergence_threshold=0.0,
+                               deformation_field_smoothing_sigma=WORKLOAD["sigma_d"],
+                               update_field_smoothing_sigma=WORKLOAD["sigma_u"], use_diffeomorphic=True, verbosity=0,
+                               field_mode=args.field_mode, device=local)
+    eng = DemonsEngine.empty(shape, (1.0, 1.0, 1.0), par)
+    eng.load_device(f.data_ptr(), m.data_ptr())
+    hw, _ = eng.run(iters)
+    whole = eng.get("deformation")
+    eng.close()
+    ident = [DemonsSlabGroup.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    grp = DemonsSlabGroup.nccl(shape, (1.0, 1.0, 1.0), par, ident[0], rank, world, local)
+    grp.load_device(f.data_ptr(), m.data_ptr())
+    hs, _ = grp.run(iters)
+    z0, z1 = grp.owned_range()
+    mine = grp.get_deformation()
+    stats = grp.exchange_stats()
+    grp.close()
+    same = bool(np.array_equal(mine, whole[z0:z1]))
+    mse_rel = float(np.max(np.abs(hs - hw) / np.abs(hw))) if len(hs) == len(hw) and len(hw) else float("nan")
+    t = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    del f, m
+    return {"shape": f"{shape[2]}x{shape[1]}x{shape[0]}", "iterations": iters, "bit_identical_on_all_ranks": bool(t[0] == 1.0),
+            "mse_history_max_rel_diff": mse_rel, "overlapped": stats["overlapped"], "transport": stats["transport"]}
+
+
 def run_slab(args):
-    """--slab: ONE registration sharded into z-slabs over the ranks (BASELINE config 4 layout): NCCL halo exchange and
-    MSE all-gather inside the loop, strong scaling (the total work is fixed).  Device-timed per rank by the engine's
-    own CUDA events, max over ranks."""
+    """N > 1 (default) or --slab: ONE registration sharded into z-slabs over the ranks (BASELINE config 4): halo exchange
+    over NVLink inside the loop, strong scaling (the total work is fixed).  Device-timed per rank by the engine's own CUDA
+    events around the loop, max over ranks."""
+    import ctypes as C
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from dicomautomaton_b200 import phantom
+    from dicomautomaton_b200 import capi, phantom
     from dicomautomaton_b200.demons import AlignViaDemonsParams, DemonsSlabGroup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else WORKLOAD["shape"]
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else SLAB_SHAPE
     spacing = WORKLOAD["spacing"]
     nvox = shape[0] * shape[1] * shape[2]
+    iters = args.slab_iters
+    mode = args.field_mode
     fixed, moving = phantom.make_pair(shape, spacing=spacing, device=dev)
     torch.cuda.synchronize()
-    par = AlignViaDemonsParams(max_iterations=args.iters, convergence_threshold=0.0,
+    par = AlignViaDemonsParams(max_iterations=iters, convergence_threshold=0.0,
                                deformation_field_smoothing_sigma=WORKLOAD["sigma_d"],
                                update_field_smoothing_sigma=WORKLOAD["sigma_u"],
-                               use_diffeomorphic=WORKLOAD["diffeomorphic"], verbosity=0, field_mode=args.field_mode,
+                               use_diffeomorphic=WORKLOAD["diffeomorphic"], verbosity=0, field_mode=mode,
                                device=local)
     ident = [DemonsSlabGroup.unique_id() if rank == 0 else None]
     if world > 1:
@@ -413,51 +514,112 @@ def run_slab(args):
 
     def step():
         grp.load_device(fixed.data_ptr(), moving.data_ptr())
-        return grp.run(args.iters)
+        return grp.run(iters)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     sampler.start()
-    ms, iters_done, launches = 0.0, 0, 0
+    t0 = time.perf_counter()
+    ms, iters_done, launches, x_ms, x_n, halo_bytes = 0.0, 0, 0, 0.0, 0, 0
     for _ in range(args.steps):
         hist, st = step()
         ms += st.loop_ms
         iters_done += st.iterations_done
         launches += st.kernel_launches
-    torch.cuda.synchronize()
+        xs = grp.exchange_stats()
+        x_ms += xs["exchange_ms"]
+        x_n += xs["exchanges"]
+        halo_bytes += grp.halo_bytes
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(launches), x_ms, float(halo_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         tm = t.clone()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = t.clone()
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        ms, launches = float(tm[0]), int(ts[1])
+        ms, launches, x_ms_max, halo_bytes_all = float(tm[0]), int(ts[1]), float(tm[2]), float(ts[3])
+    else:
+        x_ms_max, halo_bytes_all = x_ms, float(halo_bytes)
     value = nvox * iters_done / (ms * 1e-3)
     peak, peak_src = measured_peak_gbs()
-    mode = args.field_mode
+    final_mse = float(hist[-1]) if len(hist) else None
+
+    # ---- end to end through the C ABI of the sharded path with pinned HOST buffers: every rank uploads its slab of the
+    # fixed image and the whole moving image, runs the loop and downloads its slab of the fp64 field
+    lib = capi.lib()
+    z0, z1 = grp.owned_range()
+    plane = shape[1] * shape[2]
+    hf = fixed.cpu().pin_memory()
+    hm = moving.cpu().pin_memory()
+    hD = torch.empty(((z1 - z0) * plane, 3), dtype=torch.float64).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    stats = capi.RunStats()
+
+    def e2e_step():
+        capi.check(lib.dcma_b200_slab_group_load(grp._h, C.c_void_p(hf.data_ptr()), C.c_void_p(hm.data_ptr()), 0))
+        capi.check(lib.dcma_b200_slab_group_run(grp._h, iters, None, C.byref(stats)))
+        capi.check(lib.dcma_b200_slab_group_get_deformation(grp._h, C.c_void_p(hD.data_ptr())))
+    e2e_step()
+    barrier()
+    te0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        e2e_step()
+        e2e_iters += stats.iterations_done
+    barrier()
+    e2e_s = time.perf_counter() - te0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    h2d = ((z1 - z0) + (grp.exchange_stats()["halo_planes"] * 2) + shape[0]) * plane * 4  # slab of F (+halo) and whole M
+    e2e = {"value": nvox * e2e_iters / e2e_s, "unit": "voxel-updates/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int((z1 - z0) * plane * 24), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "bytes_are": "per rank (rank 0)",
+           "api": "dcma_b200_slab_group_load / _run / _get_deformation (C ABI, pinned host buffers; each rank uploads its "
+                  "slab of the fixed image and the whole moving image, downloads its slab of the fp64 AoS field)"}
+    xstats = grp.exchange_stats()
+    grp.close()
+    del hf, hm, hD, fixed, moving
+    torch.cuda.empty_cache()
+
+    check = _slab_bit_identity(args, dist, dev, rank, world, local) if world > 1 and not args.no_slab_check else None
+    replicas = None
+    if world > 1 and not args.no_replicas:
+        replicas = _replicas_throughput(args, dist, dev, rank, world, local, torch.cuda.current_stream())
+
     if rank == 0:
-        cfg = workload_config(args, mode)
-        cfg["workload"] = (f"one registration of {shape[2]}x{shape[1]}x{shape[0]} sharded into {world} z-slab(s), "
-                           f"diffeomorphic, sigma 1.5 mm, {args.iters} iterations per step; NCCL halo exchange "
-                           f"(r_z planes of U and D, halo planes of U~) and MSE all-gather every iteration")
-        cfg["parallelism"] = f"z-slabs over {world} GPU(s), moving image replicated"
+        n_it = max(iters_done, 1)
         line = {"metric": "demons_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64" if mode != "fp32" else "f32",
-                "data": "synthetic", "config": cfg, "ms_per_iteration": ms / max(iters_done, 1),
-                "final_mse": float(hist[-1]) if len(hist) else None, "clocks": clocks, "gpu_launches": launches,
-                "halo_bytes_per_step_rank0": grp.halo_bytes,
-                "roofline": {"bound": "hbm", "whole_iteration": {
-                    "algorithmic_bytes_per_voxel_update": B_ALG[mode],
-                    "achieved_GBs_per_gpu": value / world * B_ALG[mode] / 1e9,
-                    "frac_of_peak": value / world * B_ALG[mode] / 1e9 / peak}, "peak": peak, "peak_source": peak_src}}
+                "data": "synthetic", "config": slab_config(args, mode, world, shape),
+                "ms_per_iteration": ms / n_it, "final_mse": final_mse, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches, "wall_ms_timed_region": wall_ms,
+                "exchange_ms_per_iter": x_ms_max / n_it, "exchanges_per_iter": x_n / n_it,
+                "halo_bytes_per_iter": halo_bytes_all / n_it, "halo_planes": xstats["halo_planes"],
+                "exchange_overlapped": xstats["overlapped"], "transport": xstats["transport"],
+                "slab_vs_whole_check": check, "replicas": replicas,
+                "roofline": {"bound": "hbm", "kernel": "whole iteration (per-kernel split: see the N=1 line)",
+                             "achieved": value / world * B_ALG[mode] / 1e9, "peak": peak, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": value / world * B_ALG[mode] / 1e9 / peak, "traffic": None,
+                             "whole_iteration": {"algorithmic_bytes_per_voxel_update": B_ALG[mode],
+                                                 "achieved_GBs_per_gpu": value / world * B_ALG[mode] / 1e9,
+                                                 "frac_of_peak": value / world * B_ALG[mode] / 1e9 / peak}},
+                "cpu_baseline": None, "nccl": {"version": ".".join(str(v) for v in torch.cuda.nccl.version()),
+                                               "debug": os.environ.get("NCCL_DEBUG", "")},
+                "parity": "slab result == whole-volume engine bit for bit (slab_vs_whole_check, run here); the whole-volume "
+                          "engine vs the reference: tests/test_gpu_full_length.py"}
         print(json.dumps(line), flush=True)
-    grp.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -475,19 +637,27 @@ def main():
                     help="field storage/arithmetic of the measured run.  Default fp64: the reference's own storage type, "
                          "3e-7 mm from the reference engine after 200 iterations at full size.  fp32 (float fields, "
                          "FFMA2 smoothing) is ~1.9x faster and is reported beside it in `other_modes`; at full size its "
-                         "worst voxel is 1.8e-3 mm off (99.99 % of voxels within 4e-6 mm), i.e. outside the 1e-3 mm "
+                         "worst voxel is 1.8e-3 mm off (99.99 %% of voxels within 4e-6 mm), i.e. outside the 1e-3 mm "
                          "tolerance, so it is not the headline")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short fp64 run reported beside the headline")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slab", action="store_true",
-                    help="shard ONE registration into z-slabs over the ranks (NCCL halos, strong scaling) instead of "
-                         "one independent registration per GPU")
-    ap.add_argument("--shape", default="", help="--slab only: slices,rows,cols (default: the config-2 volume)")
+                    help="force the z-slab run (the default whenever WORLD_SIZE > 1) also on one GPU")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N > 1: make N independent config-2 registrations (weak scaling, no collective) the headline "
+                         "instead of the sharded 1024^3 registration")
+    ap.add_argument("--shape", default="", help="sharded run only: slices,rows,cols (default 1024,1024,1024 = config 4)")
+    ap.add_argument("--slab-iters", type=int, default=SLAB_ITERS, help="iterations per step of the sharded run")
+    ap.add_argument("--no-slab-check", action="store_true", help="skip the slab-vs-whole bit-identity check")
+    ap.add_argument("--no-replicas", action="store_true", help="skip the independent-registrations figure")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("NCCL_DEBUG") is None and world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's own diagnostics in the log (INFO is very chatty at 8 ranks)
     if args.impl == "reference":
         run_reference(args)
-    elif args.slab:
+    elif args.slab or (world > 1 and not args.replicas):
         run_slab(args)
     else:
         run_ours(args)

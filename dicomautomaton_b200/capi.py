@@ -92,6 +92,7 @@ SYMBOLS = {
     "dcma_b200_slab_group_range": (C.c_int, [_vp, _ip, _ip]),
     "dcma_b200_slab_group_get_deformation": (C.c_int, [_vp, _vp]),
     "dcma_b200_slab_group_halo_bytes": (C.c_int64, [_vp]),
+    "dcma_b200_slab_group_exchange_stats": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _LIB = None

@@ -208,15 +208,32 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
                 // the volume is sharded into z-slabs over devices 0..n_devices-1 of this process
                 std::vector<int> dev(params->n_devices);
                 for (int i = 0; i < params->n_devices; ++i) dev[i] = i;
-                dcma::SlabGroup grp(*geom, *params, dev, params->halo_planes > 0 ? params->halo_planes : -1);
-                const auto s0 = clk::now();
-                grp.load(fixed, moving, false);
-                const auto s1 = clk::now();
+                // A composition gather that leaves the halo fails the run loudly (std::logic_error from SlabGroup::run).
+                // With the default halo the registration is then repeated with a doubled one (an explicit halo_planes
+                // is the caller's decision and is not second-guessed).
+                int64_t halo = params->halo_planes > 0 ? params->halo_planes : dcma::SlabGroup::default_halo(*geom, *params);
+                std::chrono::steady_clock::time_point s0, s1, s2, s3;
                 dcma_b200_run_stats local;
-                grp.run(params->max_iterations, mse_history, &local);
-                const auto s2 = clk::now();
-                grp.get_deformation(deformation_out);
-                const auto s3 = clk::now();
+                for (;;) {
+                    dcma::SlabGroup grp(*geom, *params, dev, halo);
+                    s0 = clk::now();
+                    grp.load(fixed, moving, false);
+                    s1 = clk::now();
+                    try {
+                        grp.run(params->max_iterations, mse_history, &local);
+                    } catch (const std::logic_error &ex) {
+                        const bool overflow = std::string(ex.what()).find("left the slab halo") != std::string::npos;
+                        if (!overflow || params->halo_planes > 0 || halo * 2 * params->n_devices > geom->slices) throw;
+                        if (params->verbosity >= 1)
+                            std::fprintf(stderr, "[dcma_b200] %s -- repeating with halo_planes = %lld\n", ex.what(), (long long)(2 * halo));
+                        halo *= 2;
+                        continue;
+                    }
+                    s2 = clk::now();
+                    grp.get_deformation(deformation_out);
+                    s3 = clk::now();
+                    break;
+                }
                 if (stats) {
                     *stats = local;
                     const long long n = geom->slices * geom->rows * geom->cols;
@@ -323,6 +340,17 @@ int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deform
 }
 
 int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g) { return g ? g->impl->halo_bytes_last_run() : 0; }
+
+int dcma_b200_slab_group_exchange_stats(const dcma_b200_slab_group *g, double *exchange_ms, int64_t *exchanges, int32_t *overlapped,
+                                        int32_t *transport, int64_t *halo_planes) {
+    if (!g) return fail(DCMA_B200_EINVAL, "null group", nullptr, 0);
+    if (exchange_ms) *exchange_ms = g->impl->exchange_ms_last_run();
+    if (exchanges) *exchanges = g->impl->exchanges_last_run();
+    if (overlapped) *overlapped = g->impl->overlapped_last_run() ? 1 : 0;
+    if (transport) *transport = g->impl->transport();
+    if (halo_planes) *halo_planes = g->impl->halo();
+    return DCMA_B200_OK;
+}
 
 int dcma_b200_restrict_image(const dcma_b200_geom *fine, const float *image, dcma_b200_geom *coarse, float *out, int device,
                              char *errbuf, size_t errbuf_len) {

@@ -531,6 +531,12 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_M
                 CT ux, uy, uz, term;
                 int valid;
                 demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
+#if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
+                // feasibility probe only (tools/build_variant.py): what an fp32-stored update field would do to parity
+                ux = static_cast<CT>(static_cast<float>(ux));
+                uy = static_cast<CT>(static_cast<float>(uy));
+                uz = static_cast<CT>(static_cast<float>(uz));
+#endif
                 U[v] = ux;
                 U1[v] = uy;
                 U2[v] = uz;
@@ -838,6 +844,12 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
                 q[c][7] = (vz1 && vy1 && vx1) ? Uc[r11 + cx1] : T(0);
             }
         }
+#if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[c][i] = static_cast<CT>(static_cast<float>(q[c][i]));
+#endif
         // prefetch the next slice's displacement before consuming the gathers
         CT dn[3] = {CT(0), CT(0), CT(0)};
         if (z + 1 < z_end) {

@@ -22,6 +22,10 @@ class EngineBase {
     // ---- z-slab drivers only ----
     virtual void begin_run(int64_t max_iterations) = 0;                       // reset the loop state, allocate the history
     virtual void iter_stage(IterStage st, long long it, bool global_mse) = 0;  // enqueue one stage of iteration `it`
+    virtual void force_range(long long it, int z0, int z1) = 0;   // FORCE on owned slices [z0, z1) (local); no reduction
+    virtual void force_finish(long long it) = 0;                  // reduces the MSE partials of the force_range calls
+    virtual void update_range(long long it, int z0, int z1) = 0;  // diffeomorphic composition on owned slices [z0, z1)
+    virtual bool symmetric() const = 0;
     virtual void publish_mse(double *dev_out2) = 0;                           // (sum, count) of the last FORCE -> 2 doubles
     virtual void stop_rule(const double *dev_gather, int world, long long it) = 0;
     virtual void end_run(double *mse_history_host, dcma_b200_run_stats *stats) = 0;

@@ -129,8 +129,10 @@ class Engine final : public EngineBase {
         field_alloc_[0] = dD_;
         field_alloc_[1] = dU_;
         field_alloc_[2] = dTmp_;
-        d_part_sum_ = alloc<double>(grid_vox_);
-        d_part_cnt_ = alloc<long long>(grid_vox_);
+        // slack: a force stage split into up to kMaxForceParts z-ranges rounds each range up to whole z-chunks
+        part_cap_ = grid_vox_ + kMaxForceParts * static_cast<int>(per_plane);
+        d_part_sum_ = alloc<double>(part_cap_);
+        d_part_cnt_ = alloc<long long>(part_cap_);
         d_ctrl_ = alloc<Ctrl>(1);
         DCMA_CUDA(cudaMallocHost(&h_ctrl_, sizeof(Ctrl)));
 
@@ -308,6 +310,27 @@ class Engine final : public EngineBase {
                 break;
         }
     }
+    // ---- the per-voxel stages on a sub-range of the owned slices (slab.cu overlaps the halo exchange of the boundary
+    // planes with the interior).  FORCE: any number of force_range calls (disjoint ranges covering the owned slices),
+    // then force_finish, which reduces their MSE partials.  The symmetric force reads W with its neighbours and is
+    // not split.
+    void force_range(long long it, int z0, int z1) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        force_parts_ += launch_force(w_src_, it, d_hist_, it, 0, /*reduce=*/false, /*fused_reduce=*/false, z0, z1, force_parts_);
+    }
+    void force_finish(long long it) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        launch_reduce(it, d_hist_, it, /*count_iter=*/0, force_parts_);
+        force_parts_ = 0;
+    }
+    void update_range(long long it, int z0, int z1) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        if (p_.use_diffeomorphic != 0)
+            launch_compose(it, z0, z1);
+        else
+            throw std::logic_error("update_range is for the diffeomorphic composition");
+    }
+    bool symmetric() const override { return p_.use_symmetric_force != 0; }
     void publish_mse(double *dev_out2) override {
         DCMA_CUDA(cudaSetDevice(dev_));
         k_publish_mse<<<1, 32, 0, stream_>>>(d_ctrl_, dev_out2);
@@ -677,8 +700,10 @@ class Engine final : public EngineBase {
         rot_hist_[static_cast<size_t>(it)] = Rotation{dD_, dU_, dTmp_};
     }
 
-    void launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true,
-                      bool fused_reduce = false) {
+    // zr0/zr1 >= 0: only the owned slices [zr0, zr1) (local indices), MSE partials written from `part_off` on (the caller
+    // reduces all parts with launch_reduce(..., nparts)); returns the number of partials this launch wrote
+    int launch_force(int w_src, long long it, double *d_hist, long long hist_idx, int count_iter, bool reduce = true,
+                     bool fused_reduce = false, int zr0 = -1, int zr1 = -1, int part_off = 0) {
         if (w_src == 2) ensure_warped_buffer();
         ForceK fk;
         fk.norm_eps = p_.normalization_factor + 1.0e-10;  // cc:315
@@ -686,9 +711,21 @@ class Engine final : public EngineBase {
         fk.max_update = p_.max_update_magnitude;
         fk.mu2_lo = (fk.max_update >= 0.0) ? fk.max_update * fk.max_update * (1.0 - 8.881784197001252e-16) : -1.0;
         const dim3 blk(kTileX, kTileY);
+        Geo gq = g_;
+        dim3 grid = grid3_;
+        if (zr0 >= 0) {
+            gq.zb = zr0;
+            gq.ze = zr1;
+            grid.z = static_cast<unsigned>((zr1 - zr0 + zlen_ - 1) / zlen_);
+            if (zr1 <= zr0) return 0;
+        }
+        const int nparts = static_cast<int>(grid.x * grid.y * grid.z);
+        if (part_off + nparts > part_cap_) throw std::logic_error("force stage split into too many parts");
+        double *psum = d_part_sum_ + part_off;
+        long long *pcnt = d_part_cnt_ + part_off;
 #define DCMA_LAUNCH_FORCE2(IX, CH1, SYM)                                                                             \
-    k_warp_force<T, STRICT, IX, CH1, SYM><<<grid3_, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, g_, zlen_, w_src, fk, d_part_sum_, \
-                                                                       d_part_cnt_, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
+    k_warp_force<T, STRICT, IX, CH1, SYM><<<grid, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, gq, zlen_, w_src, fk, psum, \
+                                                                       pcnt, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
                                                                        hist_idx, count_iter)
 #define DCMA_LAUNCH_FORCE(IX, CH1)                            \
     do {                                                      \
@@ -707,10 +744,11 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
         if (reduce) launch_reduce(it, d_hist, hist_idx, count_iter && d_hist != nullptr ? 1 : 0);
+        return nparts;
     }
-    void launch_reduce(long long it, double *d_hist, long long hist_idx, int count_iter) {
-        k_reduce_final<<<1, 256, 0, stream_>>>(d_part_sum_, d_part_cnt_, grid_vox_, d_ctrl_, d_hist, it, hist_idx,
-                                               count_iter);
+    void launch_reduce(long long it, double *d_hist, long long hist_idx, int count_iter, int nparts = -1) {
+        k_reduce_final<<<1, 256, 0, stream_>>>(d_part_sum_, d_part_cnt_, nparts < 0 ? grid_vox_ : nparts, d_ctrl_, d_hist, it,
+                                               hist_idx, count_iter);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -719,11 +757,19 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
-    void launch_compose(long long it) {
+    void launch_compose(long long it, int zr0 = -1, int zr1 = -1) {
+        Geo gq = g_;
+        dim3 grid = grid3_;
+        if (zr0 >= 0) {
+            if (zr1 <= zr0) return;
+            gq.zb = zr0;
+            gq.ze = zr1;
+            grid.z = static_cast<unsigned>((zr1 - zr0 + zlen_ - 1) / zlen_);
+        }
         if (small_index_)
-            k_compose<T, STRICT, int><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, zlen_, d_ctrl_, it);
+            k_compose<T, STRICT, int><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
         else
-            k_compose<T, STRICT, long long><<<grid3_, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, g_, zlen_, d_ctrl_, it);
+            k_compose<T, STRICT, long long><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -979,7 +1025,9 @@ class Engine final : public EngineBase {
     dim3 grid3_;
     bool small_index_ = true;
     int zlen_ = 1;
-    int grid_vox_ = 1, grid_lin_ = 1;
+    int grid_vox_ = 1, grid_lin_ = 1, part_cap_ = 1;
+    static constexpr int kMaxForceParts = 4;
+    int force_parts_ = 0;  // partials written by the force_range calls of the current iteration
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
     T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;
     void *field_alloc_[3] = {nullptr, nullptr, nullptr};

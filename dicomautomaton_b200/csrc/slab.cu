@@ -13,6 +13,7 @@
 // Two transports: peer copies between engines of ONE process (any mix of devices; also the single-GPU test vehicle),
 // and NCCL send/recv + all-gather between processes (one rank per GPU, the bench/torchrun layout).  NCCL is loaded
 // with dlopen so that the library itself has no link-time dependency on it.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -98,6 +99,53 @@ NcclApi &nccl() {
     } while (0)
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ordering between ranks without NCCL launches: 32-bit counters in device memory, mapped into the neighbours through
+// CUDA IPC.  A rank RAISES a counter in its neighbour's memory with a one-thread kernel (a system-scope store after a
+// system fence; it runs in stream order, i.e. after the copies enqueued before it have landed) and WAITS for its own
+// counters with cuStreamWaitValue32 -- a front-end semaphore acquire, no SM is occupied and no kernel spins.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_raise_flags(unsigned *a, unsigned *b, unsigned value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        if (a) *reinterpret_cast<volatile unsigned *>(a) = value;
+        if (b) *reinterpret_cast<volatile unsigned *>(b) = value;
+        __threadfence_system();
+    }
+}
+// fallback when stream memory operations are not available: a one-thread kernel polling a counter that only a PEER
+// GPU (or a copy engine) raises, never a kernel of this device
+__global__ void k_wait_flag(const unsigned *f, unsigned value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        while (static_cast<int>(*reinterpret_cast<const volatile unsigned *>(f) - value) < 0) __nanosleep(200);
+        __threadfence_system();
+    }
+}
+using StreamWaitValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+        const char *off = std::getenv("DCMA_B200_SLAB_NO_MEMOPS");
+        if (off && *off == '1') return nullptr;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<StreamWaitValue32Fn>(p);
+    }();
+    return fn;
+}
+void wait_flag(cudaStream_t st, const unsigned *flag, unsigned value) {
+    if (StreamWaitValue32Fn fn = stream_wait_value32()) {
+        const CUresult r = fn(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(flag), value, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r == CUDA_SUCCESS) return;
+    }
+    k_wait_flag<<<1, 32, 0, st>>>(flag, value);
+    DCMA_CUDA(cudaGetLastError());
+}
+}  // namespace
+
 void nccl_unique_id(unsigned char id[128]) {
     ncclUniqueId u;
     DCMA_NCCL(nccl().GetUniqueId(&u));
@@ -108,6 +156,8 @@ void nccl_unique_id(unsigned char id[128]) {
 // ---------------------------------------------------------------------------------------------------------------
 // SlabGroup
 // ---------------------------------------------------------------------------------------------------------------
+static inline char *plane_ptr(EngineBase *e, int buffer, int c, int64_t l0);
+
 struct SlabGroup::Local {
     std::unique_ptr<EngineBase> eng;
     int rank = 0, device = 0;
@@ -133,6 +183,16 @@ SlabGroup::~SlabGroup() {
         if (peer_hi_[i]) cudaIpcCloseMemHandle(peer_hi_[i]);
     }
     cudaFree(d_token_);
+    if (peer_flags_lo_) cudaIpcCloseMemHandle(peer_flags_lo_);
+    if (peer_flags_hi_) cudaIpcCloseMemHandle(peer_flags_hi_);
+    cudaFree(d_flags_);
+    for (cudaEvent_t e : {ev_main_, ev_x_[0], ev_x_[1], ev_x_[2]})
+        if (e) cudaEventDestroy(e);
+    for (auto &pr : x_events_) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (comm_stream_) cudaStreamDestroy(comm_stream_);
     if (comm_) {
         try {
             nccl().CommDestroy(static_cast<ncclComm_t>(comm_));
@@ -146,8 +206,11 @@ int64_t SlabGroup::default_halo(const dcma_b200_geom &g, const dcma_b200_demons_
         return sigma > 0.0 ? std::max<int64_t>(1, static_cast<int64_t>(3.0 * sigma / g.pxl_dz)) : 0;  // cc:574-576
     };
     const int64_t r = std::max(rz(p.deformation_field_smoothing_sigma), p.use_diffeomorphic ? rz(p.update_field_smoothing_sigma) : 0);
-    // composition gathers reach ceil(|D_z| / pxl_dz) + 1 planes: 8 planes cover 7 voxels of z displacement
-    return std::max<int64_t>(r, p.use_diffeomorphic ? 8 : 1);
+    // composition gathers reach ceil(|D_z| / pxl_dz) + 1 planes beyond a slab edge: 4 planes cover |D_z| < 3 voxels (the
+    // per-iteration update is clamped to max_update_magnitude and the field is smoothed, so clinical fields stay well
+    // inside that).  A gather that does need a plane the slab does not hold raises Ctrl::halo_overflow and the run FAILS
+    // (never silent); the one-shot call then repeats the registration with a doubled halo.
+    return std::max<int64_t>(r, p.use_diffeomorphic ? 4 : 1);
 }
 
 void SlabGroup::add_local(const dcma_b200_geom &g, const dcma_b200_demons_params &p, int rank, int device) {
@@ -209,15 +272,17 @@ void SlabGroup::setup_ipc() {
     DCMA_CUDA(cudaSetDevice(l.device));
     cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
     struct Rec {
-        cudaIpcMemHandle_t h[3];
+        cudaIpcMemHandle_t h[4];  // the three field allocations + the flag block
         int ok;
         int pad[3];
     };
+    DCMA_CUDA(cudaMalloc(&d_flags_, 16 * sizeof(unsigned)));
+    DCMA_CUDA(cudaMemsetAsync(d_flags_, 0, 16 * sizeof(unsigned), st));
     Rec mine;
     std::memset(&mine, 0, sizeof(mine));
     mine.ok = 1;
-    for (int i = 0; i < 3; ++i)
-        if (cudaIpcGetMemHandle(&mine.h[i], e->field_allocation(i)) != cudaSuccess) {
+    for (int i = 0; i < 4; ++i)
+        if (cudaIpcGetMemHandle(&mine.h[i], i < 3 ? e->field_allocation(i) : static_cast<void *>(d_flags_)) != cudaSuccess) {
             cudaGetLastError();
             mine.ok = 0;
         }
@@ -233,15 +298,21 @@ void SlabGroup::setup_ipc() {
     DCMA_CUDA(cudaStreamSynchronize(st));
     int ok = 1;
     for (auto &r : all) ok &= r.ok;
-    auto open_peer = [&](int peer, void *out[3]) {
-        for (int i = 0; i < 3 && ok; ++i)
-            if (cudaIpcOpenMemHandle(&out[i], all[peer].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    auto open_peer = [&](int peer, void *out[3], unsigned **flags) {
+        for (int i = 0; i < 4 && ok; ++i) {
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[peer].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
+            } else if (i < 3) {
+                out[i] = ptr;
+            } else {
+                *flags = static_cast<unsigned *>(ptr);
             }
+        }
     };
-    if (ok && l.rank > 0) open_peer(l.rank - 1, peer_lo_);
-    if (ok && l.rank + 1 < world_) open_peer(l.rank + 1, peer_hi_);
+    if (ok && l.rank > 0) open_peer(l.rank - 1, peer_lo_, &peer_flags_lo_);
+    if (ok && l.rank + 1 < world_) open_peer(l.rank + 1, peer_hi_, &peer_flags_hi_);
     // every rank must take the same path: agree on the outcome
     mine.ok = ok;
     DCMA_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof(Rec), cudaMemcpyHostToDevice, st));
@@ -253,6 +324,67 @@ void SlabGroup::setup_ipc() {
     ipc_ok_ = (ok != 0);
     cudaFree(d_all);
     cudaFree(d_mine);
+    const char *tok = std::getenv("DCMA_B200_SLAB_NCCL_TOKENS");
+    flags_ok_ = ipc_ok_ && !(tok && *tok == '1');
+    if (flags_ok_) {
+        DCMA_CUDA(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+        DCMA_CUDA(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
+        for (auto &ev : ev_x_) DCMA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+}
+
+// One halo exchange of `n` planes of `buffer` with both z-neighbours on stream `st`, PUSH model:
+//   raise `arrived` in the neighbours  (everything enqueued on `st` before this point is done: nobody here still reads
+//                                       the halo planes the neighbours are about to overwrite)
+//   wait for the neighbours' `arrived`
+//   copy my boundary planes into the neighbours' halo planes (copy engines over NVLink, no SMs)
+//   raise `pushed` in the neighbours, wait for theirs: my halo planes are complete
+// Counter slots in MY flag block: 0/1 = arrived from the lower/upper neighbour, 2/3 = pushed from the lower/upper one.
+void SlabGroup::exchange_flags(int buffer, int64_t n, cudaStream_t st) {
+    Local &l = *locals_[0];
+    EngineBase *e = l.eng.get();
+    const SlabSpec s = e->slab();
+    const int64_t pe = e->plane_elems(), es = e->field_elem_size();
+    const size_t bytes = static_cast<size_t>(n) * pe * es;
+    const bool lo = (l.rank > 0), hi = (l.rank + 1 < world_);
+    DCMA_CUDA(cudaSetDevice(l.device));
+    int idx = -1;  // which of the three allocations currently plays `buffer` (the roles rotate identically on all ranks)
+    for (int i = 0; i < 3; ++i)
+        if (e->field_allocation(i) == e->field_base(buffer)) idx = i;
+    if (idx < 0) throw std::logic_error("field buffer is not one of the engine's allocations");
+    const unsigned id = ++xid_;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (x_events_.size() < 4096) {
+        DCMA_CUDA(cudaEventCreate(&t0));
+        DCMA_CUDA(cudaEventCreate(&t1));
+        DCMA_CUDA(cudaEventRecord(t0, st));
+    }
+    k_raise_flags<<<1, 32, 0, st>>>(lo ? peer_flags_lo_ + 1 : nullptr, hi ? peer_flags_hi_ + 0 : nullptr, id);
+    DCMA_CUDA(cudaGetLastError());
+    if (lo) wait_flag(st, d_flags_ + 0, id);
+    if (hi) wait_flag(st, d_flags_ + 1, id);
+    if (lo) {  // my first owned planes -> the lower neighbour's upper halo
+        const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank - 1, halo_);
+        for (int c = 0; c < 3; ++c)
+            DCMA_CUDA(cudaMemcpyAsync(static_cast<char *>(peer_lo_[idx]) + (c * p.local * pe + p.own1 * pe) * es,
+                                      plane_ptr(e, buffer, c, s.own0), bytes, cudaMemcpyDefault, st));
+    }
+    if (hi) {  // my last owned planes -> the upper neighbour's lower halo
+        const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank + 1, halo_);
+        for (int c = 0; c < 3; ++c)
+            DCMA_CUDA(cudaMemcpyAsync(static_cast<char *>(peer_hi_[idx]) + (c * p.local * pe + (p.own0 - n) * pe) * es,
+                                      plane_ptr(e, buffer, c, s.own1 - n), bytes, cudaMemcpyDefault, st));
+    }
+    k_raise_flags<<<1, 32, 0, st>>>(lo ? peer_flags_lo_ + 3 : nullptr, hi ? peer_flags_hi_ + 2 : nullptr, id);
+    DCMA_CUDA(cudaGetLastError());
+    if (lo) wait_flag(st, d_flags_ + 2, id);
+    if (hi) wait_flag(st, d_flags_ + 3, id);
+    if (t0) {
+        DCMA_CUDA(cudaEventRecord(t1, st));
+        x_events_.emplace_back(t0, t1);
+    }
+    halo_bytes_ += 3 * bytes * ((lo ? 1 : 0) + (hi ? 1 : 0));
+    ++exchanges_;
 }
 
 // A 4-byte send/recv with each z-neighbour in stream order: when it completes on this stream, the neighbours' streams
@@ -287,6 +419,10 @@ static inline char *plane_ptr(EngineBase *e, int buffer, int c, int64_t l0) {
 void SlabGroup::exchange(int buffer, int64_t n) {
     if (world_ == 1 || n <= 0) return;
     if (n > halo_) throw std::logic_error("exchange wider than the halo");
+    if (comm_ && flags_ok_) {
+        exchange_flags(buffer, n, static_cast<cudaStream_t>(locals_[0]->eng->stream_handle()));
+        return;
+    }
     if (comm_ && ipc_ok_) {
         // ---- NVLink copy engines: PULL the neighbours' boundary planes out of their (IPC-mapped) field buffers into my
         // halo.  The tokens order the streams: before -- the neighbours have produced the planes; after -- they may
@@ -440,7 +576,78 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
             DCMA_CUDA(cudaMalloc(&l->d_mse_hist, 2 * sizeof(double) * max_iterations));
         }
     }
+    // Overlapped schedule (one rank per process, flag transport, diffeomorphic): the per-voxel stages are split so that
+    // the planes a neighbour needs are produced first and travel (copy engines, second stream) under the rest:
+    //   FORCE   : boundary planes, then  [push U, r_z planes]  ||  interior
+    //   SMOOTH U: whole (needs the U halo)
+    //   COMPOSE : [push U~, halo planes] || interior part 1;  boundary planes (need the U~ halo);
+    //             [push D, r_z planes]   || interior part 2
+    //   SMOOTH D: whole (needs the D halo)
+    // Splitting a per-voxel kernel by z-range costs nothing; the smoothing kernels are not split (each extra start of a
+    // z march would re-stage 2 r_z slices).
+    const char *no_ov = std::getenv("DCMA_B200_SLAB_NO_OVERLAP");
+    EngineBase *e = e0;
+    const SlabSpec sp = e->slab();
+    const int own0 = static_cast<int>(sp.own0), own1 = static_cast<int>(sp.own1), H = static_cast<int>(halo_);
+    const bool overlap = comm_ && flags_ok_ && world_ > 1 && diffeo && !e->symmetric() && !(no_ov && *no_ov == '1') &&
+                         (own1 - own0) >= 4 * H + 4 && rz_u <= H && rz_d <= H;
+    overlapped_ = overlap;
+    exchanges_ = 0;
+    for (auto &pr : x_events_) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    x_events_.clear();
+    cudaStream_t s_main = static_cast<cudaStream_t>(e->stream_handle());
     for (int64_t it = 0; it < max_iterations; ++it) {
+        if (overlap) {
+            DCMA_CUDA(cudaSetDevice(locals_[0]->device));
+            const int ru = static_cast<int>(rz_u), rd = static_cast<int>(rz_d);
+            // ---- FORCE
+            if (ru > 0) {
+                e->force_range(it, own0, own0 + ru);
+                e->force_range(it, own1 - ru, own1);
+                DCMA_CUDA(cudaEventRecord(ev_main_, s_main));
+                DCMA_CUDA(cudaStreamWaitEvent(comm_stream_, ev_main_, 0));
+                exchange_flags(DCMA_B200_BUF_UPDATE, ru, comm_stream_);
+                DCMA_CUDA(cudaEventRecord(ev_x_[0], comm_stream_));
+                e->force_range(it, own0 + ru, own1 - ru);
+                e->force_finish(it);
+            } else {
+                e->iter_stage(IterStage::Force, it, true);
+            }
+            if (can_converge) {
+                gather_mse_and_stop_rule(it);
+            } else {
+                e->publish_mse(locals_[0]->d_mse_hist + 2 * it);
+                e->stop_rule(locals_[0]->d_mse_hist + 2 * it, 1, it);
+            }
+            if (ru > 0) {
+                DCMA_CUDA(cudaStreamWaitEvent(s_main, ev_x_[0], 0));
+                e->iter_stage(IterStage::SmoothU, it, true);
+            }
+            // ---- COMPOSE
+            DCMA_CUDA(cudaEventRecord(ev_main_, s_main));
+            DCMA_CUDA(cudaStreamWaitEvent(comm_stream_, ev_main_, 0));
+            exchange_flags(DCMA_B200_BUF_UPDATE, H, comm_stream_);
+            DCMA_CUDA(cudaEventRecord(ev_x_[1], comm_stream_));
+            const int mid = (own0 + own1) / 2;
+            e->update_range(it, own0 + H, mid);
+            DCMA_CUDA(cudaStreamWaitEvent(s_main, ev_x_[1], 0));
+            e->update_range(it, own0, own0 + H);
+            e->update_range(it, own1 - H, own1);
+            if (rd > 0) {
+                DCMA_CUDA(cudaEventRecord(ev_main_, s_main));
+                DCMA_CUDA(cudaStreamWaitEvent(comm_stream_, ev_main_, 0));
+                exchange_flags(DCMA_B200_BUF_DEFORMATION, rd, comm_stream_);
+                DCMA_CUDA(cudaEventRecord(ev_x_[2], comm_stream_));
+            }
+            e->update_range(it, mid, own1 - H);
+            if (rd > 0) DCMA_CUDA(cudaStreamWaitEvent(s_main, ev_x_[2], 0));
+            e->iter_stage(IterStage::SmoothD, it, true);
+            if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations) && e0->converged_poll()) break;
+            continue;
+        }
         for (auto &l : locals_) l->eng->iter_stage(IterStage::Force, it, /*global_mse=*/true);
         if (can_converge) {
             gather_mse_and_stop_rule(it);
@@ -460,6 +667,7 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
         for (auto &l : locals_) l->eng->iter_stage(IterStage::SmoothD, it, true);
         if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations) && e0->converged_poll()) break;
     }
+    if (comm_stream_) DCMA_CUDA(cudaStreamSynchronize(comm_stream_));
     dcma_b200_run_stats st0;
     bool first = true;
     for (auto &l : locals_) {
@@ -473,6 +681,13 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
         }
         first = false;
     }
+    exchange_ms_ = 0.0;
+    for (auto &pr : x_events_) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) exchange_ms_ += t;
+    }
+    if (x_events_.size() < static_cast<size_t>(exchanges_) && !x_events_.empty())
+        exchange_ms_ *= static_cast<double>(exchanges_) / static_cast<double>(x_events_.size());  // sampled
     if (stats) *stats = st0;
     if (!can_converge && mse_history_host && st0.iterations_done > 0) {
         // global MSE history: sum the slabs' terms in rank order (the order of k_stop_rule)

@@ -1,7 +1,10 @@
 // dcma_b200 -- z-slab group: one registration sharded over several engines (see slab.cu).
 #pragma once
 #include <cstdint>
+#include <cuda_runtime.h>
+
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "engine.h"
@@ -27,6 +30,11 @@ class SlabGroup {
     int64_t device_bytes() const;
     int64_t halo() const { return halo_; }
     int64_t halo_bytes_last_run() const { return halo_bytes_; }
+    double exchange_ms_last_run() const { return exchange_ms_; }    // device time inside the exchanges (all of them)
+    int64_t exchanges_last_run() const { return exchanges_; }
+    bool overlapped_last_run() const { return overlapped_; }
+    // 0: in-process peer copies + events, 1: NCCL send/recv, 2: IPC pull + NCCL tokens, 3: IPC push + flag counters
+    int transport() const { return !comm_ ? 0 : (flags_ok_ ? 3 : (ipc_ok_ ? 2 : 1)); }
     static int64_t default_halo(const dcma_b200_geom &g, const dcma_b200_demons_params &p);
 
   private:
@@ -47,6 +55,16 @@ class SlabGroup {
     bool ipc_ok_ = false;
     void *peer_lo_[3] = {nullptr, nullptr, nullptr}, *peer_hi_[3] = {nullptr, nullptr, nullptr};
     int *d_token_ = nullptr;
+    // flag transport: counters raised by the neighbours in my flag block, waited for with stream memory operations
+    void exchange_flags(int buffer, int64_t planes, cudaStream_t st);
+    bool flags_ok_ = false, overlapped_ = false;
+    unsigned *d_flags_ = nullptr, *peer_flags_lo_ = nullptr, *peer_flags_hi_ = nullptr;
+    unsigned xid_ = 0;
+    cudaStream_t comm_stream_ = nullptr;
+    cudaEvent_t ev_main_ = nullptr, ev_x_[3] = {nullptr, nullptr, nullptr};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> x_events_;
+    double exchange_ms_ = 0.0;
+    int64_t exchanges_ = 0;
     std::vector<std::unique_ptr<Local>> locals_;
 };
 

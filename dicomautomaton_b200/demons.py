@@ -405,6 +405,17 @@ class DemonsSlabGroup:
     def halo_bytes(self) -> int:
         return int(self._lib.dcma_b200_slab_group_halo_bytes(self._h))
 
+    TRANSPORTS = {0: "in-process peer copies + events", 1: "NCCL send/recv", 2: "IPC pull (copy engines) + NCCL tokens",
+                  3: "IPC push (copy engines) + flag counters (stream memory operations)"}
+
+    def exchange_stats(self) -> dict:
+        """Halo-exchange statistics of this process's last run (see dcma_b200_slab_group_exchange_stats)."""
+        ms, n, ov, tr, hp = C.c_double(0), C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        capi.check(self._lib.dcma_b200_slab_group_exchange_stats(self._h, C.byref(ms), C.byref(n), C.byref(ov), C.byref(tr),
+                                                                 C.byref(hp)))
+        return {"exchange_ms": float(ms.value), "exchanges": int(n.value), "overlapped": bool(ov.value),
+                "transport": self.TRANSPORTS.get(int(tr.value), str(tr.value)), "halo_planes": int(hp.value)}
+
 
 def AlignViaDemons(params: AlignViaDemonsParams, moving: demons_volume, stationary: demons_volume,
                    return_stats: bool = False):

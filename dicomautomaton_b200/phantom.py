@@ -139,21 +139,24 @@ def _phantom_hu_exact(x, y, z, shape):
     nz, ny, nx = (float(v) for v in shape)
     cx, cy, cz = (nx - 1.0) / 2.0, (ny - 1.0) / 2.0, (nz - 1.0) / 2.0
     small = min(nx, ny, nz)
-    ex, ey, ez = (x - cx) / (0.40 * nx), (y - cy) / (0.32 * ny), (z - cz) / (0.45 * nz)
+    # NB: never `tensor / python_scalar` here -- torch's CUDA kernel multiplies by the rounded reciprocal while the CPU
+    # kernel divides, a 1-ulp difference that flips a float32 rounding once in ~1e8 voxels.  Multiply by a reciprocal
+    # computed once in Python instead (the same double on every device).
+    ex, ey, ez = (x - cx) * (1.0 / (0.40 * nx)), (y - cy) * (1.0 / (0.32 * ny)), (z - cz) * (1.0 / (0.45 * nz))
     e = torch.sqrt(ex * ex + ey * ey + ez * ez)
-    u = (1.0 - e) / 0.06
+    u = (1.0 - e) * (1.0 / 0.06)
     body = (u / torch.sqrt(u * u + 1.0)) * 0.5 + 0.5  # algebraic sigmoid
     hu = body * 1000.0 - 1000.0
 
     def blob(amp, fx, fy, fz, s):
         bx, by, bz = cx + fx * nx, cy + fy * ny, cz + fz * nz
         dx, dy, dz = x - bx, y - by, z - bz
-        return _bump_exact((dx * dx + dy * dy + dz * dz) / ((s * small) ** 2)) * amp
+        return _bump_exact((dx * dx + dy * dy + dz * dz) * (1.0 / ((s * small) ** 2))) * amp
 
     hu = hu + body * blob(300.0, 0.15, -0.05, 0.10, 0.08)
     hu = hu + body * blob(-700.0, -0.15, 0.08, -0.12, 0.07)
     rx, ry = x - cx, y - (cy + 0.18 * ny)
-    hu = hu + body * (_bump_exact((rx * rx + ry * ry) / ((0.03 * small) ** 2)) * 900.0)
+    hu = hu + body * (_bump_exact((rx * rx + ry * ry) * (1.0 / ((0.03 * small) ** 2))) * 900.0)
     tex = _sin_exact(x * 0.9 + y * 0.3) + _sin_exact(y * 0.7 + z * 0.4) + _sin_exact(z * 0.8 + x * 0.5)
     return hu + tex * 20.0
 
@@ -182,6 +185,6 @@ def make_pair_exact(shape, spacing=(1.0, 1.0, 1.0), amplitude_mm: float = 2.0, d
         wx, wy, wz = known_warp_mm_exact(x, y, z, shape, amplitude_mm)
         if nz == 1:
             wz = wz * 0.0
-        moving[a:b] = _phantom_hu_exact(x + wx / spacing[0], y + wy / spacing[1], z + wz / spacing[2],
-                                        shape).to(torch.float32)
+        moving[a:b] = _phantom_hu_exact(x + wx * (1.0 / spacing[0]), y + wy * (1.0 / spacing[1]),
+                                        z + wz * (1.0 / spacing[2]), shape).to(torch.float32)
     return fixed, moving

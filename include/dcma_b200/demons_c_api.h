@@ -201,6 +201,12 @@ DCMA_B200_API int dcma_b200_slab_group_run(dcma_b200_slab_group *g, int64_t max_
 DCMA_B200_API int dcma_b200_slab_group_range(dcma_b200_slab_group *g, int64_t *z0, int64_t *z1);
 DCMA_B200_API int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deformation_out);
 DCMA_B200_API int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g); /* bytes exchanged by the last run */
+/* Exchange statistics of the last run of THIS process: device time spent inside halo exchanges (ms, all of them summed;
+ * with `overlapped` != 0 they ran on a second stream under the interior kernels), their number, the halo width in planes
+ * and the transport (0 in-process peer copies, 1 NCCL send/recv, 2 IPC pull + NCCL tokens, 3 IPC push + flag counters).
+ * Any pointer may be NULL.  No reference counterpart (the reference has one address space, src/Alignment_Demons.cc:171-187). */
+DCMA_B200_API int dcma_b200_slab_group_exchange_stats(const dcma_b200_slab_group *g, double *exchange_ms, int64_t *exchanges,
+                                                      int32_t *overlapped, int32_t *transport, int64_t *halo_planes);
 
 /* ---- pyramid building blocks (extension; host buffers) ------------------------------------------------------- */
 /* Next-coarser level of `image`: every axis with extent >= 8 is halved (mean of the finite voxels of each block).
