@@ -122,6 +122,55 @@ __global__ void k_wait_flag(const unsigned *f, unsigned value) {
         __threadfence_system();
     }
 }
+// Small exchanges are latency-bound (two flag kernels + six copy-engine launches cost more than the bytes): ONE kernel does
+// the whole producer side -- raise `arrived` in the neighbours, wait for theirs (a counter only a PEER GPU raises), store
+// my boundary planes straight into the neighbours' halo planes over NVLink (16-byte stores), and the last block to
+// finish raises `pushed`.
+struct PushSeg {
+    const uint4 *src;
+    uint4 *dst;
+    long long n16;  // 16-byte units
+};
+struct PushArgs {
+    PushSeg seg[6];
+    int nseg;
+    unsigned *peer_arrived[2], *peer_pushed[2];  // counters in the neighbours' flag blocks (null: no such neighbour)
+    const unsigned *my_arrived[2];                // counters in my flag block
+    unsigned *ticket;                             // in my flag block
+    unsigned id;
+};
+__global__ void __launch_bounds__(256) k_push_halo(const PushArgs a) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int i = 0; i < 2; ++i)
+                if (a.peer_arrived[i]) *reinterpret_cast<volatile unsigned *>(a.peer_arrived[i]) = a.id;
+        }
+        for (int i = 0; i < 2; ++i)
+            if (a.my_arrived[i])
+                while (static_cast<int>(*reinterpret_cast<const volatile unsigned *>(a.my_arrived[i]) - a.id) < 0) __nanosleep(100);
+        __threadfence_system();
+    }
+    __syncthreads();
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (int sg = 0; sg < a.nseg; ++sg) {
+        const uint4 *__restrict__ src = a.seg[sg].src;
+        uint4 *__restrict__ dst = a.seg[sg].dst;
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.seg[sg].n16; i += stride) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *a.ticket = 0;
+            __threadfence_system();
+            for (int i = 0; i < 2; ++i)
+                if (a.peer_pushed[i]) *reinterpret_cast<volatile unsigned *>(a.peer_pushed[i]) = a.id;
+            __threadfence_system();
+        }
+    }
+}
 using StreamWaitValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 StreamWaitValue32Fn stream_wait_value32() {
     static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
@@ -327,7 +376,12 @@ void SlabGroup::setup_ipc() {
     const char *tok = std::getenv("DCMA_B200_SLAB_NCCL_TOKENS");
     flags_ok_ = ipc_ok_ && !(tok && *tok == '1');
     if (flags_ok_) {
-        DCMA_CUDA(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+        // HIGH priority: the block scheduler serves a kernel of another stream only after every block of the kernels
+        // launched before it has been issued -- unless its stream has priority.  Without it the one-thread flag kernels of
+        // an exchange sit behind the whole interior kernel they are meant to run under (measured: no overlap at all).
+        int prio_lo = 0, prio_hi = 0;
+        DCMA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DCMA_CUDA(cudaStreamCreateWithPriority(&comm_stream_, cudaStreamNonBlocking, prio_hi));
         DCMA_CUDA(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
         for (auto &ev : ev_x_) DCMA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
@@ -358,6 +412,52 @@ void SlabGroup::exchange_flags(int buffer, int64_t n, cudaStream_t st) {
         DCMA_CUDA(cudaEventCreate(&t0));
         DCMA_CUDA(cudaEventCreate(&t1));
         DCMA_CUDA(cudaEventRecord(t0, st));
+    }
+    static const long long kernel_push_max = []() {
+        const char *v = std::getenv("DCMA_B200_SLAB_KERNEL_PUSH_MAX_MB");
+        return (v && *v) ? std::atoll(v) * (1LL << 20) : 48LL * (1LL << 20);
+    }();
+    if (static_cast<long long>(3 * bytes) <= kernel_push_max && bytes % 16 == 0 && (pe * es) % 16 == 0) {
+        PushArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.id = id;
+        a.ticket = d_flags_ + 8;
+        if (lo) {
+            const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank - 1, halo_);
+            for (int c = 0; c < 3; ++c) {
+                PushSeg &sg = a.seg[a.nseg++];
+                sg.src = reinterpret_cast<const uint4 *>(plane_ptr(e, buffer, c, s.own0));
+                sg.dst = reinterpret_cast<uint4 *>(static_cast<char *>(peer_lo_[idx]) + (c * p.local * pe + p.own1 * pe) * es);
+                sg.n16 = static_cast<long long>(bytes / 16);
+            }
+            a.peer_arrived[0] = peer_flags_lo_ + 1;
+            a.peer_pushed[0] = peer_flags_lo_ + 3;
+            a.my_arrived[0] = d_flags_ + 0;
+        }
+        if (hi) {
+            const SlabSpec p = slab_for_rank(geom_.slices, world_, l.rank + 1, halo_);
+            for (int c = 0; c < 3; ++c) {
+                PushSeg &sg = a.seg[a.nseg++];
+                sg.src = reinterpret_cast<const uint4 *>(plane_ptr(e, buffer, c, s.own1 - n));
+                sg.dst = reinterpret_cast<uint4 *>(static_cast<char *>(peer_hi_[idx]) + (c * p.local * pe + (p.own0 - n) * pe) * es);
+                sg.n16 = static_cast<long long>(bytes / 16);
+            }
+            a.peer_arrived[1] = peer_flags_hi_ + 0;
+            a.peer_pushed[1] = peer_flags_hi_ + 2;
+            a.my_arrived[1] = d_flags_ + 1;
+        }
+        const int nblk = static_cast<int>(std::max<long long>(1, std::min<long long>(32, (static_cast<long long>(a.nseg) * a.seg[0].n16 + 2047) / 2048)));
+        k_push_halo<<<nblk, 256, 0, st>>>(a);
+        DCMA_CUDA(cudaGetLastError());
+        if (lo) wait_flag(st, d_flags_ + 2, id);
+        if (hi) wait_flag(st, d_flags_ + 3, id);
+        if (t0) {
+            DCMA_CUDA(cudaEventRecord(t1, st));
+            x_events_.emplace_back(t0, t1);
+        }
+        halo_bytes_ += 3 * bytes * ((lo ? 1 : 0) + (hi ? 1 : 0));
+        ++exchanges_;
+        return;
     }
     k_raise_flags<<<1, 32, 0, st>>>(lo ? peer_flags_lo_ + 1 : nullptr, hi ? peer_flags_hi_ + 0 : nullptr, id);
     DCMA_CUDA(cudaGetLastError());

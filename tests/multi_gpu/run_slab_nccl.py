@@ -47,12 +47,14 @@ def main():
         z0, z1 = grp.owned_range()
         Ds = grp.get_deformation()
         hb = grp.halo_bytes
+        xs = grp.exchange_stats()
         grp.close()
         whole, hw, _ = AlignViaDemons(par, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
         same = np.array_equal(whole.data[z0:z1], Ds)
         mse_rel = float(np.max(np.abs(hist - hw) / hw))
         print(f"[rank {rank}/{world}] diffeo={diffeo} slices [{z0},{z1}) iters={st.iterations_done} loop_ms={st.loop_ms:.2f} "
-              f"halo_bytes={hb} bit_identical={same} mse_rel={mse_rel:.2e}", flush=True)
+              f"halo_bytes={hb} bit_identical={same} mse_rel={mse_rel:.2e} overlapped={xs['overlapped']} "
+              f"exchange_ms={xs['exchange_ms']:.2f} transport='{xs['transport']}'", flush=True)
         ok = ok and same and mse_rel < 1e-12 and st.iterations_done == a.iters
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
