@@ -91,6 +91,8 @@ SYMBOLS = {
     "dcma_b200_slab_group_run": (C.c_int, [_vp, C.c_int64, _vp, C.POINTER(RunStats)]),
     "dcma_b200_slab_group_range": (C.c_int, [_vp, _ip, _ip]),
     "dcma_b200_slab_group_get_deformation": (C.c_int, [_vp, _vp]),
+    "dcma_b200_host_alloc": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
+    "dcma_b200_host_free": (None, [_vp]),
     "dcma_b200_slab_group_halo_bytes": (C.c_int64, [_vp]),
     "dcma_b200_slab_group_exchange_stats": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
 }

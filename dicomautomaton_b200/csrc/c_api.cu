@@ -339,6 +339,25 @@ int dcma_b200_slab_group_get_deformation(dcma_b200_slab_group *g, double *deform
     return guarded([&]() { g->impl->get_deformation(deformation_out); });
 }
 
+int dcma_b200_host_alloc(void **out, size_t bytes, char *errbuf, size_t errbuf_len) {
+    if (!out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    *out = nullptr;
+    return guarded(
+        [&]() {
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+                throw dcma::CudaError(cudaErrorNoDevice, "no CUDA device is available (dcma_b200 has no CPU fallback)");
+            void *p = nullptr;
+            DCMA_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable));
+            *out = p;
+        },
+        errbuf, errbuf_len);
+}
+
+void dcma_b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int64_t dcma_b200_slab_group_halo_bytes(const dcma_b200_slab_group *g) { return g ? g->impl->halo_bytes_last_run() : 0; }
 
 int dcma_b200_slab_group_exchange_stats(const dcma_b200_slab_group *g, double *exchange_ms, int64_t *exchanges, int32_t *overlapped,

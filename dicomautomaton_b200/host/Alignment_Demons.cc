@@ -13,17 +13,249 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "dcma_b200/demons_c_api.h"
 
 using namespace AlignViaDemonsHelpers;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host-side plumbing of the drop-in: dense volumes live in PINNED host memory (dcma_b200_host_alloc; kept in a small
+// process-lifetime pool, because page-locking 1.6 GB costs about as much as it saves on one transfer), and the copies
+// between image stacks and dense volumes run slice-parallel on the host threads.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+unsigned worker_count() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(16u, hw ? hw : 4u));
+}
+template <class F>
+void parallel_for(int64_t n, F f) {
+    const unsigned nt = static_cast<unsigned>(std::min<int64_t>(worker_count(), n));
+    if (nt <= 1) {
+        for (int64_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex mu;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() {
+            try {
+                for (int64_t i = t; i < n; i += nt) f(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!err) err = std::current_exception();
+            }
+        });
+    for (auto &x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
+
+// pinned host buffers, reused across registrations of this process
+class PinnedPool {
+    struct Buf {
+        void *p;
+        size_t bytes;
+        bool busy;
+    };
+    std::vector<Buf> bufs_;
+    std::mutex mu_;
+
+  public:
+    ~PinnedPool() {
+        for (auto &b : bufs_) dcma_b200_host_free(b.p);
+    }
+    void *acquire(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu_);
+        Buf *best = nullptr;
+        for (auto &b : bufs_)
+            if (!b.busy && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+        if (best) {
+            best->busy = true;
+            return best->p;
+        }
+        void *p = nullptr;
+        char err[256] = {0};
+        if (dcma_b200_host_alloc(&p, bytes, err, sizeof err) != DCMA_B200_OK) throw std::runtime_error(std::string("dcma_b200: ") + err);
+        bufs_.push_back(Buf{p, bytes, true});
+        return p;
+    }
+    void release(void *p) {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto &b : bufs_)
+            if (b.p == p) b.busy = false;
+    }
+};
+PinnedPool &pool() {
+    static PinnedPool p;
+    return p;
+}
+template <class T>
+class Pinned {  // RAII lease of a pooled pinned buffer of n elements
+    T *p_ = nullptr;
+    size_t n_ = 0;
+
+  public:
+    Pinned() = default;
+    explicit Pinned(size_t n) : p_(static_cast<T *>(pool().acquire(std::max<size_t>(n, 1) * sizeof(T)))), n_(n) {}
+    Pinned(const Pinned &) = delete;
+    Pinned &operator=(const Pinned &) = delete;
+    Pinned(Pinned &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; }
+    Pinned &operator=(Pinned &&o) noexcept {
+        if (this != &o) {
+            if (p_) pool().release(p_);
+            p_ = o.p_;
+            n_ = o.n_;
+            o.p_ = nullptr;
+        }
+        return *this;
+    }
+    ~Pinned() {
+        if (p_) pool().release(p_);
+    }
+    T *data() const { return p_; }
+    size_t size() const { return n_; }
+};
+
+// The regular grid a stack occupies, slice index = LIST order (the order marshal_collection_to_volume uses,
+// reference Alignment_Demons.h:139-180).  false: not a regular stack, or not equally spaced in list order.
+template <class T>
+bool grid_of(const planar_image_collection<T, double> &coll, dcma_b200_grid &g) {
+    if (coll.images.empty()) return false;
+    auto &nc = const_cast<planar_image_collection<T, double> &>(coll);
+    std::list<std::reference_wrapper<planar_image<T, double>>> refs;
+    for (auto &img : nc.images) refs.push_back(std::ref(img));
+    if (!Images_Form_Regular_Grid(refs)) return false;
+    const auto &a = coll.images.front();
+    for (const auto &img : coll.images)
+        if (img.rows != a.rows || img.columns != a.columns || img.channels != a.channels) return false;
+    const auto o = a.position(0, 0);
+    auto ez = a.ortho_unit();
+    const int64_t n = static_cast<int64_t>(coll.images.size());
+    double dz = a.pxl_dz;
+    if (n > 1) {
+        const auto step = std::next(coll.images.begin())->position(0, 0) - o;
+        const double len = step.length();
+        if (!(len > 0.0)) return false;
+        if (step.Dot(ez) < 0.0) ez = ez * -1.0;  // the list runs against ortho_unit: slices still ascend along ez
+        dz = len;
+        int64_t i = 0;
+        for (const auto &img : coll.images) {
+            const auto d = img.position(0, 0) - (o + ez * (dz * static_cast<double>(i)));
+            if (d.length() > 1e-6 * std::max(1.0, dz) * 100.0) return false;
+            ++i;
+        }
+    }
+    g.geom.slices = n;
+    g.geom.rows = a.rows;
+    g.geom.cols = a.columns;
+    g.geom.channels = a.channels;
+    g.geom.pxl_dx = a.pxl_dx;
+    g.geom.pxl_dy = a.pxl_dy;
+    g.geom.pxl_dz = dz;
+    const auto ex = a.row_unit.unit(), ey = a.col_unit.unit();
+    g.origin[0] = o.x; g.origin[1] = o.y; g.origin[2] = o.z;
+    g.ex[0] = ex.x; g.ex[1] = ex.y; g.ex[2] = ex.z;
+    g.ey[0] = ey.x; g.ey[1] = ey.y; g.ey[2] = ey.z;
+    g.ez[0] = ez.x; g.ez[1] = ez.y; g.ez[2] = ez.z;
+    return true;
+}
+
+// image stack -> dense [z][y][x][c] at dst (slice-parallel; memcpy when the image's own layout is that layout)
+template <class T>
+void marshal_into(const planar_image_collection<T, double> &coll, T *dst) {
+    const auto &a = coll.images.front();
+    const int64_t R = a.rows, C = a.columns, CH = a.channels;
+    std::vector<const planar_image<T, double> *> imgs;
+    for (const auto &img : coll.images) {
+        if (img.rows != R || img.columns != C || img.channels != CH)
+            throw std::invalid_argument("Image collection has inconsistent rows/columns/channels and cannot be marshaled as a rectilinear volume");
+        imgs.push_back(&img);
+    }
+    const bool dense_layout = (a.index(0, 0, 0) == 0) && (CH == 1 || a.index(0, 0, 1) == 1) && (C == 1 || a.index(0, 1, 0) == CH) &&
+                              (R == 1 || a.index(1, 0, 0) == C * CH);
+    const size_t per = static_cast<size_t>(R * C * CH);
+    parallel_for(static_cast<int64_t>(imgs.size()), [&](int64_t z) {
+        const auto &img = *imgs[static_cast<size_t>(z)];
+        T *d = dst + static_cast<size_t>(z) * per;
+        if (dense_layout && img.data.size() == per) {
+            std::memcpy(d, img.data.data(), per * sizeof(T));
+        } else {
+            for (int64_t y = 0; y < R; ++y)
+                for (int64_t x = 0; x < C; ++x)
+                    for (int64_t c = 0; c < CH; ++c) d[(y * C + x) * CH + c] = img.value(y, x, c);
+        }
+    });
+}
+
+// dense [z][y][x][c] -> one image per slice with the geometry and metadata of the matching slice of `geometry`
+// (marshal_volume_to_collection, reference Alignment_Demons.h:182-204), slice-parallel
+template <class T, class G>
+planar_image_collection<T, double> collection_from_dense(const T *src, int64_t slices, int64_t R, int64_t C, int64_t CH,
+                                                         const planar_image_collection<G, double> &geometry) {
+    if (static_cast<int64_t>(geometry.images.size()) < slices)
+        throw std::runtime_error("Requested image index not present, unable to continue");
+    planar_image_collection<T, double> out;
+    std::vector<planar_image<T, double> *> imgs;
+    std::vector<const planar_image<G, double> *> refs;
+    auto it = geometry.images.begin();
+    for (int64_t z = 0; z < slices; ++z, ++it) {
+        out.images.emplace_back();
+        imgs.push_back(&out.images.back());
+        refs.push_back(&*it);
+    }
+    const size_t per = static_cast<size_t>(R * C * CH);
+    parallel_for(slices, [&](int64_t z) {
+        auto &img = *imgs[static_cast<size_t>(z)];
+        const auto &ref = *refs[static_cast<size_t>(z)];
+        img.init_orientation(ref.row_unit, ref.col_unit);
+        img.init_buffer(R, C, CH);
+        img.init_spatial(ref.pxl_dx, ref.pxl_dy, ref.pxl_dz, ref.anchor, ref.offset);
+        img.metadata = ref.metadata;
+        const T *s = src + static_cast<size_t>(z) * per;
+        const bool dense_layout = (img.index(0, 0, 0) == 0) && (CH == 1 || img.index(0, 0, 1) == 1) &&
+                                  (C == 1 || img.index(0, 1, 0) == CH) && (R == 1 || img.index(1, 0, 0) == C * CH);
+        if (dense_layout && img.data.size() == per) {
+            std::memcpy(img.data.data(), s, per * sizeof(T));
+        } else {
+            for (int64_t y = 0; y < R; ++y)
+                for (int64_t x = 0; x < C; ++x)
+                    for (int64_t c = 0; c < CH; ++c) img.reference(y, x, c) = s[(y * C + x) * CH + c];
+        }
+    });
+    return out;
+}
+
+void check_rc(int rc, const char *err) {
+    if (rc != DCMA_B200_OK) throw std::runtime_error(std::string("dcma_b200: ") + err);
+}
+
+}  // namespace
 
 planar_image_collection<float, double> AlignViaDemonsHelpers::resample_image_to_reference_grid(
     const planar_image_collection<float, double> &moving, const planar_image_collection<float, double> &reference) {
     if (moving.images.empty() || reference.images.empty())
         throw std::invalid_argument("Cannot resample: image collection is empty");
     const float nan = std::numeric_limits<float>::quiet_NaN();
+    // Regular stacks (the only kind AlignViaDemons accepts, Alignment_Demons.h:150-152): the per-voxel lookups of
+    // cc:722-751 run on the GPU (dcma_b200_resample_to_grid), not as a serial host loop over every fixed-grid voxel.
+    {
+        dcma_b200_grid mg, rg;
+        if (grid_of(moving, mg) && grid_of(reference, rg) && mg.geom.channels == rg.geom.channels) {
+            const size_t nm = static_cast<size_t>(mg.geom.slices * mg.geom.rows * mg.geom.cols * mg.geom.channels);
+            const size_t nr = static_cast<size_t>(rg.geom.slices * rg.geom.rows * rg.geom.cols * mg.geom.channels);
+            Pinned<float> src(nm), dst(nr);
+            marshal_into(moving, src.data());
+            char err[512] = {0};
+            check_rc(dcma_b200_resample_to_grid(&mg, src.data(), &rg, nan, dst.data(), -1, err, sizeof err), err);
+            return collection_from_dense<float>(dst.data(), rg.geom.slices, rg.geom.rows, rg.geom.cols, mg.geom.channels, reference);
+        }
+    }
     planar_image_collection<float, double> out;
     for (const auto &ref_img : reference.images) {
         out.images.push_back(ref_img);  // geometry and metadata of the reference slice
@@ -113,6 +345,24 @@ planar_image_collection<float, double> AlignViaDemonsHelpers::histogram_match(
 planar_image_collection<float, double> AlignViaDemonsHelpers::warp_image_with_field(
     const planar_image_collection<float, double> &img_coll, const deformation_field &def_field) {
     if (img_coll.images.empty()) throw std::invalid_argument("Cannot warp: image collection is empty");
+    // Regular stacks: the per-voxel body (cc:921-936: field.transform(pos), then a trilinear lookup of the image at the
+    // displaced position, NaN outside) runs on the GPU -- dcma_b200_warp_image_grid, the same kernel WarpImages binds.
+    {
+        dcma_b200_grid ig, fg;
+        const auto &fcoll = def_field.get_imagecoll_crefw().get();
+        if (grid_of(img_coll, ig) && grid_of(fcoll, fg) && fg.geom.channels == 3) {
+            const size_t ni = static_cast<size_t>(ig.geom.slices * ig.geom.rows * ig.geom.cols * ig.geom.channels);
+            const size_t nf = static_cast<size_t>(fg.geom.slices * fg.geom.rows * fg.geom.cols * 3);
+            Pinned<float> src(ni), dst(ni);
+            Pinned<double> fld(nf);
+            marshal_into(img_coll, src.data());
+            marshal_into(fcoll, fld.data());
+            char err[512] = {0};
+            check_rc(dcma_b200_warp_image_grid(&fg, fld.data(), &ig, src.data(), nullptr, std::numeric_limits<float>::quiet_NaN(),
+                                               dst.data(), -1, err, sizeof err), err);
+            return collection_from_dense<float>(dst.data(), ig.geom.slices, ig.geom.rows, ig.geom.cols, ig.geom.channels, img_coll);
+        }
+    }
     // adjacency index over the SOURCE images so that single-slice stacks are still sampled bilinearly
     auto &nc = const_cast<planar_image_collection<float, double> &>(img_coll);
     const planar_image_adjacency<float, double> src({}, {{std::ref(nc)}}, img_coll.images.front().ortho_unit());
@@ -135,25 +385,69 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
         return std::nullopt;
     }
     try {
+        // ---- dense volumes in pinned host memory.  Regular stacks: the moving image is resampled onto the stationary
+        // grid on the GPU straight from its own dense volume (no intermediate image collection); anything else takes
+        // the reference's route (resample_image_to_reference_grid, then marshal) and fails in marshal exactly as the
+        // reference does when the result is not a regular grid.
         if (params.verbosity >= 1) YLOGINFO("Resampling moving image to reference grid");
-        auto moving = resample_image_to_reference_grid(moving_in, stationary);
-        const auto fixed_vol = marshal_collection_to_volume(stationary);
-        auto moving_vol = marshal_collection_to_volume(moving);
+        dcma_b200_grid fg, mg;
+        demons_volume<float> fixed_vol;  // header only (extents, spacing); the voxels live in the pinned buffers
+        Pinned<float> fixed_px, moving_px;
+        auto header_from = [](demons_volume<float> &v, const dcma_b200_grid &gr, int64_t channels) {
+            v.slices = gr.geom.slices;
+            v.rows = gr.geom.rows;
+            v.cols = gr.geom.cols;
+            v.channels = channels;
+            v.pxl_dx = gr.geom.pxl_dx;
+            v.pxl_dy = gr.geom.pxl_dy;
+            v.pxl_dz = gr.geom.pxl_dz;
+        };
+        const bool fixed_regular = grid_of(stationary, fg);
+        size_t nfix = 0;
+        if (fixed_regular) {
+            header_from(fixed_vol, fg, fg.geom.channels);
+            // the reference takes the spacing of the FIRST image (Alignment_Demons.h:160-162)
+            fixed_vol.pxl_dz = stationary.images.front().pxl_dz;
+            nfix = static_cast<size_t>(fg.geom.slices * fg.geom.rows * fg.geom.cols * fg.geom.channels);
+            fixed_px = Pinned<float>(nfix);
+            marshal_into(stationary, fixed_px.data());
+        } else {
+            // not a stack the GPU resampler can describe (e.g. slices out of order in the list): the reference's own
+            // marshalling decides whether it is acceptable at all, and throws its diagnostics if not
+            auto fv = marshal_collection_to_volume(stationary);
+            nfix = fv.data.size();
+            fixed_px = Pinned<float>(nfix);
+            std::memcpy(fixed_px.data(), fv.data.data(), nfix * sizeof(float));
+            fv.data.clear();
+            fixed_vol = fv;
+        }
+        moving_px = Pinned<float>(nfix);
+        if (fixed_regular && grid_of(moving_in, mg) && mg.geom.channels == fg.geom.channels) {
+            const size_t nmov = static_cast<size_t>(mg.geom.slices * mg.geom.rows * mg.geom.cols * mg.geom.channels);
+            Pinned<float> raw(nmov);
+            marshal_into(moving_in, raw.data());
+            char rerr[512] = {0};
+            check_rc(dcma_b200_resample_to_grid(&mg, raw.data(), &fg, std::numeric_limits<float>::quiet_NaN(), moving_px.data(),
+                                                params.device, rerr, sizeof rerr), rerr);
+        } else {
+            auto moving = resample_image_to_reference_grid(moving_in, stationary);
+            const auto mv = marshal_collection_to_volume(moving);
+            if (mv.data.size() != nfix) throw std::invalid_argument("Resampled moving image does not match the stationary grid");
+            std::memcpy(moving_px.data(), mv.data.data(), nfix * sizeof(float));
+        }
         if (params.use_histogram_matching) {
             // reference: histogram_match(moving, stationary, ...) on the collections (cc:967-972).  Here the same
             // algorithm runs on the GPU over the dense volumes (bit-identical result; the public helper above stays a
             // host function, as in the reference)
             if (params.verbosity >= 1) YLOGINFO("Applying histogram matching");
-            std::vector<float> matched(moving_vol.data.size());
+            Pinned<float> matched(nfix);
             char herr[512] = {0};
             int32_t mapped = 0;
-            if (dcma_b200_histogram_match(moving_vol.data.data(), static_cast<int64_t>(moving_vol.data.size()),
-                                          fixed_vol.data.data(), static_cast<int64_t>(fixed_vol.data.size()),
-                                          params.histogram_bins, params.histogram_outlier_fraction, matched.data(), &mapped,
-                                          params.device, herr, sizeof herr) != DCMA_B200_OK)
-                throw std::runtime_error(herr);
+            check_rc(dcma_b200_histogram_match(moving_px.data(), static_cast<int64_t>(nfix), fixed_px.data(), static_cast<int64_t>(nfix),
+                                               params.histogram_bins, params.histogram_outlier_fraction, matched.data(), &mapped,
+                                               params.device, herr, sizeof herr), herr);
             if (!mapped) YLOGWARN("Histogram matching not applicable (no finite values or constant intensity), moving image unchanged");
-            moving_vol.data.swap(matched);
+            moving_px = std::move(matched);
         }
 
         dcma_b200_geom g;
@@ -179,36 +473,35 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
         p.max_update_magnitude = params.max_update_magnitude;
         p.verbosity = params.verbosity;
         p.field_mode = params.field_mode;
-        if (const char *e = std::getenv("DCMA_B200_FIELD_MODE")) {  // test matrix / site policy override
+        if (const char *e = std::getenv("DCMA_B200_FIELD_MODE")) {  // test matrix / site policy override: never silent
             if (!std::strcmp(e, "fp64")) p.field_mode = DCMA_B200_FIELD_FP64;
-            if (!std::strcmp(e, "fp64_strict")) p.field_mode = DCMA_B200_FIELD_FP64_STRICT;
-            if (!std::strcmp(e, "fp32")) p.field_mode = DCMA_B200_FIELD_FP32;
+            else if (!std::strcmp(e, "fp64_strict")) p.field_mode = DCMA_B200_FIELD_FP64_STRICT;
+            else if (!std::strcmp(e, "fp32")) p.field_mode = DCMA_B200_FIELD_FP32;
+            else throw std::invalid_argument(std::string("DCMA_B200_FIELD_MODE='") + e + "' is not one of fp64, fp64_strict, fp32");
+            YLOGWARN("DCMA_B200_FIELD_MODE=" << e << " overrides the caller's field_mode");
         }
         p.device = params.device;
         p.pyramid_levels = params.pyramid_levels;
         p.use_symmetric_force = params.use_symmetric_force ? 1 : 0;
         for (int i = 0; i < 3; ++i) p.pyramid_iterations[i] = params.pyramid_iterations[i];
         p.n_devices = params.n_devices;
-        if (const char *e = std::getenv("DCMA_B200_DEVICES")) p.n_devices = std::atoi(e);  // site policy: GPUs to shard over
+        if (const char *e = std::getenv("DCMA_B200_DEVICES")) {  // site policy: GPUs to shard over; never silent
+            char *end = nullptr;
+            const long n = std::strtol(e, &end, 10);
+            if (end == e || *end != '\0' || n < 1 || n > 64)
+                throw std::invalid_argument(std::string("DCMA_B200_DEVICES='") + e + "' is not a device count");
+            p.n_devices = static_cast<int32_t>(n);
+            YLOGWARN("DCMA_B200_DEVICES=" << e << " overrides the caller's n_devices");
+        }
         p.halo_planes = params.halo_planes;
 
-        demons_volume<double> def;
-        def.slices = fixed_vol.slices;
-        def.rows = fixed_vol.rows;
-        def.cols = fixed_vol.cols;
-        def.channels = 3;
-        def.pxl_dx = fixed_vol.pxl_dx;
-        def.pxl_dy = fixed_vol.pxl_dy;
-        def.pxl_dz = fixed_vol.pxl_dz;
-        def.data.resize(static_cast<size_t>(def.slices * def.rows * def.cols * 3));
-
+        const size_t nvox = static_cast<size_t>(fixed_vol.slices * fixed_vol.rows * fixed_vol.cols);
+        Pinned<double> def(nvox * 3);
         char err[512] = {0};
         dcma_b200_run_stats stats;
-        const int rc = dcma_b200_demons_register(&g, fixed_vol.data.data(), moving_vol.data.data(), &p, def.data.data(),
-                                                 nullptr, &stats, err, sizeof(err));
-        if (rc != DCMA_B200_OK) throw std::runtime_error(std::string("dcma_b200: ") + err);
-
-        auto def_coll = marshal_volume_to_collection(def, stationary);
+        check_rc(dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err)), err);
+        // marshal_volume_to_collection (Alignment_Demons.h:182-204), slice-parallel
+        auto def_coll = collection_from_dense<double>(def.data(), fixed_vol.slices, fixed_vol.rows, fixed_vol.cols, 3, stationary);
         return deformation_field(std::move(def_coll));
     } catch (const std::exception &e) {
         YLOGWARN("Demons registration failed: " << e.what());

@@ -104,7 +104,28 @@ def build_operation(verbose=True):
     return OP_EXE
 
 
+HARNESS = os.path.join(OUT, "libdcma_b200_dropin.so")
+
+
+def build_harness(verbose=True):
+    """`host/_build/libdcma_b200_dropin.so`: the C++ drop-in `AlignViaDemons` (host/Alignment_Demons.cc, against the minimal
+    Ygor stand-in) behind a C entry, so that bench.py can time the call an operation makes -- both marshalling steps,
+    the grid resampling and the pinned-buffer pool inside the timed region.  Needs no reference sources."""
+    os.makedirs(OUT, exist_ok=True)
+    libdir = os.path.join(os.path.dirname(HERE), "lib")
+    shim = os.path.join(HERE, "shim")
+    inc = ["-I", os.path.join(shim, "dcma_min"), "-I", os.path.join(shim, "ygor_min"), "-I", HERE, "-I", os.path.join(ROOT, "include")]
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-Wno-unused-function", *inc,
+           os.path.join(HERE, "dropin_harness.cc"), os.path.join(HERE, "Alignment_Demons.cc"), os.path.join(HERE, "Alignment_Field_IO.cc"),
+           "-o", HARNESS, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    if verbose:
+        print("[host tests]", " ".join(cmd))
+    subprocess.check_call(cmd)
+    return HARNESS
+
+
 if __name__ == "__main__":
+    build_harness()
     p = build()
     q = build_operation()
     print(p if p else "unavailable")

@@ -223,6 +223,14 @@ DCMA_B200_API int dcma_b200_prolong_field(const dcma_b200_geom *fine, const doub
 DCMA_B200_API int dcma_b200_warp_image(const dcma_b200_geom *geom, const float *image, const double *deformation, float oob_value,
                          int use_oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* ---- pinned host memory ------------------------------------------------------------------------------------------ */
+/* Page-locked host buffers for the volumes handed to the calls above: transfers from/to them run at PCIe speed and
+ * asynchronously (H2D of the images, D2H of the 24 B/voxel field).  The reference has no counterpart: its engine copies
+ * between std::vector and USM (src/Alignment_Demons.cc:116-121, 181-186).  Page-locking costs about as much as one
+ * transfer saves, so callers keep such buffers for the life of the process (host/Alignment_Demons.cc pools them). */
+DCMA_B200_API int dcma_b200_host_alloc(void **out, size_t bytes, char *errbuf, size_t errbuf_len);
+DCMA_B200_API void dcma_b200_host_free(void *p);
+
 /* ---- histogram matching (AlignViaDemonsHelpers::histogram_match, src/Alignment_Demons.cc:760-891) ------------- */
 /* out := source with its intensity distribution matched to `reference` (num_bins-bin CDFs between the
  * outlier_fraction / 1-outlier_fraction percentiles, first-bin->=quantile lookup, clamping outside the source range).

@@ -6,7 +6,7 @@ iteration counts without spending CPU-oracle minutes on the GPU box.
 
 For every case the UNMODIFIED reference engine (oracle/_ref/libdemons_ref.so, compiled from /root/reference by
 oracle/build_ref.py) registers a bit-reproducible phantom pair (`phantom.make_pair_exact`: IEEE-exact operations only,
-so the GPU box regenerates byte-identical inputs) and the following is stored in tests/golden/full_<case>.npz:
+so the GPU box regenerates byte-identical inputs) and the following is stored in tests/golden/full/full_<case>.npz:
 
     sha256 of the fixed and moving volumes      -> the test first proves it has the same inputs
     sha256 of the reference's deformation field -> `fp64_strict` must hash to the same value (bit identity at full size)
@@ -60,7 +60,8 @@ def main():
         D, hist, n = oracle.demons_run(F, M, oracle.make_params(**c["params"]), kind="reference")
         dt = time.time() - t
         s = c["sub"]
-        out = os.path.join(HERE, f"full_{name}.npz")
+        os.makedirs(os.path.join(HERE, "full"), exist_ok=True)
+        out = os.path.join(HERE, "full", f"full_{name}.npz")
         np.savez_compressed(out, shape=np.array(c["shape"]), sub=s, params=np.array(sorted((k, str(v)) for k, v in c["params"].items())),
                             sha_fixed=sha(F), sha_moving=sha(M), sha_deformation=sha(D), deformation_sub=D[::s, ::s, ::s].copy(),
                             mse_history=hist[:n].copy(), iterations_done=n, max_abs=np.abs(D).max(axis=(0, 1, 2)),

@@ -1,6 +1,6 @@
 """Full-length parity at BASELINE.json's real sizes and iteration counts, with NO CPU oracle time on the GPU box.
 
-tests/golden/full_*.npz were written by tests/golden/make_full_size_fixtures.py from the UNMODIFIED reference engine
+tests/golden/full/full_*.npz were written by tests/golden/make_full_size_fixtures.py from the UNMODIFIED reference engine
 (oracle/_ref) on bit-reproducible inputs (`phantom.make_pair_exact`).  For every case:
 
   1. the pair is regenerated ON THE GPU and its sha256 must equal the fixture's (same bytes as the reference was given);
@@ -22,7 +22,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full_*.npz")))
+FIXTURES = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full", "full_*.npz")))
 TOL_MM, TOL_MSE = 1e-3, 1e-4  # BASELINE.json north_star
 # modes that must be inside the tolerance at full length (fp32 is reported, not required: see DESIGN.md section 2)
 REQUIRED = ("fp64", "mixed")

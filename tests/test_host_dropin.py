@@ -32,11 +32,29 @@ def _run(exe, *args, mode=None):
     return int(m.group(1)), int(m.group(2)), int(m.group(3)), r.stdout
 
 
+def _has_gpu():
+    try:
+        from dicomautomaton_b200 import capi
+        return capi.lib().dcma_b200_device_count() > 0
+    except Exception:
+        return False
+
+
 def test_reference_host_side_cases_pass_without_gpu(exe):
-    """resample / histogram_match (exact values 10, 17.5, 25, 32.5) / warp_image_with_field / empty input."""
-    total, passed, failed, out = _run(
-        exe, "-tc=resample_image_to_reference_grid*,histogram_match*,warp_image_with_field*,AlignViaDemons handles empty inputs")
-    assert total == 6 and failed == 0, out[-2000:]
+    """histogram_match (exact values 10, 17.5, 25, 32.5) and the empty-input contract are host code and need no device."""
+    total, passed, failed, out = _run(exe, "-tc=histogram_match*,AlignViaDemons handles empty inputs")
+    assert total == 3 and failed == 0, out[-2000:]
+
+
+def test_gpu_backed_helpers_fail_loudly_without_a_device(exe):
+    """resample_image_to_reference_grid and warp_image_with_field run on the GPU for regular stacks (the reference runs
+    them as serial host loops, cc:709-755 and cc:896-941).  There is no CPU fallback: on a box without a CUDA device they
+    must fail with the library's message, not quietly compute something on the host."""
+    if _has_gpu():
+        pytest.skip("a CUDA device is present: the cases run for real in the gpu-marked test below")
+    total, passed, failed, out = _run(exe, "-tc=resample_image_to_reference_grid*,warp_image_with_field*")
+    assert total == 3 and failed == 3, out[-2000:]
+    assert out.count("no CUDA device is available (dcma_b200 has no CPU fallback)") >= 3, out[-2000:]
 
 
 @pytest.mark.gpu

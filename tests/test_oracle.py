@@ -116,3 +116,26 @@ def test_port_equals_reference_with_convergence_break(oracle_mod):
     Dp, hp, np_ = oracle_mod.demons_run(F, M, par, kind="port")
     assert nr == np_ and nr < 80
     assert np.array_equal(Dr, Dp) and np.array_equal(hr, hp)
+
+
+def test_port_reproduces_the_reference_fixture_of_config_1(oracle_mod):
+    """BASELINE config 1 at its real size and length (128^3, standard Demons, sigma_d 1.0 mm, 100 iterations): the C
+    restatement must hash to the deformation field the UNMODIFIED reference engine produced
+    (tests/golden/full/full_config1_128.npz, written by tests/golden/make_full_size_fixtures.py).  Needs no reference
+    sources, so it also pins the port on machines where oracle/_ref cannot be rebuilt."""
+    import hashlib
+    from dicomautomaton_b200 import phantom
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "full", "full_config1_128.npz")
+    d = np.load(path, allow_pickle=True)
+    shape = tuple(int(v) for v in d["shape"])
+    f, m = phantom.make_pair_exact(shape)
+    F, M = f.numpy(), m.numpy()
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).hexdigest()
+    assert sha(F) == str(d["sha_fixed"]) and sha(M) == str(d["sha_moving"])
+    conv = dict(max_iterations=int, convergence_threshold=float, deformation_field_smoothing_sigma=float,
+                update_field_smoothing_sigma=float, use_diffeomorphic=lambda s: s == "True")
+    par = oracle_mod.make_params(**{k: conv[k](v) for k, v in d["params"]})
+    D, hist, n = oracle_mod.demons_run(F, M, par, kind="port")
+    assert n == int(d["iterations_done"])
+    assert sha(D) == str(d["sha_deformation"])
+    assert np.array_equal(hist[:n], d["mse_history"])
