@@ -2,8 +2,12 @@
 // (src/Alignment_Demons.h:20-61 has no such parameter); `pyramid_levels = 1` (the default) is exactly the reference's
 // single-resolution loop.  Definition implemented here (restated on the CPU in oracle/extensions.py, "parity unpinned"):
 //   * level l+1 halves every axis whose extent at level l is >= 8 (others are kept): extent' = ceil(extent / 2),
-//     spacing' = 2 * spacing; an image voxel of level l+1 is the mean of the FINITE voxels of its 2x2x2 (2 or 1 along
-//     kept axes) block of level l, accumulated in double in z,y,x order, NaN if the block has no finite voxel;
+//     spacing' = 2 * spacing.  The level-l image is first low-passed along every halved axis (anti-aliasing: a 2x2x2 block
+//     mean alone leaves most of the energy between the new and the old Nyquist frequency, which then aliases into wrong
+//     forces on the coarse levels): Gaussian, sigma = 1 voxel of level l, 7 taps, weights renormalised over the in-grid
+//     finite taps, double accumulation in tap order, rounded to float after each axis (x, then y, then z).  An image
+//     voxel of level l+1 is then the mean of the FINITE voxels of its 2x2x2 (2 or 1 along kept axes) block of the
+//     low-passed image, accumulated in double in z,y,x order, NaN if the block has no finite voxel;
 //   * levels run coarse -> fine with the same parameters (sigmas are in mm, so radii shrink in voxels); level l starts
 //     from the level l+1 result prolonged trilinearly: fine voxel x samples the coarse field at u = x/2 - 1/4 (the coarse
 //     voxel centre of fine index 2i + 1/2), clamped to [0, extent' - 1]; displacements are in mm and are not rescaled;
@@ -65,6 +69,36 @@ __global__ void __launch_bounds__(256)
             }
         }
         coarse[i] = (n > 0) ? static_cast<float>(sum / static_cast<double>(n)) : __int_as_float(0x7fc00000);
+    }
+}
+
+// anti-aliasing low-pass along one axis (see the header comment): 7-tap Gaussian, sigma = 1 voxel
+__constant__ double c_blur_w[7] = {0.011108996538242306, 0.1353352832366127, 0.6065306597126334, 1.0,
+                                   0.6065306597126334, 0.1353352832366127, 0.011108996538242306};
+__global__ void __launch_bounds__(256)
+    k_blur_axis(const float *__restrict__ in, float *__restrict__ out, const Dim3i n, const int ch, const int axis /* 0 x, 1 y, 2 z */) {
+    const long long total = static_cast<long long>(n.S) * n.R * n.C * ch;
+    const long long stride_thr = static_cast<long long>(gridDim.x) * blockDim.x;
+    const int extent = axis == 0 ? n.C : (axis == 1 ? n.R : n.S);
+    const long long step = (axis == 0 ? 1LL : (axis == 1 ? static_cast<long long>(n.C) : static_cast<long long>(n.R) * n.C)) * ch;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride_thr) {
+        long long v = i / ch;
+        const int x = static_cast<int>(v % n.C);
+        v /= n.C;
+        const int y = static_cast<int>(v % n.R);
+        const int z = static_cast<int>(v / n.R);
+        const int pos = axis == 0 ? x : (axis == 1 ? y : z);
+        double sum = 0.0, wsum = 0.0;
+        for (int k = -3; k <= 3; ++k) {
+            const int q = pos + k;
+            if (q < 0 || q >= extent) continue;
+            const float val = in[i + k * step];
+            if (finite_f32(val)) {
+                sum = __dadd_rn(sum, __dmul_rn(c_blur_w[k + 3], static_cast<double>(val)));  // no contraction: the CPU restatement has none
+                wsum = __dadd_rn(wsum, c_blur_w[k + 3]);
+            }
+        }
+        out[i] = (wsum > 0.0) ? static_cast<float>(sum / wsum) : __int_as_float(0x7fc00000);
     }
 }
 
@@ -140,6 +174,22 @@ void coarsen_geom(const dcma_b200_geom &fine, dcma_b200_geom *coarse, int halved
     }
 }
 
+// low-pass of the level image along the axes that are about to be halved; tmp: scratch of the same size; the result is
+// in `img` again
+void prefilter_image_device(const dcma_b200_geom &g, float *d_img, float *d_tmp, const int halved[3], cudaStream_t st) {
+    const Dim3i n{static_cast<int>(g.slices), static_cast<int>(g.rows), static_cast<int>(g.cols)};
+    const long long total = g.slices * g.rows * g.cols * g.channels;
+    const int order[3] = {2, 1, 0};  // halved[] is (z, y, x); passes run x, then y, then z
+    float *a = d_img, *b = d_tmp;
+    for (int pass = 0; pass < 3; ++pass) {
+        if (!halved[order[pass]]) continue;
+        k_blur_axis<<<grid_for(total), 256, 0, st>>>(a, b, n, static_cast<int>(g.channels), pass);
+        DCMA_CUDA(cudaGetLastError());
+        std::swap(a, b);
+    }
+    if (a != d_img) DCMA_CUDA(cudaMemcpyAsync(d_img, a, sizeof(float) * static_cast<size_t>(total), cudaMemcpyDeviceToDevice, st));
+}
+
 void restrict_image_device(const dcma_b200_geom &fine, const float *d_fine, const dcma_b200_geom &coarse, const int halved[3],
                            float *d_coarse, cudaStream_t st) {
     const Dim3i nf{static_cast<int>(fine.slices), static_cast<int>(fine.rows), static_cast<int>(fine.cols)};
@@ -205,8 +255,17 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
         const long long nc = g[l].slices * g[l].rows * g[l].cols * g[l].channels;
         DevBuf<float> dF(nc), dM(nc);
         e[l - 1]->sync();
-        restrict_image_device(g[l - 1], e[l - 1]->fixed_dev(), g[l], hv[l].data(), dF.p, nullptr);
-        restrict_image_device(g[l - 1], e[l - 1]->moving_dev(), g[l], hv[l].data(), dM.p, nullptr);
+        {
+            // anti-aliasing low-pass of the level l-1 images (copies; the engine keeps the unfiltered ones), then decimation
+            const long long nfine = g[l - 1].slices * g[l - 1].rows * g[l - 1].cols * g[l - 1].channels;
+            DevBuf<float> lp(nfine), tmp(nfine);
+            for (int which = 0; which < 2; ++which) {
+                const float *src = which == 0 ? e[l - 1]->fixed_dev() : e[l - 1]->moving_dev();
+                DCMA_CUDA(cudaMemcpyAsync(lp.p, src, sizeof(float) * static_cast<size_t>(nfine), cudaMemcpyDeviceToDevice, nullptr));
+                prefilter_image_device(g[l - 1], lp.p, tmp.p, hv[l].data(), nullptr);
+                restrict_image_device(g[l - 1], lp.p, g[l], hv[l].data(), which == 0 ? dF.p : dM.p, nullptr);
+            }
+        }
         DCMA_CUDA(cudaDeviceSynchronize());
         e[l].reset(make_engine(g[l], p, nullptr, SlabSpec{}));
         e[l]->load(dF.p, dM.p, true);

@@ -55,18 +55,21 @@ def build(verbose=True):
 
 
 OP_EXE = os.path.join(OUT, "demons_operation_check")
+OP_PATCHED_EXE = os.path.join(OUT, "demons_operation_check_patched")
+OP_PATCH = os.path.join(ROOT, "patches", "RegisterImagesDemons.patch")
 
 
-def build_operation(verbose=True):
+def build_operation(verbose=True, patched=False):
     """`host/_build/demons_operation_check`: the reference's OWN operation file, src/Operations/RegisterImagesDemons.cc,
     compiled in place and unmodified (read through stdin from a scratch directory whose parent holds forwarding headers,
     so that its `../Structs.h`-style includes resolve to the stand-ins and to our Alignment_Demons.h), linked with the
     AlignViaDemons drop-in, libdcma_b200.so and the driver tests/native/operation_check.cc."""
     op_src = os.path.join(REF_SRC, "Operations", "RegisterImagesDemons.cc")
+    exe = OP_PATCHED_EXE if patched else OP_EXE
     if not os.path.isfile(op_src):
         if verbose:
-            print(f"[host tests] {op_src} not found; {'using prebuilt ' + OP_EXE if os.path.isfile(OP_EXE) else 'nothing to do'}")
-        return OP_EXE if os.path.isfile(OP_EXE) else None
+            print(f"[host tests] {op_src} not found; {'using prebuilt ' + exe if os.path.isfile(exe) else 'nothing to do'}")
+        return exe if os.path.isfile(exe) else None
     ops = os.path.join(OUT, "ops")
     os.makedirs(ops, exist_ok=True)
     libdir = os.path.join(os.path.dirname(HERE), "lib")
@@ -85,23 +88,29 @@ def build_operation(verbose=True):
                 "OperationDoc OpArgDocRegisterImagesDemons();\n"
                 "bool RegisterImagesDemons(Drover &, const OperationArgPkg &, std::map<std::string, std::string> &, const std::string &);\n")
     objs = []
-    o = os.path.join(OUT, "ref_operation.o")
+    o = os.path.join(OUT, "ref_operation_patched.o" if patched else "ref_operation.o")
     cmd = cxx + inc + ["-x", "c++", "-c", "-", "-o", o]
     if verbose:
-        print("[host tests]", " ".join(cmd), "<", op_src)
-    with open(op_src, "rb") as f:
-        subprocess.check_call(cmd, stdin=f, cwd=ops)
+        print("[host tests]", " ".join(cmd), "<", op_src, "(+ patches/RegisterImagesDemons.patch)" if patched else "")
+    if patched:
+        # the reference file with patches/RegisterImagesDemons.patch applied, streamed: `patch -o -` writes the result
+        # to stdout, nothing of the reference is written into the repository
+        text = subprocess.run(["patch", "-s", "-o", "-", op_src, OP_PATCH], check=True, capture_output=True).stdout
+        subprocess.run(cmd, input=text, check=True, cwd=ops)
+    else:
+        with open(op_src, "rb") as f:
+            subprocess.check_call(cmd, stdin=f, cwd=ops)
     objs.append(o)
     for src, name in ((os.path.join(ROOT, "tests", "native", "operation_check.cc"), "operation_check.o"),
                       (os.path.join(HERE, "Alignment_Demons.cc"), "Alignment_Demons.o")):
         o = os.path.join(OUT, name)
         subprocess.check_call(cxx + inc + ["-c", src, "-o", o])
         objs.append(o)
-    cmd = ["g++", "-o", OP_EXE, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    cmd = ["g++", "-pthread", "-o", exe, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
     if verbose:
         print("[host tests]", " ".join(cmd))
     subprocess.check_call(cmd)
-    return OP_EXE
+    return exe
 
 
 HARNESS = os.path.join(OUT, "libdcma_b200_dropin.so")
@@ -128,6 +137,7 @@ if __name__ == "__main__":
     build_harness()
     p = build()
     q = build_operation()
+    build_operation(patched=True)
     print(p if p else "unavailable")
     print(q if q else "unavailable")
     sys.exit(0 if p else 1)

@@ -100,6 +100,41 @@ def coarsen(shape, spacing):
     return cs, sp, (hz, hy, hx)
 
 
+_BLUR_W = np.array([0.011108996538242306, 0.1353352832366127, 0.6065306597126334, 1.0,
+                    0.6065306597126334, 0.1353352832366127, 0.011108996538242306], dtype=np.float64)
+
+
+def prefilter(img: np.ndarray):
+    """Anti-aliasing low-pass before decimation (csrc/pyramid.cu): along every axis that is about to be halved, a 7-tap
+    Gaussian (sigma = 1 voxel), weights renormalised over the in-grid finite taps, double accumulation in tap order,
+    rounded to float after each axis; x, then y, then z."""
+    _, _, (hz, hy, hx) = coarsen(img.shape, (1, 1, 1))
+    out = img.astype(np.float32)
+    for axis, halved in ((2, hx), (1, hy), (0, hz)):
+        if not halved:
+            continue
+        n = out.shape[axis]
+        src = out.astype(np.float64)
+        fin = np.isfinite(src)
+        vals = np.where(fin, src, 0.0)
+        acc = np.zeros_like(src)
+        wsum = np.zeros_like(src)
+        for k in range(-3, 4):
+            lo, hi = max(0, -k), min(n, n - k)  # output positions whose tap pos + k is inside the grid
+            if lo >= hi:
+                continue
+            dst = [slice(None)] * 3
+            frm = [slice(None)] * 3
+            dst[axis] = slice(lo, hi)
+            frm[axis] = slice(lo + k, hi + k)
+            dst, frm = tuple(dst), tuple(frm)
+            acc[dst] = acc[dst] + np.where(fin[frm], _BLUR_W[k + 3] * vals[frm], 0.0)
+            wsum[dst] = wsum[dst] + np.where(fin[frm], _BLUR_W[k + 3], 0.0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out = np.where(wsum > 0.0, acc / wsum, np.nan).astype(np.float32)
+    return out
+
+
 def restrict(img: np.ndarray):
     """Mean of the finite voxels of each 2x2x2 block (2 or 1 along kept axes), double accumulation in z,y,x order."""
     s, r, c = img.shape
@@ -152,8 +187,8 @@ def pyramid_run(fixed, moving, spacing, levels, iters_per_level, sigma_d, sigma_
     """iters_per_level[l] for level l (0 = finest).  Returns (D at the finest level, concatenated MSE history)."""
     F, M, SP = [fixed], [moving], [tuple(spacing)]
     for _ in range(1, levels):
-        F.append(restrict(F[-1]))
-        M.append(restrict(M[-1]))
+        F.append(restrict(prefilter(F[-1])))
+        M.append(restrict(prefilter(M[-1])))
         SP.append(coarsen(F[-2].shape, SP[-1])[1])
     D, hist = None, []
     for l in range(levels - 1, -1, -1):

@@ -2,6 +2,8 @@
 // dicomautomaton_b200/host/build_host_tests.py against the AlignViaDemons drop-in and the stand-in headers) the way the
 // dispatcher does: arguments as strings, defaults taken from OpArgDocRegisterImagesDemons().
 //   operation_check doc   prints "name=default" for every documented argument
+//   operation_check run3  (the operation with patches/RegisterImagesDemons.patch applied) the same through the additive
+//                         arguments: PyramidLevels=3, UseSymmetricForce=true, FieldMode=fp64 -- BASELINE config 3's shape of run
 //   operation_check run   registers a small synthetic pair through RegisterImagesDemons() and checks what the operation
 //                         leaves in the Drover (RegisterImagesDemons.cc:337-381).  Exit 0 = all checks passed,
 //                         3 = the operation threw (its message is printed: without a device "Demons registration failed")
@@ -69,10 +71,26 @@ int main(int argc, char **argv) {
     args.set("TransformName", "check");
     args.set("Metadata", "Study@phantom;Operator@test");
     args.set("Verbosity", "0");
+    const bool run3 = (argc > 1 && !std::strcmp(argv[1], "run3"));
+    int64_t S = 12, R = 24, C = 28;
+    if (run3) {  // needs the additive arguments of patches/RegisterImagesDemons.patch
+        bool have = false;
+        for (const auto &a : doc.args) have = have || (a.name == "PyramidLevels");
+        if (!have) {
+            std::printf("this binary was built from the unpatched operation: no PyramidLevels argument\n");
+            return 4;
+        }
+        args.set("PyramidLevels", "3");
+        args.set("PyramidIterations", "15,25,40");
+        args.set("UseSymmetricForce", "true");
+        args.set("FieldMode", "fp64");
+        args.set("MaxIterations", "40");
+        S = 32; R = 48; C = 64;  // every axis >= 8 at the coarsest of three levels
+    }
 
     Drover d;
-    d.image_data.push_back(make_array(12, 24, 28, 0.0));  // fixed
-    d.image_data.push_back(make_array(12, 24, 28, 1.5));  // moving: shifted by 1.5 voxels along x
+    d.image_data.push_back(make_array(S, R, C, 0.0));  // fixed
+    d.image_data.push_back(make_array(S, R, C, 1.5));  // moving: shifted by 1.5 voxels along x
     std::map<std::string, std::string> invocation;
     bool ok = false;
     try {
@@ -97,8 +115,8 @@ int main(int argc, char **argv) {
         CHECK(t.metadata.at("Study") == "phantom" && t.metadata.at("Operator") == "test");
         if (std::holds_alternative<deformation_field>(t.transform)) {
             const auto &imgs = std::get<deformation_field>(t.transform).get_imagecoll_crefw().get().images;
-            CHECK(imgs.size() == 12);
-            CHECK(imgs.front().rows == 24 && imgs.front().columns == 28 && imgs.front().channels == 3);
+            CHECK(static_cast<int64_t>(imgs.size()) == S);
+            CHECK(imgs.front().rows == R && imgs.front().columns == C && imgs.front().channels == 3);
         }
     }
     CHECK(d.image_data.size() == 3);  // KeepDeformedImages appends the warped moving images (:366-381)
@@ -106,7 +124,7 @@ int main(int argc, char **argv) {
         const auto &fixed = d.image_data.front()->imagecoll;
         const auto &moving = (*std::next(d.image_data.begin()))->imagecoll;
         const auto &warped = d.image_data.back()->imagecoll;
-        CHECK(warped.images.size() == 12);
+        CHECK(static_cast<int64_t>(warped.images.size()) == S);
         CHECK(warped.images.front().metadata.at("Description") == "Demons-warped moving image");
         const double before = mse(fixed, moving), after = mse(fixed, warped);
         std::printf("MSE before %.4f after %.4f\n", before, after);

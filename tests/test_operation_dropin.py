@@ -71,3 +71,46 @@ def test_operation_registers_through_the_gpu_dropin(exe):
     """On a B200 (profiles/r1_operation_check.log): MSE before 91.1138 after 0.4843, every check passes."""
     r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+# ---- the operation with patches/RegisterImagesDemons.patch applied: the additive arguments of the drop-in ----------
+ADDED_ARGS = [("FieldMode", "fp64"), ("PyramidLevels", "1"), ("PyramidIterations", ""), ("UseSymmetricForce", "false"),
+              ("Devices", "1")]
+
+
+@pytest.fixture(scope="module")
+def exe_patched():
+    import build_host_tests
+    p = build_host_tests.build_operation(verbose=False, patched=True)
+    if not p:
+        pytest.skip("reference operation source not available and no prebuilt binary")
+    return p
+
+
+def test_patch_adds_the_extension_arguments_with_reference_preserving_defaults(exe_patched):
+    """patches/RegisterImagesDemons.patch applies to the reference's file, the result compiles against the drop-in, the 16
+    reference arguments are untouched and the five additive ones follow `Verbosity` with defaults that reproduce the
+    reference (new args must be additive with reference-preserving defaults)."""
+    r = subprocess.run([exe_patched, "doc"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = [tuple(l.split("=", 1)) for l in r.stdout.strip().splitlines()[1:]]
+    i = [n for n, _ in got].index("Verbosity")
+    assert got[i + 1:i + 1 + len(ADDED_ARGS)] == ADDED_ARGS
+    assert [g for g in got if g not in ADDED_ARGS] == EXPECTED_ARGS
+
+
+def test_patched_operation_fails_like_the_reference_without_a_device(exe_patched):
+    if has_gpu():
+        pytest.skip("a device is present")
+    r = subprocess.run([exe_patched, "run3"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    assert r.returncode == 3 and "THROW: Demons registration failed" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_config3_style_run_through_the_operation_surface(exe_patched):
+    """PyramidLevels=3, UseSymmetricForce=true, KeepDeformedImages=true through RegisterImagesDemons() itself: the
+    multi-resolution symmetric-force registration (BASELINE config 3's kind of run) is reachable from the dispatcher."""
+    r = subprocess.run([exe_patched, "run3"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe_patched, "run"], capture_output=True, text=True, timeout=600, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
