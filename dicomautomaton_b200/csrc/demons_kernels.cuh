@@ -533,9 +533,11 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_M
                 demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
 #if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
                 // feasibility probe only (tools/build_variant.py): what an fp32-stored update field would do to parity
-                ux = static_cast<CT>(static_cast<float>(ux));
-                uy = static_cast<CT>(static_cast<float>(uy));
-                uz = static_cast<CT>(static_cast<float>(uz));
+                if constexpr (!STRICT) {
+                    ux = static_cast<CT>(static_cast<float>(ux));
+                    uy = static_cast<CT>(static_cast<float>(uy));
+                    uz = static_cast<CT>(static_cast<float>(uz));
+                }
 #endif
                 U[v] = ux;
                 U1[v] = uy;
@@ -845,10 +847,12 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
             }
         }
 #if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
+        if constexpr (!STRICT) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[c][i] = static_cast<CT>(static_cast<float>(q[c][i]));
+                for (int i = 0; i < 8; ++i) q[c][i] = static_cast<CT>(static_cast<float>(q[c][i]));
+        }
 #endif
         // prefetch the next slice's displacement before consuming the gathers
         CT dn[3] = {CT(0), CT(0), CT(0)};

@@ -2,7 +2,8 @@
 //
 // deformation_field::write_to (reference src/Alignment_Field.cc:322-357) prints every double of the field on its own
 // line at max_digits10; read_from (:359-436) extracts them again with `is >> val`.  The per-image headers are a few
-// lines and stay on the host (host/Alignment_Field_IO.cc); the 3 * voxels numbers per image are the work:
+// lines and stay on the host (the reference's own code, see patches/Alignment_Field.patch); the 3 * voxels numbers per
+// image are the work:
 //
 //   format_doubles_host : doubles -> "%.17g\n" lines.  k_format_lines converts one number per thread (text_format.cuh,
 //                         exact), packs the lines of a 1024-number tile contiguously in shared memory (block scan of the

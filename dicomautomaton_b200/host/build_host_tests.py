@@ -125,7 +125,7 @@ def build_harness(verbose=True):
     shim = os.path.join(HERE, "shim")
     inc = ["-I", os.path.join(shim, "dcma_min"), "-I", os.path.join(shim, "ygor_min"), "-I", HERE, "-I", os.path.join(ROOT, "include")]
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-Wno-unused-function", *inc,
-           os.path.join(HERE, "dropin_harness.cc"), os.path.join(HERE, "Alignment_Demons.cc"), os.path.join(HERE, "Alignment_Field_IO.cc"),
+           os.path.join(HERE, "dropin_harness.cc"), os.path.join(HERE, "Alignment_Demons.cc"),
            "-o", HARNESS, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
     if verbose:
         print("[host tests]", " ".join(cmd))
@@ -133,8 +133,51 @@ def build_harness(verbose=True):
     return HARNESS
 
 
+FIELD_IO_EXE = os.path.join(OUT, "field_io_check")
+FIELD_PATCH = os.path.join(ROOT, "patches", "Alignment_Field.patch")
+
+
+def build_field_io(verbose=True):
+    """`host/_build/field_io_check`: the reference's OWN `deformation_field::write_to` / `read_from`
+    (src/Alignment_Field.cc:322-436) with patches/Alignment_Field.patch applied -- the two per-value loops call the GPU
+    payload codec host/Field_Payload.cc -- driven by the reference's round-trip cases (tests/native/field_io_check.cc).
+    The patched text is streamed (`patch -o -`), cut at the textual anchor of write_to (the members before it need the
+    whole of Ygor) and compiled from stdin against the stand-in class declaration; nothing of it is written to the repo."""
+    src = os.path.join(REF_SRC, "Alignment_Field.cc")
+    if not os.path.isfile(src):
+        if verbose:
+            print(f"[host tests] {src} not found; {'using prebuilt ' + FIELD_IO_EXE if os.path.isfile(FIELD_IO_EXE) else 'nothing to do'}")
+        return FIELD_IO_EXE if os.path.isfile(FIELD_IO_EXE) else None
+    os.makedirs(OUT, exist_ok=True)
+    libdir = os.path.join(os.path.dirname(HERE), "lib")
+    shim = os.path.join(HERE, "shim")
+    inc = ["-I", os.path.join(shim, "dcma_min"), "-I", os.path.join(shim, "ygor_min"), "-I", HERE, "-I", os.path.join(ROOT, "include")]
+    cxx = ["g++", "-std=c++17", "-O2", "-Wno-unused-function", "-Wno-unused-variable"]
+    text = subprocess.run(["patch", "-s", "-o", "-", src, FIELD_PATCH], check=True, capture_output=True).stdout.decode()
+    anchor = "bool\ndeformation_field::write_to("
+    if text.count(anchor) != 1 or "dcma_b200_io::write_payload" not in text or "dcma_b200_io::read_payload" not in text:
+        raise RuntimeError("patched Alignment_Field.cc does not look as expected")
+    prologue = ("#include <cstdint>\n#include <iostream>\n#include <limits>\n#include <string>\n#include \"YgorImages.h\"\n"
+                "#include \"YgorMath.h\"\n#include \"YgorMisc.h\"\n#include \"YgorLog.h\"\n#include \"YgorBase64.h\"\n"
+                "#include \"Alignment_Field.h\"\n#include \"Field_Payload.h\"\n")
+    o_ref = os.path.join(OUT, "ref_field_io_patched.o")
+    cmd = cxx + inc + ["-x", "c++", "-c", "-", "-o", o_ref]
+    if verbose:
+        print("[host tests]", " ".join(cmd), "<", src, "(+ patches/Alignment_Field.patch, from write_to on)")
+    subprocess.run(cmd, input=(prologue + text[text.index(anchor):]).encode(), check=True, cwd=OUT)
+    objs = [o_ref]
+    for s, name in ((os.path.join(ROOT, "tests", "native", "field_io_check.cc"), "field_io_check.o"),
+                    (os.path.join(HERE, "Field_Payload.cc"), "Field_Payload.o")):
+        o = os.path.join(OUT, name)
+        subprocess.check_call(cxx + inc + ["-c", s, "-o", o])
+        objs.append(o)
+    subprocess.check_call(["g++", "-o", FIELD_IO_EXE, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"])
+    return FIELD_IO_EXE
+
+
 if __name__ == "__main__":
     build_harness()
+    build_field_io()
     p = build()
     q = build_operation()
     build_operation(patched=True)

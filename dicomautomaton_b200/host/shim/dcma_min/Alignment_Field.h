@@ -1,8 +1,10 @@
 // Stand-in for the reference's src/Alignment_Field.h, used ONLY to build the host-side tests in this container, where
 // the real file cannot compile (it needs Ygor, Structs.h, Boost...).  Inside the reference tree the drop-in uses the
 // reference's own deformation_field unchanged.  Mirrors src/Alignment_Field.h:34-77 / .cc:45-153 for the members the
-// Demons path touches: construction from a 3-channel regular stack, the two accessors, transform() and the text
-// (de)serialisation, which defers to host/Alignment_Field_IO.{h,cc} the way INTEGRATION.md installs it in the reference.
+// Demons path touches: construction from a 3-channel regular stack, the two accessors and transform().  The text
+// (de)serialisation members write_to / read_from are only DECLARED here: their definitions are the reference's own
+// (src/Alignment_Field.cc:322-436) with patches/Alignment_Field.patch applied, compiled in place by
+// host/build_host_tests.py::build_field_io -- nothing of them lives in this repository.
 #pragma once
 #include <functional>
 #include <limits>
@@ -14,8 +16,6 @@
 
 #include "YgorImages.h"
 #include "YgorMath.h"
-
-#include "Alignment_Field_IO.h"
 
 class deformation_field {
     planar_image_collection<double, double> field;
@@ -41,13 +41,12 @@ class deformation_field {
     deformation_field(std::istream &is) {  // .cc:45-49: defers to read_from(), throws on errors
         if (!read_from(is)) throw std::invalid_argument("Unable to read deformation field from stream");
     }
-    bool write_to(std::ostream &os) const { return dcma_b200_io::write_field_text(field, os); }  // .cc:322-357
-    bool read_from(std::istream &is) {                                                           // .cc:359-436
-        planar_image_collection<double, double> f;
-        if (!dcma_b200_io::read_field_text(is, f)) return false;
-        field.Swap(f);
+    bool write_to(std::ostream &os) const;  // .cc:322-357, defined by the (patched) reference source
+    bool read_from(std::istream &is);       // .cc:359-436, likewise
+    void swap_and_rebuild(planar_image_collection<double, double> &in) {  // .cc:93-123 (validation as in the constructor)
+        deformation_field tmp(std::move(in));
+        field.Swap(tmp.field);
         rebuild();
-        return true;
     }
     deformation_field(const deformation_field &o) : field(o.field) { rebuild(); }
     deformation_field(deformation_field &&o) : field(std::move(o.field)) { rebuild(); }

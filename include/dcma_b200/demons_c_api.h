@@ -270,7 +270,8 @@ DCMA_B200_API int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, con
  * the image on its own line at precision max_digits10 (`os << val << '\n'`, :346-348); read_from (:359-436) extracts
  * them again with `is >> val` (:418-420).  For a 512 x 512 x 256 field that is 2.0e8 numbers, ~4.8 GB of text.  These
  * two calls do that part on the GPU, byte-for-byte and bit-for-bit what the C library produces (correctly rounded in
- * both directions); the header lines stay with the caller (host/Alignment_Field_IO.cc shows the whole writer/reader).
+ * both directions); the header lines stay with the caller (host/Field_Payload.cc is the stream-level codec that
+ * patches/Alignment_Field.patch installs into the reference's two loops).
  *
  * dcma_b200_format_doubles: text := printf("%.17g\n") of values[0..n).  `capacity` bytes are available at `text`
  *   (25 * n always suffices; DCMA_B200_EINVAL if it turns out too small); *text_len := bytes written.  No terminator.

@@ -5,7 +5,7 @@ Two checkers live here, both behind the same ctypes interface (`OracleEngine`, `
 * ``kind="reference"`` -- ``oracle/_ref/libdemons_ref.so``: the UNMODIFIED reference engine
   (`/root/reference/src/Alignment_Demons.cc:52-704`) compiled from its own sources by ``oracle/build_ref.py``.
 * ``kind="port"``      -- ``oracle/_build/libdemons_oracle.so``: our plain-C restatement (``oracle/demons_oracle.c``),
-  pinned bit-for-bit to the reference engine by ``tests/test_oracle_vs_ref.py`` and to ``tests/golden/*.npz``.
+  pinned bit-for-bit to the reference engine by ``tests/test_oracle.py`` and to ``tests/golden/*.npz``.
 * ``kind="port_f32"``  -- the same C file built with fp32 field storage/accumulation: a CPU *prediction* of the drift of
   the GPU's fp32-storage mode, not a parity oracle.
 

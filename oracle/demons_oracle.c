@@ -4,7 +4,7 @@
  * copy: the reference is SYCL C++ lambdas over USM pointers; this is C99 loops (OpenMP over z) over the same dense
  * layout  idx = ((z*rows + y)*cols + x)*ch + c  (src/Alignment_Demons.h:77-79).
  *
- * Pinned: tests/test_oracle_vs_ref.py requires this restatement to equal the compiled reference engine
+ * Pinned: tests/test_oracle.py requires this restatement to equal the compiled reference engine
  * (oracle/_ref/libdemons_ref.so, built by oracle/build_ref.py from the reference's own sources) BIT-FOR-BIT on the
  * deformation field, update field, warped image and MSE, stage by stage and over whole loops, and
  * tests/golden/*.npz hold reference-generated vectors for machines where /root/reference is absent.

@@ -1,4 +1,6 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed): how registrations and z-slabs are spread over ranks.
+"""TEST infrastructure (not product code): torch.distributed restatement of how registrations and z-slabs are spread over
+ranks, used by tests/test_parallel_gloo.py to emulate the schedule of csrc/slab.cu on CPU with gloo.  The product data
+plane is csrc/slab.cu (IPC peer stores + flag counters); nothing under dicomautomaton_b200/ imports this file.
 
 The Demons path shards in two ways:
   * independent registrations (BASELINE config 5): round-robin over ranks, NO data-path collective -- `shard_cases`;

@@ -1,6 +1,7 @@
-// The reference's own cases for the field text format (src/Alignment_Field_Tests.cc:196-289), restated against the
-// drop-in writer/reader (host/Alignment_Field_IO.cc, numbers converted on the GPU), plus a byte-for-byte comparison with
-// the reference's statement sequence executed on the host with iostreams (src/Alignment_Field.cc:322-357).
+// The reference's own cases for the field text format (src/Alignment_Field_Tests.cc:196-289), run against the
+// reference's own write_to / read_from with patches/Alignment_Field.patch applied (numbers converted on the GPU by
+// host/Field_Payload.cc; built by host/build_host_tests.py::build_field_io), plus a byte-for-byte comparison with
+// the unpatched statement sequence executed on the host with iostreams (src/Alignment_Field.cc:322-357).
 // Exit code 0 = all passed, 77 = no device.
 #include <cmath>
 #include <cstdio>
@@ -9,12 +10,15 @@
 #include <limits>
 #include <random>
 #include <sstream>
+#include <string>
+#include <vector>
 
 #include "YgorBase64.h"
 #include "YgorImages.h"
 #include "YgorMath.h"
 
 #include "Alignment_Field.h"
+#include "Field_Payload.h"
 #include "dcma_b200/demons_c_api.h"
 
 static int g_fail = 0;
@@ -111,14 +115,35 @@ int main() {
         std::normal_distribution<double> nd(0.0, 2.5);
         auto imgs = make_field(5, 64, 48, [&](int64_t, int64_t, int64_t) { return vec3<double>(nd(rng), nd(rng) * 1e-7, std::ldexp(static_cast<double>(rng() >> 40), -20)); });
         const std::string want = host_write(imgs);
+        planar_image_collection<double, double> copy_of_imgs(imgs);
+        deformation_field field(std::move(copy_of_imgs));
         std::stringstream ss;
-        CHECK(dcma_b200_io::write_field_text(imgs, ss));
+        CHECK(field.write_to(ss));
         CHECK(ss.str() == want);
-        planar_image_collection<double, double> back;
-        CHECK(dcma_b200_io::read_field_text(ss, back));
-        CHECK(back.images.size() == imgs.images.size());
-        auto ia = imgs.images.begin(); auto ib = back.images.begin();
-        for (; ia != imgs.images.end() && ib != back.images.end(); ++ia, ++ib) { CHECK(ia->data == ib->data); CHECK(ia->offset == ib->offset); }
+        ss << "trailing 42";  // read_from must stop just behind the last number, as n extractions do
+        deformation_field back(ss);
+        std::string word; int number = 0;
+        ss >> word >> number;
+        CHECK(word == "trailing"); CHECK(number == 42);
+        const auto &bi = back.get_imagecoll_crefw().get().images;
+        CHECK(bi.size() == imgs.images.size());
+        auto ia = imgs.images.begin(); auto ib = bi.begin();
+        for (; ia != imgs.images.end() && ib != bi.end(); ++ia, ++ib) { CHECK(ia->data == ib->data); CHECK(ia->offset == ib->offset); }
+    }
+    {   // the codec alone: odd white space, long tokens (the bounded read-ahead has to grow), too few numbers
+        std::stringstream ss;
+        const int n = 300;
+        for (int i = 0; i < n; ++i) ss << "\t \n  0000000000000000000000000000000000000" << i << ".2500000000000000000000000000000000000000  \r\n";
+        ss << "end";
+        std::vector<double> v(n, -1.0);
+        CHECK(dcma_b200_io::read_payload(ss, v.data(), n));
+        for (int i = 0; i < n; ++i) CHECK(v[i] == i + 0.25);
+        std::string word; ss >> word; CHECK(word == "end");
+        std::stringstream few("1 2 3");
+        CHECK(!dcma_b200_io::read_payload(few, v.data(), 4)); CHECK(few.fail());
+        std::stringstream os2;
+        const double vals[3] = {0.1, -2.5, 1e300};
+        CHECK(dcma_b200_io::write_payload(os2, vals, 3)); CHECK(os2.str() == "0.10000000000000001\n-2.5\n1.0000000000000001e+300\n");
     }
     std::printf(g_fail ? "FAILED %d checks\n" : "ALL OK\n", g_fail);
     return g_fail ? 1 : 0;

@@ -120,16 +120,55 @@ def test_native_checks_build_and_report_no_device(tmp_path):
 
 
 def _build_native(outdir):
+    """[plain-C caller of the two entry points, the patched reference writer/reader driven by the reference's cases].  The
+    second is built where /root/reference exists (host/build_host_tests.py::build_field_io) and travels prebuilt."""
+    import sys
+    sys.path.insert(0, HOST)
+    import build_host_tests
     os.makedirs(outdir, exist_ok=True)
     rpath = "-Wl,-rpath," + LIBDIR
-    c_exe, cc_exe = os.path.join(outdir, "text_io_gpu_check"), os.path.join(outdir, "field_io_check")
+    c_exe = os.path.join(outdir, "text_io_gpu_check")
     subprocess.check_call(["gcc", "-O2", "-std=c99", "-Wall", "-D_POSIX_C_SOURCE=200809L", "-I", os.path.join(ROOT, "include"),
                            os.path.join(NATIVE, "text_io_gpu_check.c"), "-o", c_exe, "-L", LIBDIR, "-ldcma_b200", "-lm", rpath])
-    inc = ["-I", os.path.join(HOST, "shim", "dcma_min"), "-I", os.path.join(HOST, "shim", "ygor_min"), "-I", HOST, "-I",
-           os.path.join(ROOT, "include")]
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, os.path.join(NATIVE, "field_io_check.cc"),
-                           os.path.join(HOST, "Alignment_Field_IO.cc"), "-o", cc_exe, "-L", LIBDIR, "-ldcma_b200", rpath])
+    cc_exe = build_host_tests.build_field_io(verbose=False)
+    if cc_exe is None:
+        pytest.skip("reference sources not available and no prebuilt host/_build/field_io_check")
     return [c_exe, cc_exe]
+
+
+def test_patched_reference_writer_reader_host_logic_on_cpu(tmp_path):
+    """The reference's own write_to / read_from with patches/Alignment_Field.patch applied, plus the payload codec's host
+    logic (bounded read-ahead that has to grow, stream left just behind the last number, failure states), run on CPU: the
+    objects of build_field_io are linked against tests/native/fake_text_capi.c (printf / strtod) instead of the GPU
+    library, so this checks everything except the conversion kernels, which the GPU tests check."""
+    import sys
+    sys.path.insert(0, HOST)
+    import build_host_tests
+    if build_host_tests.build_field_io(verbose=False) is None:
+        pytest.skip("reference sources not available")
+    objs = [os.path.join(build_host_tests.OUT, o) for o in ("ref_field_io_patched.o", "field_io_check.o", "Field_Payload.o")]
+    if not all(os.path.isfile(o) for o in objs):
+        pytest.skip("objects of build_field_io not present (prebuilt executable only)")
+    fake = os.path.join(str(tmp_path), "fake_text_capi.o")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-c", os.path.join(NATIVE, "fake_text_capi.c"), "-o", fake])
+    exe = os.path.join(str(tmp_path), "field_io_check_cpu")
+    subprocess.check_call(["g++", "-o", exe, *objs, fake])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_field_patch_is_current():
+    """patches/Alignment_Field.patch is what tools/make_field_patch.py derives from the reference file, and touches only
+    the include list and the two per-value loops."""
+    ref = os.environ.get("DCMA_REFERENCE_SRC", "/root/reference/src")
+    if not os.path.isfile(os.path.join(ref, "Alignment_Field.cc")):
+        pytest.skip("reference sources not available")
+    patch = open(os.path.join(ROOT, "patches", "Alignment_Field.patch")).read()
+    removed = [l[1:].strip() for l in patch.splitlines() if l.startswith("-") and not l.startswith("---")]
+    assert removed == ["for(const auto &val : img.data){", "os << val << '\\n';", "for(auto &val : img.data){", "is >> val;", "}"]
+    out = subprocess.run(["patch", "-s", "-o", "-", os.path.join(ref, "Alignment_Field.cc"), os.path.join(ROOT, "patches", "Alignment_Field.patch")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.count("dcma_b200_io::") == 2
 
 
 # ---- GPU ---------------------------------------------------------------------------------------------------------------

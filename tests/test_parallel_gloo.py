@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dicomautomaton_b200 import parallel
+import _dist_helpers as parallel
 
 
 def _free_port():
@@ -84,7 +84,7 @@ def test_radius_rule_matches_reference():
 def test_library_slab_partition_matches_python_partition():
     """dcma_b200_slab_partition (pure host arithmetic of the C library, no GPU): owned ranges tile the volume, halos are
     clipped at the global faces, and the owned ranges equal parallel.slab_partition."""
-    from dicomautomaton_b200 import capi, parallel
+    from dicomautomaton_b200 import capi
     from dicomautomaton_b200.demons import slab_partition
     for slices, world, halo in ((256, 8, 8), (37, 3, 4), (10, 1, 4), (64, 4, 0)):
         ref = parallel.slab_partition(slices, world)

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/configs.json")
     a = ap.parse_args()
     import torch
-    from dicomautomaton_b200 import parallel, phantom
+    from dicomautomaton_b200 import phantom
     from dicomautomaton_b200.demons import (AlignViaDemons, AlignViaDemonsParams, DemonsEngine, DemonsSlabGroup,
                                             demons_volume, warp_image_with_field)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -115,7 +115,7 @@ def main():
         it = 100
         par = AlignViaDemonsParams(max_iterations=it, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
                                    update_field_smoothing_sigma=1.5, use_diffeomorphic=True, verbosity=0, field_mode=a.mode, device=local)
-        mine = parallel.shard_cases(n_cases, world, rank)
+        mine = list(range(rank, n_cases, world))  # round-robin (config 5)
         eng = DemonsEngine.empty((256, 256, 256), (1.0, 1.0, 1.0), par)
         torch.cuda.synchronize()
         if dist is not None:
