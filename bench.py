@@ -40,8 +40,35 @@ sys.path.insert(0, ROOT)
 WORKLOAD = {"shape": (256, 512, 512), "spacing": (1.0, 1.0, 1.0), "sigma_d": 1.5, "sigma_u": 1.5,
             "diffeomorphic": True}
 # algorithmic bytes per voxel-update, SURVEY.md section 8(d): diffeomorphic, C=1
-B_ALG = {"fp32": 136.0, "fp64": 256.0, "fp64_strict": 256.0}
-FIELD_BYTES = {"fp32": 4, "fp64": 8, "fp64_strict": 8}
+# ("mixed": D and the gradient in double, U in float: force F4+W4+G24+U12 = 44, smooth(U) 24, compose D24+U12+D24 = 60,
+#  smooth(D) 48, warp D24+M4+W4 = 32 -> 208)
+B_ALG = {"fp32": 136.0, "fp64": 256.0, "fp64_strict": 256.0, "mixed": 208.0}
+# storage bytes per element of (the deformation field D, the update field U)
+FIELD_BYTES = {"fp32": (4, 4), "fp64": (8, 8), "fp64_strict": (8, 8), "mixed": (8, 4)}
+DTYPE = {"fp32": "f32", "mixed": "f64 (update field stored as f32)", "fp64": "f64", "fp64_strict": "f64"}
+
+
+def kernel_table(mode, nvox, pst, capi):
+    """Per-kernel roofline rows from the per-stage CUDA-event profile of one step.  Algorithmic bytes per launch are the
+    bytes the kernel has to move by design: force D+M4+F4+U, smooth 2 x field, compose D+U+D."""
+    bd, bu = FIELD_BYTES[mode]
+    smooth_name = {8: "k_smooth3d_tma<double> (TMA-staged separable 3-D Gaussian, one launch per field smooth)",
+                   4: "k_smooth3d<float> (separable 3-D Gaussian, one launch per field smooth)"}
+    spec = [(capi.STAGE_FORCE, "k_warp_force (warp of M through D + fixed gradient + force + MSE)", 3 * bd + 4 + 4 + 3 * bu),
+            (capi.STAGE_SMOOTH_U, smooth_name[bu], 2 * 3 * bu),
+            (capi.STAGE_COMPOSE, "k_compose (diffeomorphic composition)", 2 * 3 * bd + 3 * bu),
+            (capi.STAGE_ADD, "k_add_update", 2 * 3 * bd + 3 * bu),
+            (capi.STAGE_SMOOTH_D, smooth_name[bd], 2 * 3 * bd)]
+    rows = {}
+    for st, name, bpv in spec:
+        n = int(pst.stage_launches[st])
+        if n <= 0:
+            continue
+        r = rows.setdefault(name, {"kernel": name, "ms": 0.0, "launches": 0, "bytes": 0.0})
+        r["ms"] += float(pst.stage_ms[st])
+        r["launches"] += n
+        r["bytes"] += float(bpv) * nvox * n
+    return list(rows.values())
 
 
 def measured_peak_gbs():
@@ -296,23 +323,30 @@ def run_ours(args):
     _, pst = eng.run(args.iters, profile=True)
     stage = {capi.STAGE_NAMES[i]: {"ms": pst.stage_ms[i], "launches": int(pst.stage_launches[i])} for i in range(8)
              if pst.stage_launches[i] > 0}
-    sm_ms = pst.stage_ms[capi.STAGE_SMOOTH_U] + pst.stage_ms[capi.STAGE_SMOOTH_D]
-    sm_n = pst.stage_launches[capi.STAGE_SMOOTH_U] + pst.stage_launches[capi.STAGE_SMOOTH_D]
     peak, peak_src = measured_peak_gbs()
-    alg_bytes_per_launch = 2.0 * 3.0 * nvox * FIELD_BYTES[mode]  # one read + one write of a 3-component field
-    achieved = alg_bytes_per_launch / (sm_ms / max(sm_n, 1) * 1e-3) / 1e9 if sm_n else None
+    rows = kernel_table(mode, nvox, pst, capi)
+    for r in rows:
+        r["ms_per_launch"] = r["ms"] / r["launches"]
+        r["algorithmic_bytes_per_launch"] = r["bytes"] / r["launches"]
+        r["achieved_GBs"] = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        r["frac"] = r["achieved_GBs"] / peak
+        r["share_of_step"] = r["ms"] / max(pst.loop_ms, 1e-9)
+        del r["bytes"]
+    dom = max(rows, key=lambda r: r["ms"])  # the dominant kernel: largest share of the step
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tp):
         try:
-            traffic = json.load(open(tp)).get(mode, {}).get("k_smooth3d_dram_bytes_per_launch")
+            per = json.load(open(tp)).get(mode, {}).get("per_kernel_dram_bytes_per_launch", {})
+            traffic = next((v for k, v in per.items() if dom["kernel"].startswith(k)), None)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_smooth3d (separable 3-D Gaussian, one launch per field smooth)",
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "ms_per_launch": sm_ms / max(sm_n, 1), "share_of_step": sm_ms / max(pst.loop_ms, 1e-9),
+    roofline = {"bound": "hbm", "kernel": dom["kernel"],
+                "achieved": dom["achieved_GBs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "ms_per_launch": dom["ms_per_launch"], "share_of_step": dom["share_of_step"],
+                "per_kernel": rows,
                 "whole_iteration": {"algorithmic_bytes_per_voxel_update": B_ALG[mode],
                                     "achieved_GBs": value / max(world, 1) * B_ALG[mode] / 1e9,
                                     "frac_of_peak": value / max(world, 1) * B_ALG[mode] / 1e9 / peak},
@@ -404,7 +438,7 @@ def run_ours(args):
 
     other = {}
     if not args.no_other_modes:
-        for om in ("fp32",):
+        for om in [m for m in args.other_modes.split(",") if m]:
             if om == mode:
                 continue
             opar = AlignViaDemonsParams(max_iterations=args.iters, convergence_threshold=0.0,
@@ -436,7 +470,7 @@ def run_ours(args):
         line = {"metric": "demons_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if mode != "fp32" else "f32",
+                "dtype": DTYPE[mode],
                 "data": "synthetic", "config": workload_config(args, mode),
                 "ms_per_iteration": ms / max(iters_done, 1), "final_mse": final_mse,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
@@ -647,7 +681,7 @@ def run_slab(args):
         n_it = max(iters_done, 1)
         line = {"metric": "demons_voxel_updates_per_s", "value": value, "unit": "voxel-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64" if mode != "fp32" else "f32",
+                "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[mode],
                 "data": "synthetic", "config": slab_config(args, mode, world, shape),
                 "ms_per_iteration": ms / n_it, "final_mse": final_mse, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "wall_ms_timed_region": wall_ms,
@@ -685,7 +719,8 @@ def main():
                          "FFMA2 smoothing) is ~1.9x faster and is reported beside it in `other_modes`; at full size its "
                          "worst voxel is 1.8e-3 mm off (99.99 %% of voxels within 4e-6 mm), i.e. outside the 1e-3 mm "
                          "tolerance, so it is not the headline")
-    ap.add_argument("--no-other-modes", action="store_true", help="skip the short fp64 run reported beside the headline")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other field modes reported beside the headline")
+    ap.add_argument("--other-modes", default="mixed,fp32", help="field modes reported beside the headline (50-iteration runs)")
     ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the pinned C-ABI end-to-end figure")
     ap.add_argument("--dropin-steps", type=int, default=10, help="timed steps of the AlignViaDemons (drop-in) end-to-end figure")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in end-to-end figure (e2e = the C-ABI figure)")

@@ -33,6 +33,7 @@ UNITS = {
     "engine_f64.cu": [],
     "engine_f64_strict.cu": ["-fmad=false"],
     "engine_f32.cu": [],
+    "engine_mixed.cu": [],
     "slab.cu": [],
     "pyramid.cu": [],
     "warp_grid.cu": [],

@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DCMA_B200_LIB") or os.path.join(HERE, "lib", "libdcma_b200.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
-FIELD_FP64, FIELD_FP64_STRICT, FIELD_FP32 = 0, 1, 2
-FIELD_MODES = {"fp64": FIELD_FP64, "fp64_strict": FIELD_FP64_STRICT, "fp32": FIELD_FP32}
+FIELD_FP64, FIELD_FP64_STRICT, FIELD_FP32, FIELD_MIXED = 0, 1, 2, 3
+FIELD_MODES = {"fp64": FIELD_FP64, "fp64_strict": FIELD_FP64_STRICT, "fp32": FIELD_FP32, "mixed": FIELD_MIXED}
 (STAGE_FORCE, STAGE_SMOOTH_U, STAGE_ADD, STAGE_COMPOSE, STAGE_SMOOTH_D, STAGE_WARP, STAGE_REDUCE,
  STAGE_GRADIENT) = range(8)
 STAGE_NAMES = ["force", "smooth_update", "add_update", "compose", "smooth_deformation", "warp", "reduce", "gradient"]

@@ -32,6 +32,7 @@ EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &
         case DCMA_B200_FIELD_FP64: return make_engine_f64(g, p, stream, slab);
         case DCMA_B200_FIELD_FP64_STRICT: return make_engine_f64_strict(g, p, stream, slab);
         case DCMA_B200_FIELD_FP32: return make_engine_f32(g, p, stream, slab);
+        case DCMA_B200_FIELD_MIXED: return make_engine_mixed(g, p, stream, slab);
         default: throw std::invalid_argument("unknown field_mode");
     }
 }

@@ -417,10 +417,11 @@ __device__ __forceinline__ void apply_stop_rule(Ctrl *ctrl, double sum, long lon
 #ifndef DCMA_FORCE_MINB64
 #define DCMA_FORCE_MINB64 4  // fp64: 64 registers, 4 blocks/SM measured 16 % faster than 80 registers, 3 blocks/SM
 #endif
-template <typename T, bool STRICT, typename IX, bool CH1, bool SYM>
+// TU: storage type of the update field (DCMA_B200_FIELD_MIXED: T = double for D and all arithmetic, TU = float)
+template <typename T, bool STRICT, typename IX, bool CH1, bool SYM, typename TU = T>
 __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_MINB64 : 4))
     k_warp_force(const float *__restrict__ F, const float *__restrict__ M, const float *__restrict__ Wbuf,
-                 const T *__restrict__ D, T *__restrict__ U, const Geo g, const int zlen, const int w_src,
+                 const T *__restrict__ D, TU *__restrict__ U, const Geo g, const int zlen, const int w_src,
                  const ForceK fk, double *part_sum, long long *part_cnt, Ctrl *ctrl, const long long it,
                  const int fused_reduce, double *mse_hist, const long long hist_idx, const int count_iter) {
     constexpr bool symmetric = SYM;  // extension a11: J = (grad F + grad W)/2; needs w_src == 2
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_M
         const IX plane = static_cast<IX>(g.R) * g.C;
         const IX vxy = static_cast<IX>(y) * g.C + x;
         const T *D1 = D + g.N, *D2 = D + 2 * g.N;
-        T *U1 = U + g.N, *U2 = U + 2 * g.N;
+        TU *U1 = U + g.N, *U2 = U + 2 * g.N;
         const AxisK<CT> ak(g);
         const InsideK ik(g);
         const GradK<IX> gk(g, x, y, ch);
@@ -531,17 +532,9 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? DCMA_FORCE_M
                 CT ux, uy, uz, term;
                 int valid;
                 demons_force<STRICT>(fixed_val, moving_val, gx, gy, gz, fk, ux, uy, uz, term, valid);
-#if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
-                // feasibility probe only (tools/build_variant.py): what an fp32-stored update field would do to parity
-                if constexpr (!STRICT) {
-                    ux = static_cast<CT>(static_cast<float>(ux));
-                    uy = static_cast<CT>(static_cast<float>(uy));
-                    uz = static_cast<CT>(static_cast<float>(uz));
-                }
-#endif
-                U[v] = ux;
-                U1[v] = uy;
-                U2[v] = uz;
+                U[v] = static_cast<TU>(ux);
+                U1[v] = static_cast<TU>(uy);
+                U2[v] = static_cast<TU>(uz);
                 acc += term;
                 cnt += valid;
                 f_prev = f_cur;
@@ -721,9 +714,9 @@ __global__ void __launch_bounds__(kTileX *kTileY)
 // ------------------------------------------------------------------------------------------------------------------
 // k_add_update: D[c] += U[c] * pxl_c   (cc:361-366)
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TU = T>
 __global__ void __launch_bounds__(256)
-    k_add_update(T *__restrict__ D, const T *__restrict__ U, const long long N, const double px, const double py,
+    k_add_update(T *__restrict__ D, const TU *__restrict__ U, const long long N, const double px, const double py,
                  const double pz, const Ctrl *__restrict__ ctrl, const long long it) {
     if (it > ctrl->converged_at) return;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -741,9 +734,9 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 // fp64: 24 gathered doubles per voxel put the kernel at ~100 registers (2 blocks/SM); capping it at 85 (3 blocks/SM)
 // measured 3 % faster.  fp32 needs no cap (48 registers).
-template <typename T, bool STRICT, typename IX>
+template <typename T, bool STRICT, typename IX, typename TU = T>
 __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
-    k_compose(T *__restrict__ D, const T *__restrict__ U, const Geo g, const int zlen, Ctrl *__restrict__ ctrl,
+    k_compose(T *__restrict__ D, const TU *__restrict__ U, const Geo g, const int zlen, Ctrl *__restrict__ ctrl,
               const long long it) {
     using CT = T;
     if (it > ctrl->converged_at) return;
@@ -768,16 +761,22 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
     const CT pxl[3] = {ak.px, ak.py, ak.pz};
     // L2 prefetch, one instruction per warp and step (see k_warp_force): lanes 0..3*NL-1 own the lines of U's three
     // components, the next 3*NL lanes those of D's, kPrefetchAhead slices ahead of the slice being composed.
-    constexpr int NL = (sizeof(T) * kTileX + 127) / 128;
+    constexpr int NL = (sizeof(T) * kTileX + 127) / 128, NLU = (sizeof(TU) * kTileX + 127) / 128;
+    static_assert(3 * (NL + NLU) <= kTileX, "one prefetch lane per line");
     const char *pf_ptr = nullptr;
-    const long long pf_step = (threadIdx.x < 6 * NL) ? static_cast<long long>(plane) * static_cast<long long>(sizeof(T)) : 0;
+    long long pf_step = 0;
     {
         const int lane = threadIdx.x;
         const long long row = (static_cast<long long>(z_begin) + kPrefetchAhead) * plane +
                               static_cast<long long>(y) * g.C + blockIdx.x * kTileX;
-        if (lane < 6 * NL) {
-            const int a = lane / (3 * NL), r = lane - a * 3 * NL, c = r / NL, h = r - c * NL;
-            pf_ptr = reinterpret_cast<const char *>((a == 0 ? U : D) + c * N + row) + h * 128;
+        if (lane < 3 * NLU) {
+            const int c = lane / NLU, h = lane - c * NLU;
+            pf_ptr = reinterpret_cast<const char *>(U + c * N + row) + h * 128;
+            pf_step = static_cast<long long>(plane) * static_cast<long long>(sizeof(TU));
+        } else if (lane < 3 * (NLU + NL)) {
+            const int r = lane - 3 * NLU, c = r / NL, h = r - c * NL;
+            pf_ptr = reinterpret_cast<const char *>(D + c * N + row) + h * 128;
+            pf_step = static_cast<long long>(plane) * static_cast<long long>(sizeof(T));
         }
     }
     for (int z = z_begin; z < z_end; ++z, zd += CT(1)) {
@@ -799,10 +798,10 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
             const IX zstep = g.is2d ? IX(0) : plane;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const T *p00 = U + c * N + o00;
-                const T *p10 = p00 + g.C;
-                const T *p01 = p00 + zstep;
-                const T *p11 = p01 + g.C;
+                const TU *p00 = U + c * N + o00;
+                const TU *p10 = p00 + g.C;
+                const TU *p01 = p00 + zstep;
+                const TU *p11 = p01 + g.C;
                 q[c][0] = p00[0];
                 q[c][1] = p00[1];
                 q[c][2] = p10[0];
@@ -834,26 +833,18 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
             const IX r01 = (static_cast<IX>(cz1) * g.R + cy0) * g.C, r11 = (static_cast<IX>(cz1) * g.R + cy1) * g.C;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const T *Uc = U + c * N;
-                q[c][0] = (vz0 && vy0 && vx0) ? Uc[r00 + cx0] : T(0);
-                q[c][1] = (vz0 && vy0 && vx1) ? Uc[r00 + cx1] : T(0);
-                q[c][2] = (vz0 && vy1 && vx0) ? Uc[r10 + cx0] : T(0);
-                q[c][3] = (vz0 && vy1 && vx1) ? Uc[r10 + cx1] : T(0);
+                const TU *Uc = U + c * N;
+                q[c][0] = (vz0 && vy0 && vx0) ? static_cast<CT>(Uc[r00 + cx0]) : CT(0);
+                q[c][1] = (vz0 && vy0 && vx1) ? static_cast<CT>(Uc[r00 + cx1]) : CT(0);
+                q[c][2] = (vz0 && vy1 && vx0) ? static_cast<CT>(Uc[r10 + cx0]) : CT(0);
+                q[c][3] = (vz0 && vy1 && vx1) ? static_cast<CT>(Uc[r10 + cx1]) : CT(0);
                 // slices == 1: z1 == z0, the z0 plane is reused (cc:436-442)
-                q[c][4] = (vz1 && vy0 && vx0) ? Uc[r01 + cx0] : T(0);
-                q[c][5] = (vz1 && vy0 && vx1) ? Uc[r01 + cx1] : T(0);
-                q[c][6] = (vz1 && vy1 && vx0) ? Uc[r11 + cx0] : T(0);
-                q[c][7] = (vz1 && vy1 && vx1) ? Uc[r11 + cx1] : T(0);
+                q[c][4] = (vz1 && vy0 && vx0) ? static_cast<CT>(Uc[r01 + cx0]) : CT(0);
+                q[c][5] = (vz1 && vy0 && vx1) ? static_cast<CT>(Uc[r01 + cx1]) : CT(0);
+                q[c][6] = (vz1 && vy1 && vx0) ? static_cast<CT>(Uc[r11 + cx0]) : CT(0);
+                q[c][7] = (vz1 && vy1 && vx1) ? static_cast<CT>(Uc[r11 + cx1]) : CT(0);
             }
         }
-#if defined(DCMA_EMULATE_MIXED) && DCMA_EMULATE_MIXED
-        if constexpr (!STRICT) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) q[c][i] = static_cast<CT>(static_cast<float>(q[c][i]));
-        }
-#endif
         // prefetch the next slice's displacement before consuming the gathers
         CT dn[3] = {CT(0), CT(0), CT(0)};
         if (z + 1 < z_end) {

@@ -34,8 +34,9 @@ class EngineBase {
     virtual bool update_smoothed() const = 0, deformation_smoothed() const = 0, diffeomorphic() const = 0;
     virtual int smoothing_radius_z(bool update_field) const = 0;
     virtual void *field_base(int buffer) = 0;     // DCMA_B200_BUF_UPDATE / _DEFORMATION: device pointer of component 0
-    virtual void *field_allocation(int i) = 0;    // the three field allocations (fixed identity; their roles rotate)
-    virtual int64_t field_elem_size() const = 0;  // 4 or 8
+    virtual int field_allocation_count() const = 0;  // 3, or 4 when U and D differ in type (DCMA_B200_FIELD_MIXED)
+    virtual void *field_allocation(int i) = 0;    // the field allocations (fixed identity; their roles rotate)
+    virtual int64_t field_elem_size(int buffer) const = 0;  // 4 or 8, of DCMA_B200_BUF_UPDATE / _DEFORMATION
     virtual int64_t field_comp_stride() const = 0, plane_elems() const = 0;
     virtual void *stream_handle() = 0;
     virtual void get_owned_deformation(double *host_aos) = 0;  // owned slices only, AoS doubles
@@ -59,6 +60,7 @@ class EngineBase {
 EngineBase *make_engine_f64(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
 EngineBase *make_engine_f64_strict(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
 EngineBase *make_engine_f32(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
+EngineBase *make_engine_mixed(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
 EngineBase *make_engine(const dcma_b200_geom &g, const dcma_b200_demons_params &p, void *stream, const SlabSpec &slab);
 
 // warp_moving semantics on host buffers (strict fp64 translation unit)

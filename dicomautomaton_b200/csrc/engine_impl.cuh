@@ -1,5 +1,7 @@
-// dcma_b200 -- Engine<T, STRICT>: owns the HBM buffers and launches the kernels of one registration.
-// Included by exactly three translation units (engine_f64.cu, engine_f64_strict.cu, engine_f32.cu), each with its own
+// dcma_b200 -- Engine<T, STRICT, TU>: owns the HBM buffers and launches the kernels of one registration.  T is the storage
+// and arithmetic type of the deformation field D, TU the storage type of the update field U (== T except in
+// DCMA_B200_FIELD_MIXED, where D stays double and U is stored and smoothed as float).
+// Included by exactly four translation units (engine_f64.cu, engine_f64_strict.cu, engine_f32.cu, engine_mixed.cu), each with its own
 // DCMA_NS so that no device function compiled with different flags (-fmad=false for STRICT) can be shared by accident.
 //
 // Mirrors the reference engine (src/Alignment_Demons.cc:52-704):
@@ -15,6 +17,7 @@
 #include <limits>
 #include <map>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "demons_kernels.cuh"
@@ -44,8 +47,10 @@ struct SmoothPlan {
     double *dw[3] = {nullptr, nullptr, nullptr};    // weights in global memory for k_smooth_axis
 };
 
-template <typename T, bool STRICT>
+template <typename T, bool STRICT, typename TU = T>
 class Engine final : public EngineBase {
+    static constexpr bool kSameU = std::is_same<T, TU>::value;
+
   public:
     Engine(const dcma_b200_geom &geom, const dcma_b200_demons_params &params, void *stream_in, const SlabSpec &slab_in)
         : p_(params), slab_(slab_in) {
@@ -124,11 +129,16 @@ class Engine final : public EngineBase {
         dF_ = alloc<float>(N * g_.CH);
         dM_ = alloc<float>(Ng * g_.CH);  // the moving image is always held whole: the warp gathers have no a-priori bound
         dD_ = alloc<T>(3 * N);
-        dU_ = alloc<T>(3 * N);
+        dU_ = alloc<TU>(3 * N);
         dTmp_ = alloc<T>(3 * N);
         field_alloc_[0] = dD_;
         field_alloc_[1] = dU_;
         field_alloc_[2] = dTmp_;
+        if constexpr (!kSameU) {  // U cannot share D's scratch field: its own, in its own type (same total bytes as 3 x T)
+            dTmpU_ = alloc<TU>(3 * N);
+            field_alloc_[3] = dTmpU_;
+            n_field_alloc_ = 4;
+        }
         // slack: a force stage split into up to kMaxForceParts z-ranges rounds each range up to whole z-chunks
         part_cap_ = grid_vox_ + kMaxForceParts * static_cast<int>(per_plane);
         d_part_sum_ = alloc<double>(part_cap_);
@@ -140,7 +150,7 @@ class Engine final : public EngineBase {
         build_plan(plan_d_, p_.deformation_field_smoothing_sigma);
         reset_ctrl();
         DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * N, stream_));
-        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(T) * 3 * N, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(TU) * 3 * N, stream_));
     }
 
     ~Engine() override {
@@ -174,7 +184,7 @@ class Engine final : public EngineBase {
                                   stream_));
         DCMA_CUDA(cudaMemcpyAsync(dM_, moving, sizeof(float) * Ng_ * g_.CH, kind, stream_));
         DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * g_.N, stream_));
-        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(T) * 3 * g_.N, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(TU) * 3 * g_.N, stream_));
         w_src_ = 0;  // W := M (cc:183)
         reset_ctrl();
         if (!on_device) DCMA_CUDA(cudaStreamSynchronize(stream_));  // host buffers may be released by the caller
@@ -248,6 +258,7 @@ class Engine final : public EngineBase {
             dD_ = r.d;
             dU_ = r.u;
             dTmp_ = r.tmp;
+            dTmpU_ = r.tmpu;
         }
         rot_hist_.clear();
         if (mse_history_host && done > 0)
@@ -295,7 +306,7 @@ class Engine final : public EngineBase {
                 launch_force(w_src_, it, d_hist_, it, global_mse ? 0 : 1, /*reduce=*/false, /*fused_reduce=*/true);
                 break;
             case IterStage::SmoothU:
-                if (diffeo && plan_u_.active) smooth(dU_, plan_u_, it);
+                if (diffeo && plan_u_.active) smooth(dU_, tmp_u(), plan_u_, it);
                 break;
             case IterStage::Update:
                 if (diffeo)
@@ -304,7 +315,7 @@ class Engine final : public EngineBase {
                     launch_add(it);
                 break;
             case IterStage::SmoothD:
-                if (plan_d_.active) smooth(dD_, plan_d_, it);
+                if (plan_d_.active) smooth(dD_, dTmp_, plan_d_, it);
                 w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
                 record_rotation(it);
                 break;
@@ -348,8 +359,11 @@ class Engine final : public EngineBase {
     bool diffeomorphic() const override { return p_.use_diffeomorphic != 0; }
     int smoothing_radius_z(bool update_field) const override { return update_field ? plan_u_.r[2] : plan_d_.r[2]; }
     void *field_base(int buffer) override { return buffer == DCMA_B200_BUF_UPDATE ? static_cast<void *>(dU_) : static_cast<void *>(dD_); }
+    int field_allocation_count() const override { return n_field_alloc_; }
     void *field_allocation(int i) override { return field_alloc_[i]; }
-    int64_t field_elem_size() const override { return static_cast<int64_t>(sizeof(T)); }
+    int64_t field_elem_size(int buffer) const override {
+        return static_cast<int64_t>(buffer == DCMA_B200_BUF_UPDATE ? sizeof(TU) : sizeof(T));
+    }
     int64_t field_comp_stride() const override { return g_.N; }
     int64_t plane_elems() const override { return static_cast<int64_t>(g_.R) * g_.C; }
     void *stream_handle() override { return stream_; }
@@ -377,8 +391,10 @@ class Engine final : public EngineBase {
             }
             case DCMA_B200_STAGE_SMOOTH_U:
             case DCMA_B200_STAGE_SMOOTH_D: {
-                SmoothPlan<T> &pl = plan_for(sigma_mm);
-                smooth(stage == DCMA_B200_STAGE_SMOOTH_U ? dU_ : dD_, pl, it);
+                if (stage == DCMA_B200_STAGE_SMOOTH_U)
+                    smooth(dU_, tmp_u(), plan_for<TU>(sigma_mm), it);
+                else
+                    smooth(dD_, dTmp_, plan_for<T>(sigma_mm), it);
                 break;
             }
             case DCMA_B200_STAGE_ADD: launch_add(it); break;
@@ -418,7 +434,10 @@ class Engine final : public EngineBase {
             }
             case DCMA_B200_BUF_UPDATE:
             case DCMA_B200_BUF_DEFORMATION:
-                export_field_host(buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_, static_cast<double *>(host));
+                if (buffer == DCMA_B200_BUF_UPDATE)
+                    export_field_host(dU_, static_cast<double *>(host));
+                else
+                    export_field_host(dD_, static_cast<double *>(host));
                 break;
             default: throw std::invalid_argument("unknown buffer id");
         }
@@ -442,7 +461,10 @@ class Engine final : public EngineBase {
                 break;
             case DCMA_B200_BUF_UPDATE:
             case DCMA_B200_BUF_DEFORMATION:
-                import_field_host(static_cast<const double *>(host), buffer == DCMA_B200_BUF_UPDATE ? dU_ : dD_);
+                if (buffer == DCMA_B200_BUF_UPDATE)
+                    import_field_host(static_cast<const double *>(host), dU_);
+                else
+                    import_field_host(static_cast<const double *>(host), dD_);
                 break;
             default: throw std::invalid_argument("buffer is not writable");
         }
@@ -473,7 +495,8 @@ class Engine final : public EngineBase {
         if (!d_stage_[half]) d_stage_[half] = alloc<double>(3 * kStageVoxels);
         return d_stage_[half];
     }
-    void export_field_host(const T *field, double *host) {
+    template <typename X>
+    void export_field_host(const X *field, double *host) {
         if (!ev_stage_[0]) {
             DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[0], cudaEventDisableTiming));
             DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[1], cudaEventDisableTiming));
@@ -489,7 +512,7 @@ class Engine final : public EngineBase {
             double *st = staging(half);
             // the kernel may overwrite this half only after the copy that last read it has finished
             DCMA_CUDA(cudaStreamWaitEvent(stream_, ev_stage_[half], 0));
-            k_export_aos<T><<<grid_lin_, 256, 0, stream_>>>(field, st, g_.N, v0, v1);
+            k_export_aos<X><<<grid_lin_, 256, 0, stream_>>>(field, st, g_.N, v0, v1);
             DCMA_CUDA(cudaGetLastError());
             DCMA_CUDA(cudaEventRecord(done, stream_));
             DCMA_CUDA(cudaStreamWaitEvent(copy_stream_, done, 0));
@@ -500,13 +523,14 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaStreamSynchronize(stream_));
         cudaEventDestroy(done);
     }
-    void import_field_host(const double *host, T *field) {
+    template <typename X>
+    void import_field_host(const double *host, X *field) {
         const long long vb = owned_v0(), ve = owned_v1();
         for (long long v0 = vb; v0 < ve; v0 += kStageVoxels) {
             const long long v1 = std::min(ve, v0 + kStageVoxels);
             double *st = staging(0);
             DCMA_CUDA(cudaMemcpyAsync(st, host + 3 * (v0 - vb), sizeof(double) * 3 * (v1 - v0), cudaMemcpyHostToDevice, stream_));
-            k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(st, field, g_.N, v0, v1);
+            k_import_aos<X><<<grid_lin_, 256, 0, stream_>>>(st, field, g_.N, v0, v1);
             DCMA_CUDA(cudaGetLastError());
         }
         DCMA_CUDA(cudaStreamSynchronize(stream_));
@@ -552,7 +576,8 @@ class Engine final : public EngineBase {
     }
 
     // Gaussian weights and per-position weight sums, cc:574-600 (host side, identical arithmetic and order).
-    void build_plan(SmoothPlan<T> &pl, double sigma_mm) {
+    template <typename X>
+    void build_plan(SmoothPlan<X> &pl, double sigma_mm) {
         pl.active = (sigma_mm > 0.0);
         if (!pl.active) return;
         const double pxl[3] = {g_.px, g_.py, g_.pz};
@@ -583,35 +608,56 @@ class Engine final : public EngineBase {
             for (int a = 0; a < 3; ++a) {
                 const int rad = pl.r[a];
                 pl.W.r[a] = rad;
-                for (int k = 0; k < 2 * kMaxFastRadius + 1; ++k) pl.W.w[a][k] = T(0);
-                for (int k = -rad; k <= rad; ++k) pl.W.w[a][k + rk] = static_cast<T>(pl.w[a][k + rad]);
+                for (int k = 0; k < 2 * kMaxFastRadius + 1; ++k) pl.W.w[a][k] = X(0);
+                for (int k = -rad; k <= rad; ++k) pl.W.w[a][k + rk] = static_cast<X>(pl.w[a][k + rad]);
                 const int padded = ((extent[a] + 127) / 128) * 128 + 128;  // whole tiles: the kernel never tests bounds
-                std::vector<T> tab(padded, T(1));
+                std::vector<X> tab(padded, X(1));
                 for (int pos = 0; pos < extent[a]; ++pos) {
                     // in-order accumulation over the in-grid taps, in the kernel's own type (cc:620-631); the padded
                     // zero weights leave the sum unchanged
-                    T wsum = 0;
+                    X wsum = 0;
                     for (int k = -rk; k <= rk; ++k) {
                         const int q = pos + k;
                         if (q >= 0 && q < extent[a]) wsum += pl.W.w[a][k + rk];
                     }
-                    tab[pos] = STRICT ? wsum : static_cast<T>(1.0 / static_cast<double>(wsum));
+                    tab[pos] = STRICT ? wsum : static_cast<X>(1.0 / static_cast<double>(wsum));
                 }
-                pl.tab[a] = alloc<T>(padded);
-                DCMA_CUDA(cudaMemcpy(pl.tab[a], tab.data(), sizeof(T) * tab.size(), cudaMemcpyHostToDevice));
+                pl.tab[a] = alloc<X>(padded);
+                DCMA_CUDA(cudaMemcpy(pl.tab[a], tab.data(), sizeof(X) * tab.size(), cudaMemcpyHostToDevice));
             }
         }
     }
 
-    SmoothPlan<T> &plan_for(double sigma_mm) {
-        if (sigma_mm == p_.update_field_smoothing_sigma) return plan_u_;
-        if (sigma_mm == p_.deformation_field_smoothing_sigma) return plan_d_;
-        auto it = extra_plans_.find(sigma_mm);
-        if (it == extra_plans_.end()) {
-            it = extra_plans_.emplace(sigma_mm, SmoothPlan<T>()).first;
+    // plans of the stage API, per element type of the field being smoothed
+    template <typename X>
+    SmoothPlan<X> &plan_for(double sigma_mm) {
+        if constexpr (std::is_same<X, TU>::value) {
+            if (sigma_mm == p_.update_field_smoothing_sigma) return plan_u_;
+        }
+        if constexpr (std::is_same<X, T>::value) {
+            if (sigma_mm == p_.deformation_field_smoothing_sigma) return plan_d_;
+        }
+        auto &plans = extra_plans<X>();
+        auto it = plans.find(sigma_mm);
+        if (it == plans.end()) {
+            it = plans.emplace(sigma_mm, SmoothPlan<X>()).first;
             build_plan(it->second, sigma_mm);
         }
         return it->second;
+    }
+    template <typename X>
+    std::map<double, SmoothPlan<X>> &extra_plans() {
+        if constexpr (std::is_same<X, T>::value)
+            return extra_plans_;
+        else
+            return extra_plans_u_;
+    }
+    // scratch field of the update-field smoothing: D's scratch when both fields have one type
+    TU *&tmp_u() {
+        if constexpr (kSameU)
+            return dTmp_;
+        else
+            return dTmpU_;
     }
 
     void prof_begin(int stage) {
@@ -669,7 +715,7 @@ class Engine final : public EngineBase {
         }
         if (diffeo && plan_u_.active) {
             prof_begin(DCMA_B200_STAGE_SMOOTH_U);
-            smooth(dU_, plan_u_, it);
+            smooth(dU_, tmp_u(), plan_u_, it);
             prof_end();
         }
         if (!diffeo) {
@@ -683,7 +729,7 @@ class Engine final : public EngineBase {
         }
         if (plan_d_.active) {
             prof_begin(DCMA_B200_STAGE_SMOOTH_D);
-            smooth(dD_, plan_d_, it);
+            smooth(dD_, dTmp_, plan_d_, it);
             prof_end();
         }
         w_src_ = 1;  // the next force kernel warps M through the new D (cc:106)
@@ -692,12 +738,15 @@ class Engine final : public EngineBase {
 
     // which allocation plays D / U / scratch after loop iteration `it` (the smoothing calls swap pointers)
     struct Rotation {
-        T *d, *u, *tmp;
+        T *d;
+        TU *u;
+        T *tmp;
+        TU *tmpu;
     };
     void record_rotation(long long it) {
         if (it < 0) return;
-        if (rot_hist_.size() <= static_cast<size_t>(it)) rot_hist_.resize(static_cast<size_t>(it) + 1, Rotation{dD_, dU_, dTmp_});
-        rot_hist_[static_cast<size_t>(it)] = Rotation{dD_, dU_, dTmp_};
+        if (rot_hist_.size() <= static_cast<size_t>(it)) rot_hist_.resize(static_cast<size_t>(it) + 1, Rotation{dD_, dU_, dTmp_, dTmpU_});
+        rot_hist_[static_cast<size_t>(it)] = Rotation{dD_, dU_, dTmp_, dTmpU_};
     }
 
     // zr0/zr1 >= 0: only the owned slices [zr0, zr1) (local indices), MSE partials written from `part_off` on (the caller
@@ -724,7 +773,7 @@ class Engine final : public EngineBase {
         double *psum = d_part_sum_ + part_off;
         long long *pcnt = d_part_cnt_ + part_off;
 #define DCMA_LAUNCH_FORCE2(IX, CH1, SYM)                                                                             \
-    k_warp_force<T, STRICT, IX, CH1, SYM><<<grid, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, gq, zlen_, w_src, fk, psum, \
+    k_warp_force<T, STRICT, IX, CH1, SYM, TU><<<grid, blk, 0, stream_>>>(dF_, dM_, dW_, dD_, dU_, gq, zlen_, w_src, fk, psum, \
                                                                        pcnt, d_ctrl_, it, fused_reduce ? 1 : 0, d_hist, \
                                                                        hist_idx, count_iter)
 #define DCMA_LAUNCH_FORCE(IX, CH1)                            \
@@ -753,7 +802,7 @@ class Engine final : public EngineBase {
         ++launches_;
     }
     void launch_add(long long it) {
-        k_add_update<T><<<grid_lin_, 256, 0, stream_>>>(dD_, dU_, g_.N, g_.px, g_.py, g_.pz, d_ctrl_, it);
+        k_add_update<T, TU><<<grid_lin_, 256, 0, stream_>>>(dD_, dU_, g_.N, g_.px, g_.py, g_.pz, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -767,9 +816,9 @@ class Engine final : public EngineBase {
             grid.z = static_cast<unsigned>((zr1 - zr0 + zlen_ - 1) / zlen_);
         }
         if (small_index_)
-            k_compose<T, STRICT, int><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
+            k_compose<T, STRICT, int, TU><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
         else
-            k_compose<T, STRICT, long long><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
+            k_compose<T, STRICT, long long, TU><<<grid, dim3(kTileX, kTileY), 0, stream_>>>(dD_, dU_, gq, zlen_, d_ctrl_, it);
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -809,31 +858,32 @@ class Engine final : public EngineBase {
     }
 
     // smooth_on_device, cc:563-702.  Result ends in `field` (pointer swap instead of the reference's copy-back).
-    void smooth(T *&field, SmoothPlan<T> &pl, long long it) {
+    template <typename X>
+    void smooth(X *&field, X *&tmp, SmoothPlan<X> &pl, long long it) {
         if (!pl.active) return;
         if (pl.fast) {
-            launch_smooth3d(field, dTmp_, pl, it);
-            std::swap(field, dTmp_);
+            launch_smooth3d(field, tmp, pl, it);
+            std::swap(field, tmp);
         } else {
-            T *bufs[2] = {field, dTmp_};
+            X *bufs[2] = {field, tmp};
             for (int a = 0; a < 3; ++a) {  // x: field->tmp (cc:609), y: tmp->field (cc:638), z: field->tmp (cc:667)
-                k_smooth_axis<T><<<grid_lin_, 256, 0, stream_>>>(bufs[a & 1], bufs[(a + 1) & 1], g_, a, pl.r[a], pl.dw[a],
+                k_smooth_axis<X><<<grid_lin_, 256, 0, stream_>>>(bufs[a & 1], bufs[(a + 1) & 1], g_, a, pl.r[a], pl.dw[a],
                                                               d_ctrl_, it);
                 DCMA_CUDA(cudaGetLastError());
                 ++launches_;
             }
-            // three passes: field -> tmp -> field -> tmp; the result is in dTmp_
-            std::swap(field, dTmp_);
+            // three passes: field -> tmp -> field -> tmp; the result is in tmp
+            std::swap(field, tmp);
         }
     }
 
-    template <int R, int TX, int TY, int NT, int MINB, bool VEC>
-    void launch_smooth3d_cfg(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
-        using Cfg = Smooth3dCfg<T, R, TX, TY, NT>;
-        constexpr bool WS = (DCMA_SMOOTH_WS < 0) ? (sizeof(T) == 8) : (DCMA_SMOOTH_WS != 0);
+    template <typename X, int R, int TX, int TY, int NT, int MINB, bool VEC>
+    void launch_smooth3d_cfg(const X *in, X *out, const SmoothPlan<X> &pl, long long it) {
+        using Cfg = Smooth3dCfg<X, R, TX, TY, NT>;
+        constexpr bool WS = (DCMA_SMOOTH_WS < 0) ? (sizeof(X) == 8) : (DCMA_SMOOTH_WS != 0);
         constexpr int NTL = WS ? 2 * NT : NT;  // threads per CTA at launch
         constexpr size_t SMEM = WS ? Cfg::smem_bytes_ws : Cfg::smem_bytes;
-        auto kern = k_smooth3d<T, STRICT, R, TX, TY, NT, (WS ? 2 : MINB), VEC, WS>;
+        auto kern = k_smooth3d<X, STRICT, R, TX, TY, NT, (WS ? 2 : MINB), VEC, WS>;
         static thread_local bool attr_set[64] = {false};
         if (!attr_set[dev_ & 63]) {
             DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM)));
@@ -889,7 +939,8 @@ class Engine final : public EngineBase {
         return fn;
     }
     // the field as a 4-D tensor {x, y, z, component}; one box = one staged slice tile (+halo), out-of-grid -> zeros
-    const CUtensorMap *tensor_map(const T *base, int box_x, int box_y) {
+    template <typename X>
+    const CUtensorMap *tensor_map(const X *base, int box_x, int box_y) {
         const auto key = std::make_tuple(static_cast<const void *>(base), box_x, box_y);
         auto itm = tmaps_.find(key);
         if (itm != tmaps_.end()) return &itm->second;
@@ -897,32 +948,33 @@ class Engine final : public EngineBase {
         if (!enc) return nullptr;
         CUtensorMap m;
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(g_.C), static_cast<cuuint64_t>(g_.R), static_cast<cuuint64_t>(g_.S), 3};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g_.C) * sizeof(T),
-                                       static_cast<cuuint64_t>(g_.R) * g_.C * sizeof(T),
-                                       static_cast<cuuint64_t>(g_.N) * sizeof(T)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g_.C) * sizeof(X),
+                                       static_cast<cuuint64_t>(g_.R) * g_.C * sizeof(X),
+                                       static_cast<cuuint64_t>(g_.N) * sizeof(X)};
         const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_x), static_cast<cuuint32_t>(box_y), 1, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<T *>(base), dims, strides, box, estr,
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<X *>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return nullptr;
         return &tmaps_.emplace(key, m).first->second;
     }
-    bool tma_usable(const T *in) const {
-        return DCMA_SMOOTH_TMA != 0 && sizeof(T) == 8 && (g_.C % 2) == 0 && (reinterpret_cast<uintptr_t>(in) % 16) == 0 &&
+    template <typename X>
+    bool tma_usable(const X *in) const {
+        return DCMA_SMOOTH_TMA != 0 && sizeof(X) == 8 && (g_.C % 2) == 0 && (reinterpret_cast<uintptr_t>(in) % 16) == 0 &&
                (g_.N % 2) == 0 && g_.C >= 2;
     }
-    template <int R>
-    bool launch_smooth3d_tma(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
-        if constexpr (sizeof(T) != 8 || R > 4) {
+    template <typename X, int R>
+    bool launch_smooth3d_tma(const X *in, X *out, const SmoothPlan<X> &pl, long long it) {
+        if constexpr (sizeof(X) != 8 || R > 4) {
             return false;
         } else {
             constexpr int TX = DCMA_TMA_TX, TY = DCMA_TMA_TY, OY = DCMA_TMA_OY, NS = DCMA_TMA_NS, NXB = DCMA_TMA_NXB;
-            using Cfg = SmoothTmaCfg<T, R, TX, TY, OY, NS, NXB>;
+            using Cfg = SmoothTmaCfg<X, R, TX, TY, OY, NS, NXB>;
             if (!tma_usable(in)) return false;
             const CUtensorMap *tm = tensor_map(in, Cfg::PWP, Cfg::PH);
             if (!tm) return false;
-            auto kern = k_smooth3d_tma<T, STRICT, R, TX, TY, OY, NS, NXB>;
+            auto kern = k_smooth3d_tma<X, STRICT, R, TX, TY, OY, NS, NXB>;
             static thread_local bool attr_set[64] = {false};
             if (!attr_set[dev_ & 63]) {
                 DCMA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::smem_bytes)));
@@ -978,31 +1030,32 @@ class Engine final : public EngineBase {
         nz = (So + zchunk - 1) / zchunk;
     }
 
-    template <int R>
-    void launch_smooth3d_r(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+    template <typename X, int R>
+    void launch_smooth3d_r(const X *in, X *out, const SmoothPlan<X> &pl, long long it) {
         // NT = 128 threads per role, 2 adjacent output rows x one 16-byte vector per thread; the register z window
         // (72 registers) puts the one-role kernel at ~165 registers, so 3 CTAs/SM (fp32); the warp-specialised form
         // (fp64) launches 2*NT threads, 2 CTAs/SM.  float: 64x16 tile; double: 32x16 tile.
-        constexpr int TX = (sizeof(T) == 4) ? 64 : 32;
+        constexpr int TX = (sizeof(X) == 4) ? 64 : 32;
         constexpr int TY = DCMA_SMOOTH_TY;
         constexpr int NT = DCMA_SMOOTH_NT;
         constexpr int MINB = DCMA_SMOOTH_MINB;
-        if (launch_smooth3d_tma<R>(in, out, pl, it)) return;
-        const bool vec = (g_.C % static_cast<int>(16 / sizeof(T)) == 0);
+        if (launch_smooth3d_tma<X, R>(in, out, pl, it)) return;
+        const bool vec = (g_.C % static_cast<int>(16 / sizeof(X)) == 0);
         if (vec)
-            launch_smooth3d_cfg<R, TX, TY, NT, MINB, true>(in, out, pl, it);
+            launch_smooth3d_cfg<X, R, TX, TY, NT, MINB, true>(in, out, pl, it);
         else
-            launch_smooth3d_cfg<R, TX, TY, NT, MINB, false>(in, out, pl, it);
+            launch_smooth3d_cfg<X, R, TX, TY, NT, MINB, false>(in, out, pl, it);
     }
 
-    void launch_smooth3d(const T *in, T *out, const SmoothPlan<T> &pl, long long it) {
+    template <typename X>
+    void launch_smooth3d(const X *in, X *out, const SmoothPlan<X> &pl, long long it) {
         switch (pl.rk) {
-            case 1: launch_smooth3d_r<1>(in, out, pl, it); break;
-            case 2: launch_smooth3d_r<2>(in, out, pl, it); break;
-            case 3: launch_smooth3d_r<3>(in, out, pl, it); break;
-            case 4: launch_smooth3d_r<4>(in, out, pl, it); break;
-            case 5: launch_smooth3d_r<5>(in, out, pl, it); break;
-            case 6: launch_smooth3d_r<6>(in, out, pl, it); break;
+            case 1: launch_smooth3d_r<X, 1>(in, out, pl, it); break;
+            case 2: launch_smooth3d_r<X, 2>(in, out, pl, it); break;
+            case 3: launch_smooth3d_r<X, 3>(in, out, pl, it); break;
+            case 4: launch_smooth3d_r<X, 4>(in, out, pl, it); break;
+            case 5: launch_smooth3d_r<X, 5>(in, out, pl, it); break;
+            case 6: launch_smooth3d_r<X, 6>(in, out, pl, it); break;
             default: throw std::logic_error("fast smoothing radius out of range");
         }
     }
@@ -1029,16 +1082,20 @@ class Engine final : public EngineBase {
     static constexpr int kMaxForceParts = 4;
     int force_parts_ = 0;  // partials written by the force_range calls of the current iteration
     float *dF_ = nullptr, *dM_ = nullptr, *dW_ = nullptr;
-    T *dD_ = nullptr, *dU_ = nullptr, *dTmp_ = nullptr;
-    void *field_alloc_[3] = {nullptr, nullptr, nullptr};
+    T *dD_ = nullptr, *dTmp_ = nullptr;
+    TU *dU_ = nullptr, *dTmpU_ = nullptr;  // dTmpU_: only when TU != T
+    void *field_alloc_[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_field_alloc_ = 3;
     double *d_part_sum_ = nullptr;
     long long *d_part_cnt_ = nullptr;
     Ctrl *d_ctrl_ = nullptr, *h_ctrl_ = nullptr;
     double *d_stage_[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage_[2] = {nullptr, nullptr};
     cudaStream_t copy_stream_ = nullptr;
-    SmoothPlan<T> plan_u_, plan_d_;
+    SmoothPlan<TU> plan_u_;
+    SmoothPlan<T> plan_d_;
     std::map<double, SmoothPlan<T>> extra_plans_;
+    std::map<double, SmoothPlan<TU>> extra_plans_u_;  // used only when TU != T
     std::map<std::tuple<const void *, int, int>, CUtensorMap> tmaps_;
     int w_src_ = 0;
     std::vector<void *> allocs_;

@@ -227,7 +227,7 @@ SlabGroup::~SlabGroup() {
         if (l->ev_done) cudaEventDestroy(l->ev_done);
         l->eng.reset();
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kMaxFieldAllocs; ++i) {
         if (peer_lo_[i]) cudaIpcCloseMemHandle(peer_lo_[i]);
         if (peer_hi_[i]) cudaIpcCloseMemHandle(peer_hi_[i]);
     }
@@ -321,7 +321,7 @@ void SlabGroup::setup_ipc() {
     DCMA_CUDA(cudaSetDevice(l.device));
     cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
     struct Rec {
-        cudaIpcMemHandle_t h[4];  // the three field allocations + the flag block
+        cudaIpcMemHandle_t h[kMaxFieldAllocs + 1];  // the field allocations (3, or 4 in mixed mode) + the flag block (last)
         int ok;
         int pad[3];
     };
@@ -330,11 +330,15 @@ void SlabGroup::setup_ipc() {
     Rec mine;
     std::memset(&mine, 0, sizeof(mine));
     mine.ok = 1;
-    for (int i = 0; i < 4; ++i)
-        if (cudaIpcGetMemHandle(&mine.h[i], i < 3 ? e->field_allocation(i) : static_cast<void *>(d_flags_)) != cudaSuccess) {
+    const int nf = e->field_allocation_count();
+    if (nf > kMaxFieldAllocs) throw std::logic_error("more field allocations than the slab group can map");
+    for (int i = 0; i <= kMaxFieldAllocs; ++i) {
+        if (i >= nf && i < kMaxFieldAllocs) continue;
+        if (cudaIpcGetMemHandle(&mine.h[i], i < nf ? e->field_allocation(i) : static_cast<void *>(d_flags_)) != cudaSuccess) {
             cudaGetLastError();
             mine.ok = 0;
         }
+    }
     Rec *d_all = nullptr, *d_mine = nullptr;
     DCMA_CUDA(cudaMalloc(&d_all, sizeof(Rec) * world_));
     DCMA_CUDA(cudaMalloc(&d_mine, sizeof(Rec)));
@@ -347,13 +351,14 @@ void SlabGroup::setup_ipc() {
     DCMA_CUDA(cudaStreamSynchronize(st));
     int ok = 1;
     for (auto &r : all) ok &= r.ok;
-    auto open_peer = [&](int peer, void *out[3], unsigned **flags) {
-        for (int i = 0; i < 4 && ok; ++i) {
+    auto open_peer = [&](int peer, void **out, unsigned **flags) {
+        for (int i = 0; i <= kMaxFieldAllocs && ok; ++i) {
+            if (i >= nf && i < kMaxFieldAllocs) continue;
             void *ptr = nullptr;
             if (cudaIpcOpenMemHandle(&ptr, all[peer].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
-            } else if (i < 3) {
+            } else if (i < nf) {
                 out[i] = ptr;
             } else {
                 *flags = static_cast<unsigned *>(ptr);
@@ -398,12 +403,12 @@ void SlabGroup::exchange_flags(int buffer, int64_t n, cudaStream_t st) {
     Local &l = *locals_[0];
     EngineBase *e = l.eng.get();
     const SlabSpec s = e->slab();
-    const int64_t pe = e->plane_elems(), es = e->field_elem_size();
+    const int64_t pe = e->plane_elems(), es = e->field_elem_size(buffer);
     const size_t bytes = static_cast<size_t>(n) * pe * es;
     const bool lo = (l.rank > 0), hi = (l.rank + 1 < world_);
     DCMA_CUDA(cudaSetDevice(l.device));
-    int idx = -1;  // which of the three allocations currently plays `buffer` (the roles rotate identically on all ranks)
-    for (int i = 0; i < 3; ++i)
+    int idx = -1;  // which of the field allocations currently plays `buffer` (the roles rotate identically on all ranks)
+    for (int i = 0; i < e->field_allocation_count(); ++i)
         if (e->field_allocation(i) == e->field_base(buffer)) idx = i;
     if (idx < 0) throw std::logic_error("field buffer is not one of the engine's allocations");
     const unsigned id = ++xid_;
@@ -513,7 +518,7 @@ void SlabGroup::load(const float *fixed, const float *moving, bool on_device) {
 
 // planes [l0, l0 + n) of component c of `buffer`
 static inline char *plane_ptr(EngineBase *e, int buffer, int c, int64_t l0) {
-    return static_cast<char *>(e->field_base(buffer)) + (c * e->field_comp_stride() + l0 * e->plane_elems()) * e->field_elem_size();
+    return static_cast<char *>(e->field_base(buffer)) + (c * e->field_comp_stride() + l0 * e->plane_elems()) * e->field_elem_size(buffer);
 }
 
 void SlabGroup::exchange(int buffer, int64_t n) {
@@ -530,12 +535,12 @@ void SlabGroup::exchange(int buffer, int64_t n) {
         Local &l = *locals_[0];
         EngineBase *e = l.eng.get();
         const SlabSpec s = e->slab();
-        const int64_t pe = e->plane_elems(), es = e->field_elem_size();
+        const int64_t pe = e->plane_elems(), es = e->field_elem_size(buffer);
         const size_t bytes = static_cast<size_t>(n) * pe * es;
         cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
         DCMA_CUDA(cudaSetDevice(l.device));
-        int idx = -1;  // which of the three allocations currently plays `buffer` (the roles rotate identically on all ranks)
-        for (int i = 0; i < 3; ++i)
+        int idx = -1;  // which of the field allocations currently plays `buffer` (the roles rotate identically on all ranks)
+        for (int i = 0; i < e->field_allocation_count(); ++i)
             if (e->field_allocation(i) == e->field_base(buffer)) idx = i;
         if (idx < 0) throw std::logic_error("field buffer is not one of the engine's allocations");
         token_sync();
@@ -562,7 +567,7 @@ void SlabGroup::exchange(int buffer, int64_t n) {
         Local &l = *locals_[0];
         EngineBase *e = l.eng.get();
         const SlabSpec s = e->slab();
-        const size_t bytes = static_cast<size_t>(n) * e->plane_elems() * e->field_elem_size();
+        const size_t bytes = static_cast<size_t>(n) * e->plane_elems() * e->field_elem_size(buffer);
         cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
         DCMA_CUDA(cudaSetDevice(l.device));
         DCMA_NCCL(nccl().GroupStart());
@@ -590,7 +595,7 @@ void SlabGroup::exchange(int buffer, int64_t n) {
         Local &lo = *locals_[r], &hi = *locals_[r + 1];
         EngineBase *a = lo.eng.get(), *b = hi.eng.get();
         const SlabSpec sa = a->slab(), sb = b->slab();
-        const size_t bytes = static_cast<size_t>(n) * a->plane_elems() * a->field_elem_size();
+        const size_t bytes = static_cast<size_t>(n) * a->plane_elems() * a->field_elem_size(buffer);
         cudaStream_t st_a = static_cast<cudaStream_t>(a->stream_handle()), st_b = static_cast<cudaStream_t>(b->stream_handle());
         // up: a's last owned planes -> b's lower halo, on b's stream
         DCMA_CUDA(cudaSetDevice(hi.device));

@@ -53,7 +53,8 @@ class SlabGroup {
     void setup_ipc();
     void token_sync();
     bool ipc_ok_ = false;
-    void *peer_lo_[3] = {nullptr, nullptr, nullptr}, *peer_hi_[3] = {nullptr, nullptr, nullptr};
+    static constexpr int kMaxFieldAllocs = 4;  // D, U, scratch (+ U's own scratch in DCMA_B200_FIELD_MIXED)
+    void *peer_lo_[kMaxFieldAllocs] = {nullptr, nullptr, nullptr, nullptr}, *peer_hi_[kMaxFieldAllocs] = {nullptr, nullptr, nullptr, nullptr};
     int *d_token_ = nullptr;
     // flag transport: counters raised by the neighbours in my flag block, waited for with stream memory operations
     void exchange_flags(int buffer, int64_t planes, cudaStream_t st);

@@ -32,7 +32,7 @@ class AlignViaDemonsParams:
     max_update_magnitude: float = 2.0
     verbosity: int = 1
     # extensions (defaults keep reference behaviour)
-    field_mode: str = "fp64"  # "fp64" | "fp64_strict" | "fp32"
+    field_mode: str = "fp64"  # "fp64" | "fp64_strict" | "fp32" | "mixed" (D fp64, U fp32)
     device: int = -1
     check_every: int = 0
     pyramid_levels: int = 1

@@ -477,7 +477,8 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
             if (!std::strcmp(e, "fp64")) p.field_mode = DCMA_B200_FIELD_FP64;
             else if (!std::strcmp(e, "fp64_strict")) p.field_mode = DCMA_B200_FIELD_FP64_STRICT;
             else if (!std::strcmp(e, "fp32")) p.field_mode = DCMA_B200_FIELD_FP32;
-            else throw std::invalid_argument(std::string("DCMA_B200_FIELD_MODE='") + e + "' is not one of fp64, fp64_strict, fp32");
+            else if (!std::strcmp(e, "mixed")) p.field_mode = DCMA_B200_FIELD_MIXED;
+            else throw std::invalid_argument(std::string("DCMA_B200_FIELD_MODE='") + e + "' is not one of fp64, fp64_strict, fp32, mixed");
             YLOGWARN("DCMA_B200_FIELD_MODE=" << e << " overrides the caller's field_mode");
         }
         p.device = params.device;

@@ -40,7 +40,7 @@ struct AlignViaDemonsParams {
     int64_t verbosity = 1;
 
     // ---- dcma_b200 extensions (absent in the reference; defaults reproduce the reference) ----
-    int32_t field_mode = 0;           // 0: fp64 fields, 1: fp64 bit-exact vs the reference's CPU build, 2: fp32 fields
+    int32_t field_mode = 0;           // 0: fp64 fields, 1: fp64 bit-exact vs the reference's CPU build, 2: fp32 fields, 3: fp64 D + fp32 U
     int32_t device = -1;              // CUDA device ordinal, -1 = current
     int32_t pyramid_levels = 1;       // multi-resolution levels (1 = single resolution, as the reference)
     bool use_symmetric_force = false; // (grad F + grad W)/2 in the force (false = fixed-image gradient, as the reference)

@@ -51,7 +51,10 @@ typedef enum {
     DCMA_B200_FIELD_FP64 = 0,        /* double storage + double arithmetic with FMA contraction (default) */
     DCMA_B200_FIELD_FP64_STRICT = 1, /* double storage, no contraction, IEEE division: bit-identical deformation field
                                         to the reference's x86-64 build */
-    DCMA_B200_FIELD_FP32 = 2         /* float storage, fp32 smoothing; coordinates/interpolation/force stay fp64 */
+    DCMA_B200_FIELD_FP32 = 2,        /* float storage, fp32 smoothing; coordinates/interpolation/force stay fp64 */
+    DCMA_B200_FIELD_MIXED = 3        /* deformation field and all arithmetic as DCMA_B200_FIELD_FP64; only the per-iteration
+                                        update field is stored (and smoothed) as float: 176 instead of 256 algorithmic
+                                        bytes per voxel-update, within 1e-6 mm of the reference after 200 iterations */
 } dcma_b200_field_mode;
 
 /* POD mirror of `AlignViaDemonsParams` (src/Alignment_Demons.h:20-61), same names, same defaults

@@ -4,6 +4,7 @@ Bars (BASELINE.json north_star: max |d displacement| <= 1e-3 mm, final MSE withi
   * field_mode fp64_strict : BIT-IDENTICAL deformation/update/warped (NaN masks included) -- stage by stage and loops
   * field_mode fp64        : <= 1e-9 mm   (FMA contraction and reciprocal multiplies only)
   * field_mode fp32        : <= 1e-4 mm on these sizes (fp32 storage/arithmetic of the fields)
+  * field_mode mixed       : <= 1e-5 mm (D and all arithmetic fp64; only U is stored and smoothed as float)
 MSE values: the GPU reduces in a tree, the reference serially => 1e-12 relative is the bar for fp64 modes.
 """
 import numpy as np
@@ -13,10 +14,10 @@ from _helpers import phantom_pair, random_smooth_field, ref_kind
 
 pytestmark = pytest.mark.gpu
 
-TOL_MM = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 1e-4}
-TOL_MSE = {"fp64_strict": 1e-12, "fp64": 1e-12, "fp32": 1e-4}
+TOL_MM = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 1e-4, "mixed": 1e-5}
+TOL_MSE = {"fp64_strict": 1e-12, "fp64": 1e-12, "fp32": 1e-4, "mixed": 1e-6}
 # warped intensities (HU): fp32 fields move the sample point by ~1e-7 voxel
-TOL_HU = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 2e-3}
+TOL_HU = {"fp64_strict": 0.0, "fp64": 1e-9, "fp32": 2e-3, "mixed": 1e-6}
 
 
 
@@ -50,7 +51,7 @@ def _params(oracle, mode, iters, sigma, diffeo, fused=True, threshold=0.0, **kw)
     return oracle.make_params(**common), AlignViaDemonsParams(verbosity=0, field_mode=mode, fused=fused, **common)
 
 
-@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
+@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "mixed", "fp32"])
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}" for c in CASES])
 def test_stage_level_parity(oracle_mod, mode, fused, case):
@@ -103,7 +104,7 @@ def test_stage_level_parity(oracle_mod, mode, fused, case):
         O.close()
 
 
-@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
+@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "mixed", "fp32"])
 @pytest.mark.parametrize("diffeo", [False, True])
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}" for c in CASES])
 def test_loop_parity(oracle_mod, mode, diffeo, case):
@@ -136,7 +137,7 @@ def test_unfused_equals_fused(oracle_mod, mode):
 
 
 @pytest.mark.parametrize("diffeo", [False, True], ids=["standard", "diffeomorphic"])
-@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
+@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "mixed", "fp32"])
 def test_convergence_rule_matches_reference(oracle_mod, mode, diffeo):
     """The stop rule (cc:987-993) runs on the device: same number of iterations, same field as the oracle.
 
@@ -170,7 +171,7 @@ def test_convergence_rule_matches_reference(oracle_mod, mode, diffeo):
     assert any(s % 2 == 1 for s in skipped_seen) and any(s % 3 != 0 for s in skipped_seen), skipped_seen
 
 
-@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
+@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "mixed", "fp32"])
 def test_non_finite_inputs(oracle_mod, mode):
     """NaN/Inf voxels in fixed and moving (e.g. outside a resampled field of view): same NaN handling as the
     reference -- zero force, excluded from the MSE, zero gradient next to them (cc:238, 297-304, 535-539)."""

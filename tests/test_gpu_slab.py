@@ -38,7 +38,7 @@ def _slabs(F, M, sp, par, n, halo=-1):
     return D, hist, st, hb
 
 
-@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "fp32"])
+@pytest.mark.parametrize("mode", ["fp64_strict", "fp64", "mixed", "fp32"])
 @pytest.mark.parametrize("diffeo", [False, True])
 @pytest.mark.parametrize("n", [2, 3])
 def test_slab_group_equals_whole_volume_engine(mode, diffeo, n):
@@ -49,7 +49,7 @@ def test_slab_group_equals_whole_volume_engine(mode, diffeo, n):
     Ds, hs, sts, hb = _slabs(F, M, sp, par, n)
     assert sts.iterations_done == stw.iterations_done == iters
     assert np.array_equal(Dw, Ds), f"max diff {np.abs(Dw - Ds).max():.3e}"
-    assert np.max(np.abs(hs - hw) / hw) <= (1e-6 if mode == "fp32" else 1e-13)
+    assert np.max(np.abs(hs - hw) / hw) <= (1e-6 if mode in ("fp32", "mixed") else 1e-13)
     assert hb > 0
 
 
