@@ -713,7 +713,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=200, help="Demons iterations per step (BASELINE config 2: 200)")
     ap.add_argument("--field-mode", default=os.environ.get("DCMA_B200_FIELD_MODE", "fp64"),
-                    choices=["fp64", "fp64_strict", "fp32"],
+                    choices=["fp64", "fp64_strict", "mixed", "fp32"],
                     help="field storage/arithmetic of the measured run.  Default fp64: the reference's own storage type, "
                          "3e-7 mm from the reference engine after 200 iterations at full size.  fp32 (float fields, "
                          "FFMA2 smoothing) is ~1.9x faster and is reported beside it in `other_modes`; at full size its "

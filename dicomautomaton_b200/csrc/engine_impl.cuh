@@ -60,8 +60,6 @@ class Engine final : public EngineBase {
             throw std::invalid_argument("voxel spacing must be > 0");
         if (geom.slices > (1 << 19) || geom.rows > (1 << 19) || geom.cols > (1 << 19))
             throw std::invalid_argument("volume extent too large");
-        if (slab_.local > 0 && slab_.local != geom.slices && p_.use_symmetric_force)
-            throw std::invalid_argument("use_symmetric_force is not available with z-slab sharding yet (W needs a z halo)");
         if (slab_.local <= 0) slab_ = SlabSpec{0, geom.slices, 0, geom.slices};  // whole volume
         if (slab_.zoff < 0 || slab_.zoff + slab_.local > geom.slices || slab_.own0 < 0 || slab_.own1 > slab_.local ||
             slab_.own0 >= slab_.own1)
@@ -303,7 +301,14 @@ class Engine final : public EngineBase {
         const bool diffeo = (p_.use_diffeomorphic != 0);
         switch (st) {
             case IterStage::Force:
-                launch_force(w_src_, it, d_hist_, it, global_mse ? 0 : 1, /*reduce=*/false, /*fused_reduce=*/true);
+                if (p_.use_symmetric_force) {
+                    // extension a11 on a slab: the gradient of W reads W one plane beyond the owned range, so W is
+                    // evaluated on owned +- 1 planes; the slab group has exchanged that plane of the smoothed D
+                    materialise_warped(/*z_margin=*/1);
+                    launch_force(2, it, d_hist_, it, global_mse ? 0 : 1, /*reduce=*/false, /*fused_reduce=*/true);
+                } else {
+                    launch_force(w_src_, it, d_hist_, it, global_mse ? 0 : 1, /*reduce=*/false, /*fused_reduce=*/true);
+                }
                 break;
             case IterStage::SmoothU:
                 if (diffeo && plan_u_.active) smooth(dU_, tmp_u(), plan_u_, it);
@@ -828,31 +833,39 @@ class Engine final : public EngineBase {
             DCMA_CUDA(cudaMemcpyAsync(dW_, dM_ + local_offset_in_moving(), sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
         }
     }
-    void launch_warp_to_buffer(long long it = 0) {
+    // z_margin: also warp that many held planes on either side of the owned range (slab engines, symmetric force)
+    void launch_warp_to_buffer(long long it = 0, int z_margin = 0) {
         (void)it;
         ensure_warped_buffer();
         const dim3 blk(kTileX, kTileY);
+        Geo gq = g_;
+        dim3 grid = grid3_;
+        if (z_margin > 0) {
+            gq.zb = std::max(0, g_.zb - z_margin);
+            gq.ze = std::min(g_.S, g_.ze + z_margin);
+            grid.z = static_cast<unsigned>((gq.ze - gq.zb + zlen_ - 1) / zlen_);
+        }
         if (small_index_) {
             if (g_.CH == 1)
-                k_warp<T, STRICT, int, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
+                k_warp<T, STRICT, int, true><<<grid, blk, 0, stream_>>>(dM_, dD_, dW_, gq, zlen_, 0, 0.f);
             else
-                k_warp<T, STRICT, int, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
+                k_warp<T, STRICT, int, false><<<grid, blk, 0, stream_>>>(dM_, dD_, dW_, gq, zlen_, 0, 0.f);
         } else {
             if (g_.CH == 1)
-                k_warp<T, STRICT, long long, true><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
+                k_warp<T, STRICT, long long, true><<<grid, blk, 0, stream_>>>(dM_, dD_, dW_, gq, zlen_, 0, 0.f);
             else
-                k_warp<T, STRICT, long long, false><<<grid3_, blk, 0, stream_>>>(dM_, dD_, dW_, g_, zlen_, 0, 0.f);
+                k_warp<T, STRICT, long long, false><<<grid, blk, 0, stream_>>>(dM_, dD_, dW_, gq, zlen_, 0, 0.f);
         }
         DCMA_CUDA(cudaGetLastError());
         ++launches_;
     }
     // bring the explicit `warped` buffer up to date with the engine state
-    void materialise_warped() {
+    void materialise_warped(int z_margin = 0) {
         ensure_warped_buffer();
         if (w_src_ == 0) {
             DCMA_CUDA(cudaMemcpyAsync(dW_, dM_ + local_offset_in_moving(), sizeof(float) * g_.N * g_.CH, cudaMemcpyDeviceToDevice, stream_));
         } else if (w_src_ == 1) {
-            launch_warp_to_buffer();
+            launch_warp_to_buffer(0, z_margin);
         }
         w_src_ = 2;
     }

@@ -770,6 +770,9 @@ void SlabGroup::run(int64_t max_iterations, double *mse_history_host, dcma_b200_
         for (auto &l : locals_) l->eng->iter_stage(IterStage::Update, it, true);
         if (rz_d > 0) exchange(DCMA_B200_BUF_DEFORMATION, rz_d);
         for (auto &l : locals_) l->eng->iter_stage(IterStage::SmoothD, it, true);
+        // symmetric force (extension a11): the next force stage needs W = warp(M, D) one plane beyond the owned range to
+        // take the z gradient of W at the slab faces, i.e. one plane of the FINAL D of this iteration from each neighbour
+        if (e0->symmetric() && it + 1 < max_iterations) exchange(DCMA_B200_BUF_DEFORMATION, 1);
         if (can_converge && ((it + 1) % poll == 0) && (it + 1 < max_iterations) && e0->converged_poll()) break;
     }
     if (comm_stream_) DCMA_CUDA(cudaStreamSynchronize(comm_stream_));

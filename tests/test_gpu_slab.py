@@ -53,6 +53,24 @@ def test_slab_group_equals_whole_volume_engine(mode, diffeo, n):
     assert hb > 0
 
 
+@pytest.mark.parametrize("mode", ["fp64_strict", "mixed"])
+@pytest.mark.parametrize("diffeo", [False, True])
+def test_slab_group_with_the_symmetric_force(mode, diffeo):
+    """Extension a11 on slabs: the gradient of the warped image needs W one plane beyond the owned range (one plane of the
+    final D travels per iteration and W is evaluated on owned +- 1 planes).  Same field as the whole-volume engine, bit for
+    bit, and different from the fixed-gradient force."""
+    shape, sp, sigma, iters = (45, 40, 72), (1.0, 1.0, 1.0), 1.5, 8
+    F, M = phantom_pair(shape, sp)
+    par = _params(mode, iters, sigma, diffeo, use_symmetric_force=True)
+    Dw, hw, stw = _whole(F, M, sp, par)
+    Ds, hs, sts, hb = _slabs(F, M, sp, par, 3)
+    assert sts.iterations_done == stw.iterations_done == iters
+    assert np.array_equal(Dw, Ds), f"max diff {np.abs(Dw - Ds).max():.3e}"
+    assert np.max(np.abs(hs - hw) / hw) <= 1e-6
+    Dn, _, _ = _whole(F, M, sp, _params(mode, iters, sigma, diffeo))
+    assert np.abs(Dn - Dw).max() > 1e-3
+
+
 def test_slab_group_anisotropic_literal_smoothing_and_ragged_split():
     """per-axis radii (k_smooth_axis path), slices not divisible by the number of slabs, 2 mm slices (r_z = 2)."""
     shape, sp = (37, 21, 19), (0.9, 1.1, 2.0)
