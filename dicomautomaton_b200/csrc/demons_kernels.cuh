@@ -16,6 +16,7 @@
 // Template parameters: T = field storage type; STRICT = reproduce the reference's x86-64 arithmetic bit for bit
 // (true IEEE divisions; the translation unit is compiled with -fmad=false so nothing is contracted).
 #pragma once
+#include <type_traits>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -787,7 +788,12 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
         }
         const Tri<CT> t = tri_coords<CT, STRICT>(g, ak, x, y, z + g.zoff, xd, yd, zd, d[0], d[1], d[2]);
         const CT tx = t.tx, ty = t.ty, tz = t.tz;
-        CT q[3][8];
+        // DCMA_B200_FIELD_MIXED (U stored as float, D as double): the eight gathered values stay float and are interpolated
+        // in float; one conversion per component instead of 24 (F2F.F64.F32 runs on the quarter-rate XU pipe: ncu showed
+        // it 45 % busy with the conversions).  The reference itself narrows half of these values to float (cc:439-442).
+        constexpr bool kNarrowU = sizeof(TU) < sizeof(T);
+        using QT = typename std::conditional<kNarrowU, TU, CT>::type;
+        QT q[3][8];
         const int lz0 = t.z0 - g.zoff;  // local slice of the lower corners
         // all corners inside the grid AND inside this slab's buffers (always true for a whole-volume engine)
         const bool inside = ik(t) && static_cast<unsigned>(lz0) < static_cast<unsigned>(g.is2d ? g.S : g.S - 1);
@@ -834,15 +840,15 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const TU *Uc = U + c * N;
-                q[c][0] = (vz0 && vy0 && vx0) ? static_cast<CT>(Uc[r00 + cx0]) : CT(0);
-                q[c][1] = (vz0 && vy0 && vx1) ? static_cast<CT>(Uc[r00 + cx1]) : CT(0);
-                q[c][2] = (vz0 && vy1 && vx0) ? static_cast<CT>(Uc[r10 + cx0]) : CT(0);
-                q[c][3] = (vz0 && vy1 && vx1) ? static_cast<CT>(Uc[r10 + cx1]) : CT(0);
+                q[c][0] = (vz0 && vy0 && vx0) ? static_cast<QT>(Uc[r00 + cx0]) : QT(0);
+                q[c][1] = (vz0 && vy0 && vx1) ? static_cast<QT>(Uc[r00 + cx1]) : QT(0);
+                q[c][2] = (vz0 && vy1 && vx0) ? static_cast<QT>(Uc[r10 + cx0]) : QT(0);
+                q[c][3] = (vz0 && vy1 && vx1) ? static_cast<QT>(Uc[r10 + cx1]) : QT(0);
                 // slices == 1: z1 == z0, the z0 plane is reused (cc:436-442)
-                q[c][4] = (vz1 && vy0 && vx0) ? static_cast<CT>(Uc[r01 + cx0]) : CT(0);
-                q[c][5] = (vz1 && vy0 && vx1) ? static_cast<CT>(Uc[r01 + cx1]) : CT(0);
-                q[c][6] = (vz1 && vy1 && vx0) ? static_cast<CT>(Uc[r11 + cx0]) : CT(0);
-                q[c][7] = (vz1 && vy1 && vx1) ? static_cast<CT>(Uc[r11 + cx1]) : CT(0);
+                q[c][4] = (vz1 && vy0 && vx0) ? static_cast<QT>(Uc[r01 + cx0]) : QT(0);
+                q[c][5] = (vz1 && vy0 && vx1) ? static_cast<QT>(Uc[r01 + cx1]) : QT(0);
+                q[c][6] = (vz1 && vy1 && vx0) ? static_cast<QT>(Uc[r11 + cx0]) : QT(0);
+                q[c][7] = (vz1 && vy1 && vx1) ? static_cast<QT>(Uc[r11 + cx1]) : QT(0);
             }
         }
         // prefetch the next slice's displacement before consuming the gathers
@@ -854,6 +860,18 @@ __global__ void __launch_bounds__(kTileX *kTileY, (sizeof(T) == 8 ? 3 : 4))
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+            if constexpr (kNarrowU) {
+                const QT fx = static_cast<QT>(tx), fy = static_cast<QT>(ty), fz = static_cast<QT>(tz);
+                const QT c00 = q[c][0] * (QT(1) - fx) + q[c][1] * fx;
+                const QT c10 = q[c][2] * (QT(1) - fx) + q[c][3] * fx;
+                const QT c01 = q[c][4] * (QT(1) - fx) + q[c][5] * fx;
+                const QT c11 = q[c][6] * (QT(1) - fx) + q[c][7] * fx;
+                const QT c0 = c00 * (QT(1) - fy) + c10 * fy;
+                const QT c1 = c01 * (QT(1) - fy) + c11 * fy;
+                const CT u = static_cast<CT>(c0 * (QT(1) - fz) + c1 * fz);
+                D[v + c * N] = d[c] + u * pxl[c];  // cc:460-462
+                continue;
+            }
             const CT c000 = q[c][0], c100 = q[c][1], c010 = q[c][2], c110 = q[c][3];
             // the four upper-z corners are narrowed to float as the reference does (cc:439-442)
             const CT c001 = narrow_to_float<STRICT>(q[c][4]);

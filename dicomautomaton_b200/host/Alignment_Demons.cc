@@ -15,6 +15,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -195,9 +196,12 @@ void marshal_into(const planar_image_collection<T, double> &coll, T *dst) {
 
 // dense [z][y][x][c] -> one image per slice with the geometry and metadata of the matching slice of `geometry`
 // (marshal_volume_to_collection, reference Alignment_Demons.h:182-204), slice-parallel
+// Two steps, because the first one does not depend on the voxel values: building the images (allocation and first touch
+// of their buffers -- 1.6 GB of fresh pages for a 512x512x256 field, the most expensive host step of a registration) can
+// run while the GPU iterates; only the copy has to wait for the result.
 template <class T, class G>
-planar_image_collection<T, double> collection_from_dense(const T *src, int64_t slices, int64_t R, int64_t C, int64_t CH,
-                                                         const planar_image_collection<G, double> &geometry) {
+planar_image_collection<T, double> collection_like(int64_t slices, int64_t R, int64_t C, int64_t CH,
+                                                   const planar_image_collection<G, double> &geometry) {
     if (static_cast<int64_t>(geometry.images.size()) < slices)
         throw std::runtime_error("Requested image index not present, unable to continue");
     planar_image_collection<T, double> out;
@@ -209,7 +213,6 @@ planar_image_collection<T, double> collection_from_dense(const T *src, int64_t s
         imgs.push_back(&out.images.back());
         refs.push_back(&*it);
     }
-    const size_t per = static_cast<size_t>(R * C * CH);
     parallel_for(slices, [&](int64_t z) {
         auto &img = *imgs[static_cast<size_t>(z)];
         const auto &ref = *refs[static_cast<size_t>(z)];
@@ -217,6 +220,16 @@ planar_image_collection<T, double> collection_from_dense(const T *src, int64_t s
         img.init_buffer(R, C, CH);
         img.init_spatial(ref.pxl_dx, ref.pxl_dy, ref.pxl_dz, ref.anchor, ref.offset);
         img.metadata = ref.metadata;
+    });
+    return out;
+}
+template <class T>
+void fill_from_dense(planar_image_collection<T, double> &out, const T *src, int64_t R, int64_t C, int64_t CH) {
+    std::vector<planar_image<T, double> *> imgs;
+    for (auto &img : out.images) imgs.push_back(&img);
+    const size_t per = static_cast<size_t>(R * C * CH);
+    parallel_for(static_cast<int64_t>(imgs.size()), [&](int64_t z) {
+        auto &img = *imgs[static_cast<size_t>(z)];
         const T *s = src + static_cast<size_t>(z) * per;
         const bool dense_layout = (img.index(0, 0, 0) == 0) && (CH == 1 || img.index(0, 0, 1) == 1) &&
                                   (C == 1 || img.index(0, 1, 0) == CH) && (R == 1 || img.index(1, 0, 0) == C * CH);
@@ -228,6 +241,12 @@ planar_image_collection<T, double> collection_from_dense(const T *src, int64_t s
                     for (int64_t c = 0; c < CH; ++c) img.reference(y, x, c) = s[(y * C + x) * CH + c];
         }
     });
+}
+template <class T, class G>
+planar_image_collection<T, double> collection_from_dense(const T *src, int64_t slices, int64_t R, int64_t C, int64_t CH,
+                                                         const planar_image_collection<G, double> &geometry) {
+    auto out = collection_like<T>(slices, R, C, CH, geometry);
+    fill_from_dense(out, src, R, C, CH);
     return out;
 }
 
@@ -500,9 +519,22 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
         Pinned<double> def(nvox * 3);
         char err[512] = {0};
         dcma_b200_run_stats stats;
-        check_rc(dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err)), err);
-        // marshal_volume_to_collection (Alignment_Demons.h:182-204), slice-parallel
-        auto def_coll = collection_from_dense<double>(def.data(), fixed_vol.slices, fixed_vol.rows, fixed_vol.cols, 3, stationary);
+        // marshal_volume_to_collection (Alignment_Demons.h:182-204) in two steps: the output images are built (allocated,
+        // first-touched) by a helper thread WHILE the GPU iterates; the copy runs when the field has arrived
+        planar_image_collection<double, double> def_coll;
+        std::exception_ptr alloc_error;
+        std::thread builder([&]() {
+            try {
+                def_coll = collection_like<double>(fixed_vol.slices, fixed_vol.rows, fixed_vol.cols, 3, stationary);
+            } catch (...) {
+                alloc_error = std::current_exception();
+            }
+        });
+        const int rc = dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err));
+        builder.join();
+        check_rc(rc, err);
+        if (alloc_error) std::rethrow_exception(alloc_error);
+        fill_from_dense(def_coll, def.data(), fixed_vol.rows, fixed_vol.cols, 3);
         return deformation_field(std::move(def_coll));
     } catch (const std::exception &e) {
         YLOGWARN("Demons registration failed: " << e.what());

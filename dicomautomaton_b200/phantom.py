@@ -21,7 +21,28 @@ import math
 import torch
 
 
-def _phantom_hu(x, y, z, shape, case: int = 0):
+# Fine structure of the phantom.  "periodic" (the benchmark phantom): three plane waves of ~7-9 voxels wavelength, 20 HU
+# each -- every voxel gets a well-conditioned force, but the only information below the organ scale is
+# periodic, so displacements beyond half a wavelength (~3.5 voxels) are ambiguous.  "multiscale": the same three wave
+# directions at four octaves (wavelengths ~7 ... ~70 voxels, amplitude growing with wavelength, incommensurate phases) --
+# structure at every scale, as anatomy has, which is what a multi-resolution registration feeds on (BASELINE config 3).
+TEXTURES = ("periodic", "multiscale")
+
+
+def _texture(x, y, z, ph, texture):
+    if texture == "periodic":
+        return 20.0 * (torch.sin(0.9 * x + 0.3 * y + ph) + torch.sin(0.7 * y + 0.4 * z) + torch.sin(0.8 * z + 0.5 * x))
+    if texture != "multiscale":
+        raise ValueError(f"texture must be one of {TEXTURES}")
+    out = 0.0
+    for k, amp in enumerate((20.0, 30.0, 45.0, 70.0)):
+        s = 0.5 ** k * (1.0 + 0.07 * k)  # not exact octaves: no common period
+        out = out + amp * (torch.sin(s * (0.9 * x + 0.3 * y) + ph + 1.3 * k) + torch.sin(s * (0.7 * y + 0.4 * z) + 2.1 * k) +
+                           torch.sin(s * (0.8 * z + 0.5 * x) + 0.7 * k))
+    return out
+
+
+def _phantom_hu(x, y, z, shape, case: int = 0, texture: str = "periodic"):
     """x, y, z: float64 tensors of voxel-index coordinates (x=col, y=row, z=slice). shape = (slices, rows, cols)."""
     nz, ny, nx = (float(v) for v in shape)
     cx, cy, cz = (nx - 1.0) / 2.0, (ny - 1.0) / 2.0, (nz - 1.0) / 2.0
@@ -41,7 +62,7 @@ def _phantom_hu(x, y, z, shape, case: int = 0):
     hu = hu + body * blob(-700.0, -0.15 * math.cos(ph), 0.08, -0.12 + 0.05 * math.sin(ph), 0.07)
     rho2 = (x - cx) ** 2 + (y - (cy + 0.18 * ny)) ** 2
     hu = hu + body * 900.0 * torch.exp(-0.5 * rho2 / (0.03 * small) ** 2)
-    hu = hu + 20.0 * (torch.sin(0.9 * x + 0.3 * y + ph) + torch.sin(0.7 * y + 0.4 * z) + torch.sin(0.8 * z + 0.5 * x))
+    hu = hu + _texture(x, y, z, ph, texture)
     return hu
 
 
@@ -57,7 +78,7 @@ def known_warp_mm(x, y, z, shape, amplitude_mm: float = 2.0, case: int = 0):
 
 
 def make_pair(shape, spacing=(1.0, 1.0, 1.0), amplitude_mm: float = 2.0, case: int = 0, device="cpu",
-              z_range=None, chunk: int = 16):
+              z_range=None, chunk: int = 16, texture: str = "periodic"):
     """Returns (fixed, moving) float32 tensors of shape (slices, rows, cols) [or the z_range sub-slab of it].
 
     spacing = (pxl_dx, pxl_dy, pxl_dz) mm. For a single-slice volume the z component of the warp is dropped."""
@@ -72,12 +93,12 @@ def make_pair(shape, spacing=(1.0, 1.0, 1.0), amplitude_mm: float = 2.0, case: i
         b = min(a + chunk, z1)
         zs = torch.arange(a, b, dtype=torch.float64, device=dev).view(b - a, 1, 1)
         x, y, z = torch.broadcast_tensors(xs, ys, zs)
-        fixed[a - z0:b - z0] = _phantom_hu(x, y, z, shape, case).to(torch.float32)
+        fixed[a - z0:b - z0] = _phantom_hu(x, y, z, shape, case, texture).to(torch.float32)
         wx, wy, wz = known_warp_mm(x, y, z, shape, amplitude_mm, case)
         if nz == 1:
             wz = torch.zeros_like(wz)
         moving[a - z0:b - z0] = _phantom_hu(x + wx / spacing[0], y + wy / spacing[1], z + wz / spacing[2],
-                                            shape, case).to(torch.float32)
+                                            shape, case, texture).to(torch.float32)
     return fixed, moving
 
 

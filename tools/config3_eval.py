@@ -4,7 +4,7 @@ the phantom pair with a KNOWN warp w.  Pull convention: warped(p) = moving(p + D
 perfect field satisfies  D(p) + w(p + D(p)) = 0;  the reported error is the RMS (and 99th percentile) of that residual in mm
 over the voxels at least 8 voxels inside the volume.
 
-    python tools/config3_eval.py [--shape 512,512,512] [--amplitude 4.0] [--out profiles/r2_config3_quality.json]
+    python tools/config3_eval.py [--shape 512,512,512] [--amplitude 4.0] [--texture multiscale|periodic] [--out ...]
 """
 import argparse
 import json
@@ -44,6 +44,10 @@ def main():
     ap.add_argument("--shape", default="512,512,512")
     ap.add_argument("--amplitude", type=float, default=4.0)
     ap.add_argument("--mode", default="fp64")
+    ap.add_argument("--texture", default="multiscale", choices=["periodic", "multiscale"],
+                    help="fine structure of the phantom (dicomautomaton_b200/phantom.py): the benchmark phantom's periodic 7-voxel "
+                         "texture is ambiguous beyond ~3.5 voxels of displacement at EVERY pyramid level that resolves it; "
+                         "'multiscale' has structure at every scale, which is what a coarse-to-fine scheme feeds on")
     ap.add_argument("--out", default="gpurun_out/config3_quality.json")
     a = ap.parse_args()
     import torch
@@ -51,7 +55,7 @@ def main():
     from dicomautomaton_b200.demons import AlignViaDemons, AlignViaDemonsParams, demons_volume
     shape = tuple(int(v) for v in a.shape.split(","))
     dev = torch.device("cuda", 0)
-    f, m = phantom.make_pair(shape, amplitude_mm=a.amplitude, device=dev)
+    f, m = phantom.make_pair(shape, amplitude_mm=a.amplitude, device=dev, texture=a.texture)
     F, M = f.cpu().numpy(), m.cpu().numpy()
     del f, m
     iters = (25, 50, 100)  # finest, level 1, level 2
@@ -65,7 +69,7 @@ def main():
         "single_fixed_gradient_equal_cost": dict(max_iterations=int(round(cost)), use_symmetric_force=False),
         "single_fixed_gradient_200": dict(max_iterations=200, use_symmetric_force=False),
     }
-    rep = {"shape": list(shape), "amplitude_mm": a.amplitude, "mode": a.mode,
+    rep = {"shape": list(shape), "amplitude_mm": a.amplitude, "mode": a.mode, "texture": a.texture,
            "zero_field": residual_stats(np.zeros(shape + (3,)), shape, a.amplitude, dev),
            "pyramid_cost_in_finest_iterations": cost, "runs": {}}
     for name, kw in runs.items():
