@@ -413,6 +413,16 @@ int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, const double *de
         errbuf_len);
 }
 
+int dcma_b200_warp_to_grid(const dcma_b200_grid *field_grid, const double *deformation, const dcma_b200_grid *source_grid,
+                           const float *source, const dcma_b200_grid *out_grid, const unsigned char *mask, int32_t channel,
+                           float oob_value, float *out_inout, int device, char *errbuf, size_t errbuf_len) {
+    if (!field_grid || !deformation || !source_grid || !source || !out_grid || !out_inout)
+        return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded(
+        [&]() { dcma::warp_to_grid_host(*field_grid, deformation, *source_grid, source, *out_grid, mask, channel, oob_value, out_inout, device); },
+        errbuf, errbuf_len);
+}
+
 int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *image, const dcma_b200_grid *dst_grid, float oob_value,
                                float *out, int device, char *errbuf, size_t errbuf_len) {
     if (!src_grid || !image || !dst_grid || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);

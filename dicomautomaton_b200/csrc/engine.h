@@ -75,6 +75,11 @@ int histogram_match_host(const float *source, long long n_src, const float *refe
 void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &image_grid,
                           const float *image, const unsigned char *mask, float oob_value, float *out, int device);
 
+// the same with separate source and output stacks, ROI mask and channel selection, as the operation has them
+void warp_to_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &source_grid,
+                       const float *source, const dcma_b200_grid &out_grid, const unsigned char *mask, int channel, float oob_value,
+                       float *out_inout, int device);
+
 void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
                            float *out, int device);
 

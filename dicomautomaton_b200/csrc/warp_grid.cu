@@ -104,6 +104,45 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// The same body with THREE grids, as the operation has them (WarpImages.cc:385-456): the voxels of the OUTPUT stack (a copy
+// of the ReferenceImageSelection, the geometry placeholder) are visited, displaced through the field, and take the
+// trilinear sample of the SOURCE stack (the ImageSelection).  `out` holds the placeholder's voxels on entry: voxels
+// outside the mask, and channels other than `channel` (>= 0), keep them -- the operation's functor only assigns
+// `voxel_val` for bounded voxels of the selected channel (:419-422, 454).
+__global__ void __launch_bounds__(256)
+    k_warp_to_grid(const GridK fg, const double *__restrict__ field_aos, const GridK sg, const float *__restrict__ source,
+                   const GridK og, const unsigned char *__restrict__ mask, const int channel, const float oob_value,
+                   float *__restrict__ out) {
+    const long long nvox = static_cast<long long>(og.S) * og.R * og.C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvox; v += stride) {
+        if (mask && !mask[v]) continue;
+        const int x = static_cast<int>(v % og.C);
+        const long long r = v / og.C;
+        const int y = static_cast<int>(r % og.R);
+        const int z = static_cast<int>(r / og.R);
+        double p[3];
+        for (int k = 0; k < 3; ++k) p[k] = og.o[k] + x * og.dx * og.ex[k] + y * og.dy * og.ey[k] + z * og.dz * og.ez[k];
+        double u[3];
+        to_index(fg, p, u);
+        bool okx, oky, okz;
+        const double ddx = trilinear(field_aos, fg, 3, 0, u, okx);
+        const double ddy = trilinear(field_aos, fg, 3, 1, u, oky);
+        const double ddz = trilinear(field_aos, fg, 3, 2, u, okz);
+        const bool okd = okx && oky && okz;
+        double cp[3];
+        for (int k = 0; k < 3; ++k) cp[k] = p[k] + ddx * fg.ex[k] + ddy * fg.ey[k] + ddz * fg.ez[k];
+        double us[3];
+        to_index(sg, cp, us);
+        for (int c = 0; c < og.CH; ++c) {
+            if (channel >= 0 && c != channel) continue;
+            bool ok = false;
+            const double val = okd ? trilinear(source, sg, sg.CH, c, us, ok) : 0.0;
+            out[v * og.CH + c] = (okd && ok) ? static_cast<float>(val) : oob_value;
+        }
+    }
+}
+
 // resample_image_to_reference_grid (src/Alignment_Demons.cc:709-755): every voxel of the destination grid takes the
 // trilinear sample of the source image at its own position, `oob_value` (the reference: NaN, cc:743) outside.
 __global__ void __launch_bounds__(256)
@@ -185,6 +224,51 @@ void warp_image_grid_host(const dcma_b200_grid &field_grid, const double *deform
         k_warp_grid<<<grid, 256>>>(fg, dD, ig, dI, dMask, oob_value, dO);
         DCMA_CUDA(cudaGetLastError());
         DCMA_CUDA(cudaMemcpy(out, dO, sizeof(float) * ni * ig.CH, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+void warp_to_grid_host(const dcma_b200_grid &field_grid, const double *deformation_aos, const dcma_b200_grid &source_grid,
+                       const float *source, const dcma_b200_grid &out_grid, const unsigned char *mask, int channel, float oob_value,
+                       float *out_inout, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw CudaError(cudaErrorNoDevice, "no CUDA device is available (dcma_b200 has no CPU fallback)");
+    if (device >= 0) DCMA_CUDA(cudaSetDevice(device));
+    GridK fg = make_gridk(field_grid);
+    const GridK sg = make_gridk(source_grid), og = make_gridk(out_grid);
+    fg.CH = 3;
+    if (channel >= og.CH) throw std::invalid_argument("Encountered image without requested channel");
+    if ((channel < 0 ? og.CH : channel + 1) > sg.CH) throw std::invalid_argument("the source stack lacks a channel of the output stack");
+    const long long nf = static_cast<long long>(fg.S) * fg.R * fg.C, ns = static_cast<long long>(sg.S) * sg.R * sg.C * sg.CH,
+                    no = static_cast<long long>(og.S) * og.R * og.C;
+    double *dD = nullptr;
+    float *dS = nullptr, *dO = nullptr;
+    unsigned char *dMask = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dD);
+        cudaFree(dS);
+        cudaFree(dO);
+        cudaFree(dMask);
+    };
+    try {
+        DCMA_CUDA(cudaMalloc(&dD, sizeof(double) * 3 * nf));
+        DCMA_CUDA(cudaMalloc(&dS, sizeof(float) * ns));
+        DCMA_CUDA(cudaMalloc(&dO, sizeof(float) * no * og.CH));
+        DCMA_CUDA(cudaMemcpy(dD, deformation_aos, sizeof(double) * 3 * nf, cudaMemcpyHostToDevice));
+        DCMA_CUDA(cudaMemcpy(dS, source, sizeof(float) * ns, cudaMemcpyHostToDevice));
+        DCMA_CUDA(cudaMemcpy(dO, out_inout, sizeof(float) * no * og.CH, cudaMemcpyHostToDevice));
+        if (mask) {
+            DCMA_CUDA(cudaMalloc(&dMask, static_cast<size_t>(no)));
+            DCMA_CUDA(cudaMemcpy(dMask, mask, static_cast<size_t>(no), cudaMemcpyHostToDevice));
+        }
+        const int grid = static_cast<int>(std::min<long long>((no + 255) / 256, 148LL * 16));
+        k_warp_to_grid<<<grid, 256>>>(fg, dD, sg, dS, og, dMask, channel, oob_value, dO);
+        DCMA_CUDA(cudaGetLastError());
+        DCMA_CUDA(cudaMemcpy(out_inout, dO, sizeof(float) * no * og.CH, cudaMemcpyDeviceToHost));
     } catch (...) {
         cleanup();
         throw;

@@ -270,6 +270,24 @@ def warp_image_on_grid(field_grid: capi.Grid, deformation: np.ndarray, image_gri
     return out
 
 
+def warp_to_grid(field_grid: capi.Grid, deformation: np.ndarray, source_grid: capi.Grid, source: np.ndarray, out_grid: capi.Grid,
+                 placeholder: np.ndarray, mask: Optional[np.ndarray] = None, channel: int = -1, oob_value: float = 0.0,
+                 device: int = -1) -> np.ndarray:
+    """WarpImages' voxel body with the operation's three stacks (reference src/Operations/WarpImages.cc:385-456): the voxels
+    of `placeholder` (the copy of the reference image array, on `out_grid`) that `mask` selects take
+    source(p + D(p)); the others, and channels other than `channel` (>= 0), are returned unchanged."""
+    lib = capi.lib()
+    D = np.ascontiguousarray(deformation, dtype=np.float64)
+    src = np.ascontiguousarray(source, dtype=np.float32)
+    out = np.array(placeholder, dtype=np.float32, order="C", copy=True)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_warp_to_grid(C.byref(field_grid), D.ctypes.data, C.byref(source_grid), src.ctypes.data,
+                                          C.byref(out_grid), None if m is None else m.ctypes.data, int(channel), float(oob_value),
+                                          out.ctypes.data, device, err, len(err)), err)
+    return out
+
+
 def resample_to_grid(src_grid: capi.Grid, image: np.ndarray, dst_grid: capi.Grid, oob_value: float = float("nan"),
                      device: int = -1) -> np.ndarray:
     """resample_image_to_reference_grid (reference src/Alignment_Demons.cc:709-755) for regular grids."""

@@ -262,6 +262,16 @@ DCMA_B200_API int dcma_b200_warp_image_grid(const dcma_b200_grid *field_grid, co
                                             const dcma_b200_grid *image_grid, const float *image, const unsigned char *mask,
                                             float oob_value, float *out, int device, char *errbuf, size_t errbuf_len);
 
+/* The same body with the operation's THREE stacks (src/Operations/WarpImages.cc:385-456): every voxel p of the OUTPUT stack
+ * (the operation's copy of the ReferenceImageSelection, `out_inout` holds its voxels on entry) that `mask` selects (NULL =
+ * all; the operation's bounded voxels, i.e. inside the selected ROIs) takes source(p + D(p)), the SOURCE stack (the
+ * ImageSelection) sampled trilinearly; `oob_value` where a lookup leaves its grid.  channel >= 0: only that channel is
+ * assigned (:422); < 0: all.  Unselected voxels and channels keep their values.  All pointers HOST. */
+DCMA_B200_API int dcma_b200_warp_to_grid(const dcma_b200_grid *field_grid, const double *deformation,
+                                         const dcma_b200_grid *source_grid, const float *source, const dcma_b200_grid *out_grid,
+                                         const unsigned char *mask, int32_t channel, float oob_value, float *out_inout,
+                                         int device, char *errbuf, size_t errbuf_len);
+
 /* resample_image_to_reference_grid (src/Alignment_Demons.cc:709-755): the source image sampled trilinearly at the
  * positions of the destination grid's voxels, `oob_value` (the reference passes NaN, cc:743) outside the source grid.
  * out: dst voxels x src channels.  The reference's lookup is Ygor's (unpinned); definition as dcma_b200_warp_image_grid. */

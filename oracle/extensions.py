@@ -252,6 +252,28 @@ def warp_image_on_grid(field, f_spacing, f_origin, image, i_spacing, i_origin, o
     return out
 
 
+def warp_to_grid(field, f_spacing, f_origin, source, s_spacing, s_origin, placeholder, o_spacing, o_origin, oob_value=0.0,
+                 mask=None):
+    """The same with the operation's three stacks (src/Operations/WarpImages.cc:385-456), axis-aligned grids, one channel:
+    voxels of `placeholder` (on the output grid) selected by `mask` take source(p + D(p)); the others are kept."""
+    S, R, C = placeholder.shape
+    z, y, x = np.meshgrid(np.arange(S, dtype=np.float64), np.arange(R, dtype=np.float64), np.arange(C, dtype=np.float64),
+                          indexing="ij")
+    p = [o_origin[0] + x * o_spacing[0], o_origin[1] + y * o_spacing[1], o_origin[2] + z * o_spacing[2]]
+    uf = [(p[k] - f_origin[k]) / f_spacing[k] for k in range(3)]
+    d, okd = [], np.ones(placeholder.shape, dtype=bool)
+    for c in range(3):
+        v, ok = _trilinear(field[..., c], uf)
+        d.append(v)
+        okd &= ok
+    us = [(p[k] + np.where(okd, d[k], 0.0) - s_origin[k]) / s_spacing[k] for k in range(3)]
+    val, ok = _trilinear(source, us)
+    out = np.where(okd & ok, val, oob_value).astype(np.float32)
+    if mask is not None:
+        out = np.where(mask.astype(bool), out, placeholder.astype(np.float32))
+    return out
+
+
 # ---- row a14 / f4: histogram_match, reference src/Alignment_Demons.cc:760-891 (pure std:: code, no Ygor arithmetic) ----
 # PINNED: tests/test_oracle_extensions.py checks the reference's own known answers (10, 17.5, 25, 32.5 for a 2x2 ramp
 # with 4 bins, constants returned unchanged: src/Alignment_Demons_Tests.cc:204-236).

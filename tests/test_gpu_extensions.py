@@ -153,6 +153,41 @@ def test_warp_on_another_grid_matches_the_cpu_restatement_and_the_reference_prop
     assert np.abs(a - b)[inside].max() <= 2e-3   # float rounding of the two code paths (HU)
 
 
+def test_warp_with_three_stacks_as_the_operation_has_them():
+    """dcma_b200_warp_to_grid: field on the CT grid, SOURCE stack (ImageSelection) on a dose grid, OUTPUT stack (copy of the
+    ReferenceImageSelection) on a third grid; ROI mask and channel selection leave everything else untouched
+    (src/Operations/WarpImages.cc:385-456)."""
+    from dicomautomaton_b200.demons import make_grid, warp_image_on_grid, warp_to_grid
+    from oracle import extensions as ext
+    fshape, fsp, forg = (20, 32, 36), (1.0, 1.0, 2.0), (-10.0, 5.0, 0.0)
+    sshape, ssp, sorg = (12, 14, 13), (2.5, 2.0, 3.0), (-8.0, 7.5, 1.0)
+    oshape, osp, oorg = (9, 17, 21), (1.5, 1.5, 4.0), (-9.0, 6.0, 2.0)
+    D = random_smooth_field(fshape, 3.0, seed=9)
+    rng = np.random.default_rng(5)
+    src = rng.uniform(0.0, 70.0, size=sshape).astype(np.float32)
+    place = rng.uniform(-5.0, -1.0, size=oshape).astype(np.float32)  # the reference array's own voxels (negative: recognisable)
+    fg, sg, og = make_grid(fshape, fsp, forg), make_grid(sshape, ssp, sorg), make_grid(oshape, osp, oorg)
+    mask = np.zeros(oshape, dtype=np.uint8)
+    mask[1:8, 2:15, 3:19] = 1
+    got = warp_to_grid(fg, D, sg, src, og, place, mask=mask, oob_value=0.0)
+    ref = ext.warp_to_grid(D, fsp, forg, src, ssp, sorg, place, osp, oorg, 0.0, mask)
+    assert np.abs(got - ref).max() <= 1e-4 * 70.0
+    assert np.array_equal(got[mask == 0], place[mask == 0]) and (got[mask == 1] >= 0.0).all()
+    assert (got[mask == 1] == 0.0).any() and (got[mask == 1] > 0.0).any()   # some lookups leave a grid, some do not
+    # output grid == source grid, no mask: the two-grid call
+    same = warp_to_grid(fg, D, sg, src, sg, src, oob_value=0.0)
+    assert np.array_equal(same, warp_image_on_grid(fg, D, sg, src, oob_value=0.0))
+    # two channels, only channel 1 selected: channel 0 keeps the placeholder's values
+    src2 = np.stack([src, src * 0.5], axis=-1)
+    place2 = np.stack([place, place], axis=-1)
+    sg2, og2 = make_grid(sshape, ssp, sorg, channels=2), make_grid(oshape, osp, oorg, channels=2)
+    g2 = warp_to_grid(fg, D, sg2, src2, og2, place2, mask=mask, channel=1, oob_value=0.0)
+    assert np.array_equal(g2[..., 0], place) and np.allclose(g2[..., 1][mask == 1], 0.5 * got[mask == 1], rtol=0, atol=1e-4)
+    from dicomautomaton_b200 import capi
+    with pytest.raises(capi.DcmaError):
+        warp_to_grid(fg, D, sg, src, og2, place2, channel=1)   # the source stack has no channel 1
+
+
 def test_gpu_histogram_match_is_bit_identical_to_the_reference_algorithm():
     """dcma_b200_histogram_match vs the pinned restatement of src/Alignment_Demons.cc:760-891: the reference's known
     answers, then random CT-like volumes with NaNs, outliers, different sizes and bin counts -- bit for bit."""
