@@ -113,6 +113,63 @@ def build_operation(verbose=True, patched=False):
     return exe
 
 
+WARP_EXE = os.path.join(OUT, "warp_operation_check")
+WARP_PATCHED_EXE = os.path.join(OUT, "warp_operation_check_patched")
+WARP_PATCH = os.path.join(ROOT, "patches", "WarpImages.patch")
+
+
+def build_warp_operation(verbose=True, patched=False):
+    """`host/_build/warp_operation_check[_patched]`: the reference's OWN operation file src/Operations/WarpImages.cc,
+    compiled in place -- unmodified, or with patches/WarpImages.patch applied (streamed through `patch -o -`, nothing of
+    the reference is written into the repository) -- against the stand-in headers, linked with host/Warp_Images_Field.cc,
+    libdcma_b200.so and the driver tests/native/warp_operation_check.cc."""
+    op_src = os.path.join(REF_SRC, "Operations", "WarpImages.cc")
+    exe = WARP_PATCHED_EXE if patched else WARP_EXE
+    if not os.path.isfile(op_src):
+        if verbose:
+            print(f"[host tests] {op_src} not found; {'using prebuilt ' + exe if os.path.isfile(exe) else 'nothing to do'}")
+        return exe if os.path.isfile(exe) else None
+    top = os.path.join(OUT, "warp")          # plays the reference's src/ ; the operation is compiled from warp/ops
+    ops = os.path.join(top, "ops")
+    os.makedirs(ops, exist_ok=True)
+    libdir = os.path.join(os.path.dirname(HERE), "lib")
+    shim = os.path.join(HERE, "shim")
+    inc = ["-I", os.path.join(shim, "dcma_min"), "-I", os.path.join(shim, "ygor_min"), "-I", HERE, "-I", os.path.join(ROOT, "include")]
+    cxx = ["g++", "-std=c++17", "-O2", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unused-but-set-variable"]
+    for h in ("Structs.h", "Regex_Selectors.h", "Thread_Pool.h", "Metadata.h", "Alignment_Rigid.h", "Alignment_TPSRPM.h",
+              "Alignment_Field.h", "Warp_Images_Field.h"):
+        with open(os.path.join(top, h), "w") as f:
+            f.write(f"#pragma once\n#include <{h}>\n")
+    for sub, h in (("YgorImages_Functors/Grouping", "Misc_Functors.h"),
+                   ("YgorImages_Functors/Processing", "Partitioned_Image_Voxel_Visitor_Mutator.h")):
+        os.makedirs(os.path.join(top, sub), exist_ok=True)
+        with open(os.path.join(top, sub, h), "w") as f:
+            f.write(f"#pragma once\n#include <{h}>\n")
+    with open(os.path.join(ops, "WarpImages.h"), "w") as f:  # the operation's own header declares exactly these two
+        f.write("#pragma once\n#include <map>\n#include <string>\n#include <Structs.h>\n#include <Regex_Selectors.h>\n"
+                "OperationDoc OpArgDocWarpImages();\n"
+                "bool WarpImages(Drover &, const OperationArgPkg &, std::map<std::string, std::string> &, const std::string &);\n")
+    objs = []
+    o = os.path.join(OUT, "ref_warp_operation_patched.o" if patched else "ref_warp_operation.o")
+    cmd = cxx + inc + ["-x", "c++", "-c", "-", "-o", o]
+    if verbose:
+        print("[host tests]", " ".join(cmd), "<", op_src, "(+ patches/WarpImages.patch)" if patched else "")
+    if patched:
+        text = subprocess.run(["patch", "-s", "-o", "-", op_src, WARP_PATCH], check=True, capture_output=True).stdout
+        subprocess.run(cmd, input=text, check=True, cwd=ops)
+    else:
+        with open(op_src, "rb") as f:
+            subprocess.check_call(cmd, stdin=f, cwd=ops)
+    objs.append(o)
+    for src, name in ((os.path.join(ROOT, "tests", "native", "warp_operation_check.cc"), "warp_operation_check.o"),
+                      (os.path.join(HERE, "Warp_Images_Field.cc"), "Warp_Images_Field.o")):
+        o = os.path.join(OUT, name)
+        subprocess.check_call(cxx + inc + ["-c", src, "-o", o])
+        objs.append(o)
+    subprocess.check_call(["g++", "-pthread", "-o", exe, *objs, "-L", libdir, "-ldcma_b200", "-Wl,-rpath,$ORIGIN/../../lib"])
+    return exe
+
+
 HARNESS = os.path.join(OUT, "libdcma_b200_dropin.so")
 
 
@@ -178,6 +235,8 @@ def build_field_io(verbose=True):
 if __name__ == "__main__":
     build_harness()
     build_field_io()
+    build_warp_operation()
+    build_warp_operation(patched=True)
     p = build()
     q = build_operation()
     build_operation(patched=True)

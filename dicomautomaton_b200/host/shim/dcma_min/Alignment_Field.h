@@ -55,6 +55,7 @@ class deformation_field {
 
     std::reference_wrapper<const planar_image_collection<double, double>> get_imagecoll_crefw() const { return std::cref(field); }
     std::reference_wrapper<const planar_image_adjacency<double, double>> get_adjacency_crefw() const { return std::cref(adj.value()); }
+    void apply_to(vec3<double> &v) const { v = transform(v); }  // .cc:161-165
     vec3<double> transform(const vec3<double> &v) const {  // .cc:138-153
         const double oob = std::numeric_limits<double>::quiet_NaN();
         return v + vec3<double>(adj->trilinearly_interpolate(v, 0, oob), adj->trilinearly_interpolate(v, 1, oob),

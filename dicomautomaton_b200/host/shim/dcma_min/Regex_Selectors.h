@@ -1,7 +1,8 @@
-// Stand-in for the part of the reference's src/Regex_Selectors.h that RegisterImagesDemons.cc uses: Compile_Regex,
-// All_IAs, Whitelist for image arrays (positional selectors only: first, last, all, none, #N, #-N, and !negation) and
-// IAWhitelistOpArgDoc.  NOT a product component.
+// Stand-in for the part of the reference's src/Regex_Selectors.h that RegisterImagesDemons.cc and WarpImages.cc use:
+// Compile_Regex; All_IAs / All_T3s with Whitelist (positional selectors only: first, last, all, none, #N, #-N, and
+// !negation); All_CCs with Whitelist by ROI label regexes; the matching *WhitelistOpArgDoc helpers.  NOT a product component.
 #pragma once
+#include <functional>
 #include <iterator>
 #include <list>
 #include <memory>
@@ -23,13 +24,14 @@ inline IA_iter_list All_IAs(Drover &d) {
     return out;
 }
 
-inline IA_iter_list Whitelist(IA_iter_list all, std::string sel) {
+template <class IterList>
+inline IterList Whitelist_positional(IterList all, std::string sel) {
     bool negate = false;
     if (!sel.empty() && sel.front() == '!') {
         negate = true;
         sel.erase(sel.begin());
     }
-    IA_iter_list picked;
+    IterList picked;
     const auto n = static_cast<long>(all.size());
     auto nth = [&](long i) {
         if (i >= 0 && i < n) picked.push_back(*std::next(all.begin(), i));
@@ -42,11 +44,57 @@ inline IA_iter_list Whitelist(IA_iter_list all, std::string sel) {
     else if (sel.size() > 1 && sel[0] == '#') nth(std::stol(sel.substr(1)));
     else throw std::invalid_argument("selector '" + sel + "' is not supported by this stand-in");
     if (!negate) return picked;
-    IA_iter_list rest;
+    IterList rest;
     for (const auto &it : all)
         if (std::find(picked.begin(), picked.end(), it) == picked.end()) rest.push_back(it);
     return rest;
 }
+
+inline IA_iter_list Whitelist(IA_iter_list all, std::string sel) { return Whitelist_positional(std::move(all), std::move(sel)); }
+
+using T3_iter_list = std::list<std::list<std::shared_ptr<Transform3>>::iterator>;
+inline T3_iter_list All_T3s(Drover &d) {
+    T3_iter_list out;
+    for (auto it = d.trans_data.begin(); it != d.trans_data.end(); ++it) out.push_back(it);
+    return out;
+}
+inline T3_iter_list Whitelist(T3_iter_list all, std::string sel) { return Whitelist_positional(std::move(all), std::move(sel)); }
+
+using CC_ref_list = std::list<std::reference_wrapper<contour_collection<double>>>;
+inline CC_ref_list All_CCs(Drover &d) {
+    CC_ref_list out;
+    if (d.contour_data)
+        for (auto &cc : d.contour_data->ccs) out.push_back(std::ref(cc));
+    return out;
+}
+// collections whose first contour's "ROIName" and "NormalizedROIName" match the two regexes; the third selector is positional
+inline CC_ref_list Whitelist(CC_ref_list all, const std::string &roi_regex, const std::string &norm_regex, const std::string &sel = "all") {
+    const auto r1 = Compile_Regex(roi_regex), r2 = Compile_Regex(norm_regex);
+    CC_ref_list out;
+    for (auto &cc : all) {
+        if (cc.get().contours.empty()) continue;
+        const auto &md = cc.get().contours.front().metadata;
+        const auto a = md.find("ROIName"), b = md.find("NormalizedROIName");
+        if (a == md.end() || b == md.end()) continue;
+        if (std::regex_match(a->second, r1) && std::regex_match(b->second, r2)) out.push_back(cc);
+    }
+    if (!std::regex_match(sel, Compile_Regex("^al?l?$"))) throw std::invalid_argument("ROISelection '" + sel + "' is not supported by this stand-in");
+    return out;
+}
+
+inline OperationArgDoc simple_selector_doc(const char *name, const char *desc, const char *def) {
+    OperationArgDoc out;
+    out.name = name;
+    out.desc = desc;
+    out.default_val = def;
+    out.expected = true;
+    out.examples = {def};
+    return out;
+}
+inline OperationArgDoc T3WhitelistOpArgDoc() { return simple_selector_doc("TransformSelection", "Select one or more transform objects.", "last"); }
+inline OperationArgDoc NCWhitelistOpArgDoc() { return simple_selector_doc("NormalizedROILabelRegex", "Regex of normalised ROI labels.", ".*"); }
+inline OperationArgDoc RCWhitelistOpArgDoc() { return simple_selector_doc("ROILabelRegex", "Regex of ROI labels.", ".*"); }
+inline OperationArgDoc CCWhitelistOpArgDoc() { return simple_selector_doc("ROISelection", "Select one or more contour collections.", "all"); }
 
 inline OperationArgDoc IAWhitelistOpArgDoc() {
     OperationArgDoc out;

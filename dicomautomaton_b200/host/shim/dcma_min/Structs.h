@@ -15,6 +15,8 @@
 #include "YgorImages.h"
 
 #include "Alignment_Field.h"
+#include "Alignment_Rigid.h"
+#include "Alignment_TPSRPM.h"
 
 enum class OpArgVisibility { Show, Hide };
 enum class OpArgFlow { Unknown, Ingress, Egress };
@@ -63,17 +65,19 @@ struct Image_Array {
     std::string filename;
 };
 
-template <class T>
-class affine_transform {};
-class thin_plate_spline {};
 
 struct Transform3 {
     std::variant<std::monostate, affine_transform<double>, thin_plate_spline, deformation_field> transform;
     std::map<std::string, std::string> metadata;
 };
 
+struct Contour_Data {
+    std::list<contour_collection<double>> ccs;
+};
+
 class Drover {
   public:
+    std::shared_ptr<Contour_Data> contour_data;
     std::list<std::shared_ptr<Image_Array>> image_data;
     std::list<std::shared_ptr<Transform3>> trans_data;
 };

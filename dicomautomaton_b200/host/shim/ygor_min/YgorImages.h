@@ -9,6 +9,7 @@
 //   x <-> column <-> row_unit <-> pxl_dx ; y <-> row <-> col_unit <-> pxl_dy ; z <-> slice <-> pxl_dz
 #pragma once
 #include <algorithm>
+#include <any>
 #include <cmath>
 #include <cstdint>
 #include <functional>
@@ -36,6 +37,7 @@ class planar_image {
         rows = r; columns = c; channels = ch;
         data.assign(static_cast<size_t>(r * c * ch), T(0));
     }
+    void fill_pixels(T v) { std::fill(data.begin(), data.end(), v); }
     void init_spatial(R dx, R dy, R dz, const vec3<R> &a, const vec3<R> &o) { pxl_dx = dx; pxl_dy = dy; pxl_dz = dz; anchor = a; offset = o; }
     int64_t index(int64_t r, int64_t c, int64_t ch = 0) const {
         if (r < 0 || r >= rows || c < 0 || c >= columns || ch < 0 || ch >= channels) return -1;
@@ -142,7 +144,16 @@ class planar_image_collection {
         idx.build(images, unit);
         return idx.sample(p, unit, ch, oob, true);
     }
-    std::map<std::string, std::string> get_common_metadata() const {
+    using images_list_it_t = typename std::list<planar_image<T, R>>::iterator;
+    // one call of `op` per image (the only grouping the Demons-path operations use: GroupIndividualImages); serial here
+    template <class Grouper, class Op>
+    bool Process_Images_Parallel(Grouper, Op op, std::list<std::reference_wrapper<planar_image_collection<T, R>>> external,
+                                 std::list<std::reference_wrapper<contour_collection<R>>> ccs, std::any user_data = {}) {
+        for (auto it = images.begin(); it != images.end(); ++it)
+            if (!op(it, std::list<images_list_it_t>{it}, external, ccs, user_data)) return false;
+        return true;
+    }
+    std::map<std::string, std::string> get_common_metadata(const std::list<images_list_it_t> & = {}) const {
         std::map<std::string, std::string> out;
         if (images.empty()) return out;
         out = images.front().metadata;
@@ -171,9 +182,25 @@ class planar_image_adjacency {
         for (auto &e : v) { idx_.pos.push_back(e.first); idx_.imgs.push_back(e.second); }
     }
     T trilinearly_interpolate(const vec3<R> &p, int64_t ch, T oob) const { return idx_.sample(p, unit_, ch, oob, false); }
-    const planar_image<T, R> &int_to_img(int64_t i) const { return *idx_.imgs.at(static_cast<size_t>(i)); }
-    int64_t size() const { return static_cast<int64_t>(idx_.imgs.size()); }
+    const std::vector<const planar_image<T, R> *> &int_to_img = idx_.imgs;  // index along the stacking direction -> image
 };
+
+// Parallel planes with the same in-plane grid (spacing along the stacking direction may vary).
+template <class T, class R>
+bool Images_Form_Rectilinear_Grid(const std::list<std::reference_wrapper<planar_image<T, R>>> &imgs, R eps = R(1e-6)) {
+    if (imgs.empty()) return false;
+    const auto &a = imgs.front().get();
+    const vec3<R> unit = a.ortho_unit();
+    for (const auto &r : imgs) {
+        const auto &b = r.get();
+        if (b.rows != a.rows || b.columns != a.columns) return false;
+        if (std::abs(b.pxl_dx - a.pxl_dx) > eps || std::abs(b.pxl_dy - a.pxl_dy) > eps) return false;
+        if ((b.row_unit - a.row_unit).length() > eps || (b.col_unit - a.col_unit).length() > eps) return false;
+        const vec3<R> d = (b.anchor + b.offset) - (a.anchor + a.offset);
+        if ((d - unit * d.Dot(unit)).length() > eps * std::max<R>(R(1), d.length())) return false;
+    }
+    return true;
+}
 
 // Same extents, spacing and orientation everywhere, and equally spaced along the stacking direction.
 template <class T, class R>

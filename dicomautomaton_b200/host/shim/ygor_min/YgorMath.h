@@ -6,6 +6,8 @@
 #include <cmath>
 #include <iosfwd>
 #include <list>
+#include <map>
+#include <string>
 #include <ostream>
 #include <istream>
 
@@ -38,6 +40,20 @@ std::istream &operator>>(std::istream &is, vec3<T> &v) {  // "(x, y, z)"
     is >> c >> v.x >> c >> v.y >> c >> v.z >> c;
     return is;
 }
+
+// closed planar polygons with metadata ("ROIName", "NormalizedROIName"), as WarpImages selects them
+template <class T>
+class contour_of_points {
+  public:
+    std::list<vec3<T>> points;
+    bool closed = true;
+    std::map<std::string, std::string> metadata;
+};
+template <class T>
+class contour_collection {
+  public:
+    std::list<contour_of_points<T>> contours;
+};
 
 template <class T>
 class point_set {
