@@ -207,8 +207,7 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
             }
             if (params->n_devices > 1) {
                 // the volume is sharded into z-slabs over devices 0..n_devices-1 of this process
-                std::vector<int> dev(params->n_devices);
-                for (int i = 0; i < params->n_devices; ++i) dev[i] = i;
+                const std::vector<int> dev = dcma::slab_devices(params->n_devices);
                 // A composition gather that leaves the halo fails the run loudly (std::logic_error from SlabGroup::run).
                 // With the default halo the registration is then repeated with a doubled one (an explicit halo_planes
                 // is the caller's decision and is not second-guessed).

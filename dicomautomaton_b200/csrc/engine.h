@@ -48,6 +48,9 @@ class EngineBase {
     virtual void set(int buffer, const void *host) = 0;
     virtual void export_deformation_device(double *device_out) = 0;
     virtual void import_deformation_device(const double *device_aos) = 0;  // warm start: D := field, W := warp(M, D)
+    // the same for a slab engine: `device_aos_whole` is the field of the WHOLE volume (any device this one can read);
+    // every slice the engine holds is taken from it, halo planes included
+    virtual void import_deformation_whole(const double *device_aos_whole) = 0;
     virtual const float *fixed_dev() const = 0;
     virtual const float *moving_dev() const = 0;
     virtual void sync() = 0;

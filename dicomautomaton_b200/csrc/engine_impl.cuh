@@ -108,7 +108,18 @@ class Engine final : public EngineBase {
             DCMA_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
             own_stream_ = true;
         }
+        // from here on a throwing allocation must not leak what the constructor already holds: the destructor does not
+        // run for a half-built object
+        try {
+            allocate_and_plan(geom, Ng, N);
+        } catch (...) {
+            release_all();
+            throw;
+        }
+    }
 
+  private:
+    void allocate_and_plan(const dcma_b200_geom &geom, const long long Ng, const long long N) {
         // per-voxel kernels: 3-D grid of 32x8 tiles, striding over the owned slices; ~16 resident-CTA waves of blocks
         const int ntx = (g_.C + kTileX - 1) / kTileX, nty = (g_.R + kTileY - 1) / kTileY;
         if (nty > 65535) throw std::invalid_argument("too many rows");
@@ -150,20 +161,35 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * N, stream_));
         DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(TU) * 3 * N, stream_));
     }
-
-    ~Engine() override {
+    void release_all() noexcept {
         cudaSetDevice(dev_);
-        cudaStreamSynchronize(stream_);
+        if (stream_) cudaStreamSynchronize(stream_);
         for (void *p : allocs_) cudaFree(p);
+        allocs_.clear();
         if (h_ctrl_) cudaFreeHost(h_ctrl_);
         if (d_hist_) cudaFree(d_hist_);
         if (ev_run0_) cudaEventDestroy(ev_run0_);
         if (ev_run1_) cudaEventDestroy(ev_run1_);
         for (cudaEvent_t e : ev_stage_)
             if (e) cudaEventDestroy(e);
+        for (auto &pr : prof_) {
+            cudaEventDestroy(pr.a);
+            cudaEventDestroy(pr.b);
+        }
+        prof_.clear();
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
-        if (own_stream_) cudaStreamDestroy(stream_);
+        if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+        h_ctrl_ = nullptr;
+        d_hist_ = nullptr;
+        ev_run0_ = ev_run1_ = nullptr;
+        ev_stage_[0] = ev_stage_[1] = nullptr;
+        copy_stream_ = nullptr;
+        stream_ = nullptr;
+        cudaGetLastError();  // a failed allocation leaves a sticky-looking (non-fatal) error code behind
     }
+
+  public:
+    ~Engine() override { release_all(); }
 
     int device() const override { return dev_; }
     int64_t device_bytes() const override { return bytes_; }
@@ -486,6 +512,13 @@ class Engine final : public EngineBase {
     void import_deformation_device(const double *device_aos) override {
         DCMA_CUDA(cudaSetDevice(dev_));
         k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(device_aos, dD_, g_.N, owned_v0(), owned_v1());
+        DCMA_CUDA(cudaGetLastError());
+        w_src_ = 1;
+    }
+    void import_deformation_whole(const double *device_aos_whole) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        const long long first = static_cast<long long>(g_.zoff) * g_.R * g_.C;  // global index of local voxel 0
+        k_import_aos<T><<<grid_lin_, 256, 0, stream_>>>(device_aos_whole + 3 * first, dD_, g_.N, 0, g_.N);
         DCMA_CUDA(cudaGetLastError());
         w_src_ = 1;
     }

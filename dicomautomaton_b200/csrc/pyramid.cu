@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "engine.h"
 #include "pyramid.h"
+#include "slab.h"
 
 namespace dcma {
 
@@ -241,7 +242,13 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
                       double *deformation_out, double *mse_history, dcma_b200_run_stats *stats) {
     const int L = params.pyramid_levels;
     if (L < 1 || L > 4) throw std::invalid_argument("pyramid_levels must be in 1..4");
-    if (params.n_devices > 1) throw std::invalid_argument("pyramid_levels > 1 is not available together with z-slab sharding");
+    // n_devices > 1: the FINEST level -- all but 1/7 of the work -- is sharded into z-slabs over devices 0..n-1 of this
+    // process (SlabGroup); the coarse levels (1/8, 1/64, ... of the voxels) run whole on the current device
+    const bool sharded = params.n_devices > 1;
+    if (sharded && L < 2) throw std::invalid_argument("pyramid_register on slabs needs at least two levels");
+    if (params.device >= 0) DCMA_CUDA(cudaSetDevice(params.device));
+    int dev0 = 0;  // the coarse levels, the restriction and the prolongation run here; slab calls switch devices
+    DCMA_CUDA(cudaGetDevice(&dev0));
     std::vector<dcma_b200_geom> g(L);
     std::vector<std::array<int, 3>> hv(L);
     g[0] = geom;
@@ -249,18 +256,38 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
     dcma_b200_demons_params p = params;
     p.pyramid_levels = 1;
     std::vector<std::unique_ptr<EngineBase>> e(L);
-    e[0].reset(make_engine(g[0], p, nullptr, SlabSpec{}));
-    e[0]->load(fixed, moving, false);
+    std::unique_ptr<SlabGroup> grp0;
+    std::vector<int> devices;
+    int64_t halo0 = 0;
+    std::unique_ptr<DevBuf<float>> f0, m0;  // sharded: the whole finest images on the current device, for the restriction only
+    if (sharded) {
+        devices = slab_devices(params.n_devices);
+        // the warm start makes |D_z| at the finest level as large as the warp itself: composition gathers reach that far
+        halo0 = params.halo_planes > 0 ? params.halo_planes : std::max<int64_t>(SlabGroup::default_halo(g[0], p), 8);
+        p.n_devices = 0;
+        grp0.reset(new SlabGroup(g[0], p, devices, halo0));
+        grp0->load(fixed, moving, false);
+        DCMA_CUDA(cudaSetDevice(dev0));
+        const long long n0 = g[0].slices * g[0].rows * g[0].cols * g[0].channels;
+        f0.reset(new DevBuf<float>(n0));
+        m0.reset(new DevBuf<float>(n0));
+        DCMA_CUDA(cudaMemcpy(f0->p, fixed, sizeof(float) * static_cast<size_t>(n0), cudaMemcpyHostToDevice));
+        DCMA_CUDA(cudaMemcpy(m0->p, moving, sizeof(float) * static_cast<size_t>(n0), cudaMemcpyHostToDevice));
+    } else {
+        e[0].reset(make_engine(g[0], p, nullptr, SlabSpec{}));
+        e[0]->load(fixed, moving, false);
+    }
     for (int l = 1; l < L; ++l) {
         const long long nc = g[l].slices * g[l].rows * g[l].cols * g[l].channels;
         DevBuf<float> dF(nc), dM(nc);
-        e[l - 1]->sync();
+        if (e[l - 1]) e[l - 1]->sync();
         {
             // anti-aliasing low-pass of the level l-1 images (copies; the engine keeps the unfiltered ones), then decimation
             const long long nfine = g[l - 1].slices * g[l - 1].rows * g[l - 1].cols * g[l - 1].channels;
             DevBuf<float> lp(nfine), tmp(nfine);
             for (int which = 0; which < 2; ++which) {
-                const float *src = which == 0 ? e[l - 1]->fixed_dev() : e[l - 1]->moving_dev();
+                const float *src = (l == 1 && sharded) ? (which == 0 ? f0->p : m0->p)
+                                                       : (which == 0 ? e[l - 1]->fixed_dev() : e[l - 1]->moving_dev());
                 DCMA_CUDA(cudaMemcpyAsync(lp.p, src, sizeof(float) * static_cast<size_t>(nfine), cudaMemcpyDeviceToDevice, nullptr));
                 prefilter_image_device(g[l - 1], lp.p, tmp.p, hv[l].data(), nullptr);
                 restrict_image_device(g[l - 1], lp.p, g[l], hv[l].data(), which == 0 ? dF.p : dM.p, nullptr);
@@ -270,6 +297,10 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
         e[l].reset(make_engine(g[l], p, nullptr, SlabSpec{}));
         e[l]->load(dF.p, dM.p, true);
         e[l]->sync();
+        if (l == 1) {
+            f0.reset();
+            m0.reset();
+        }
     }
     dcma_b200_run_stats total;
     std::memset(&total, 0, sizeof(total));
@@ -282,9 +313,36 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
             e[l + 1]->sync();
             prolong_field_device(g[l + 1], aC.p, g[l], hv[l + 1].data(), aF.p, nullptr);
             DCMA_CUDA(cudaDeviceSynchronize());
+            e[l + 1].reset();
+            if (l == 0 && sharded) {
+                // finest level on slabs.  A composition gather that leaves the halo fails the run loudly; with the default
+                // halo the level is then repeated from the same warm start with a doubled one (as the one-shot call does)
+                for (;;) {
+                    DCMA_CUDA(cudaSetDevice(dev0));
+                    grp0->import_deformation_device(aF.p);
+                    dcma_b200_run_stats st;
+                    try {
+                        grp0->run(params.max_iterations, mse_history ? mse_history + hist_off : nullptr, &st);
+                    } catch (const std::logic_error &ex) {
+                        const bool overflow = std::string(ex.what()).find("left the slab halo") != std::string::npos;
+                        if (!overflow || params.halo_planes > 0 || halo0 * 2 * params.n_devices > geom.slices) throw;
+                        halo0 *= 2;
+                        grp0.reset();
+                        grp0.reset(new SlabGroup(g[0], p, devices, halo0));
+                        grp0->load(fixed, moving, false);
+                        continue;
+                    }
+                    hist_off += st.iterations_done;
+                    total.iterations_done += st.iterations_done;
+                    total.kernel_launches += st.kernel_launches;
+                    total.loop_ms += st.loop_ms;
+                    break;
+                }
+                DCMA_CUDA(cudaSetDevice(dev0));
+                continue;
+            }
             e[l]->import_deformation_device(aF.p);
             e[l]->sync();
-            e[l + 1].reset();
         }
         int64_t iters = params.max_iterations;
         if (l >= 1 && l - 1 < 3 && params.pyramid_iterations[l - 1] > 0) iters = params.pyramid_iterations[l - 1];
@@ -295,7 +353,10 @@ void pyramid_register(const dcma_b200_geom &geom, const float *fixed, const floa
         total.kernel_launches += st.kernel_launches;
         total.loop_ms += st.loop_ms;
     }
-    e[0]->get(DCMA_B200_BUF_DEFORMATION, deformation_out);
+    if (sharded)
+        grp0->get_deformation(deformation_out);
+    else
+        e[0]->get(DCMA_B200_BUF_DEFORMATION, deformation_out);
     if (stats) *stats = total;
 }
 

@@ -195,6 +195,25 @@ void wait_flag(cudaStream_t st, const unsigned *flag, unsigned value) {
 }
 }  // namespace
 
+std::vector<int> slab_devices(int n) {
+    std::vector<int> dev;
+    if (const char *e = std::getenv("DCMA_B200_SLAB_DEVICES")) {
+        const char *p = e;
+        while (*p && static_cast<int>(dev.size()) < n) {
+            char *end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p || v < 0 || v > 1023) throw std::invalid_argument(std::string("DCMA_B200_SLAB_DEVICES='") + e + "' is not a list of device ordinals");
+            dev.push_back(static_cast<int>(v));
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',' && *end != '\0') throw std::invalid_argument(std::string("DCMA_B200_SLAB_DEVICES='") + e + "' is not a list of device ordinals");
+        }
+        if (static_cast<int>(dev.size()) < n) throw std::invalid_argument("DCMA_B200_SLAB_DEVICES lists fewer devices than n_devices");
+        return dev;
+    }
+    for (int i = 0; i < n; ++i) dev.push_back(i);
+    return dev;
+}
+
 void nccl_unique_id(unsigned char id[128]) {
     ncclUniqueId u;
     DCMA_NCCL(nccl().GetUniqueId(&u));
@@ -848,6 +867,11 @@ void SlabGroup::get_deformation(double *host_aos) {
         const SlabSpec s = l->eng->slab();
         l->eng->get_owned_deformation(host_aos + (s.zoff + s.own0 - z0) * plane3);
     }
+}
+
+void SlabGroup::import_deformation_device(const double *device_aos_whole) {
+    for (auto &l : locals_) l->eng->import_deformation_whole(device_aos_whole);
+    for (auto &l : locals_) l->eng->sync();
 }
 
 int64_t SlabGroup::device_bytes() const {

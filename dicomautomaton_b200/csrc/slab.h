@@ -14,6 +14,10 @@ namespace dcma {
 // contiguous balanced z-slabs (earlier ranks take the remainder) extended by `halo` planes on interior sides
 SlabSpec slab_for_rank(int64_t slices, int world, int rank, int64_t halo);
 void nccl_unique_id(unsigned char id[128]);
+// The devices a one-process registration with n_devices = n is sharded over: 0..n-1, or the first n entries of the
+// comma-separated list in DCMA_B200_SLAB_DEVICES (site policy, e.g. "4,5,6,7"; repeats are allowed, which is also how
+// the sharded paths are exercised on a single-GPU box).
+std::vector<int> slab_devices(int n);
 
 class SlabGroup {
   public:
@@ -27,6 +31,8 @@ class SlabGroup {
     void run(int64_t max_iterations, double *mse_history_host, dcma_b200_run_stats *stats);
     void owned_range(int64_t *z0, int64_t *z1) const;  // slices held by THIS process
     void get_deformation(double *host_aos);             // those slices, AoS doubles
+    // warm start (pyramid): D := the given field of the WHOLE volume, a device buffer every engine of the group can read
+    void import_deformation_device(const double *device_aos_whole);
     int64_t device_bytes() const;
     int64_t halo() const { return halo_; }
     int64_t halo_bytes_last_run() const { return halo_bytes_; }

@@ -71,6 +71,28 @@ def test_slab_group_with_the_symmetric_force(mode, diffeo):
     assert np.abs(Dn - Dw).max() > 1e-3
 
 
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_pyramid_with_the_finest_level_on_slabs(monkeypatch, symmetric):
+    """Extension a12 on slabs (BASELINE config 3 across GPUs): the coarse levels run whole on one device, the finest level --
+    warm-started from the prolonged coarse field, halo planes included -- on a slab group.  Same field as the one-device
+    pyramid, bit for bit.  DCMA_B200_SLAB_DEVICES maps both slabs onto device 0 so that a one-GPU box exercises the path;
+    the one-shot call with n_devices = 2 (no pyramid) takes the same device list."""
+    monkeypatch.setenv("DCMA_B200_SLAB_DEVICES", "0,0")
+    shape, sp = (48, 64, 64), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp, amplitude_mm=5.0)
+    kw = dict(pyramid_levels=3, pyramid_iterations=(12, 12, 0), use_symmetric_force=symmetric)
+    Dw, hw, stw = _whole(F, M, sp, _params("fp64_strict", 8, 1.5, True, **kw))
+    Ds, hs, sts = _whole(F, M, sp, _params("fp64_strict", 8, 1.5, True, n_devices=2, **kw))
+    assert sts.iterations_done == stw.iterations_done == 32
+    assert np.array_equal(Dw, Ds), f"max diff {np.abs(Dw - Ds).max():.3e}"
+    assert np.max(np.abs(hs - hw) / hw) <= 1e-12
+    assert np.abs(Dw).max() > 3.0   # the warm start is far larger than the default 4-plane halo rule assumes per iteration
+    # the plain sharded one-shot call honours the same device list
+    D1, _, _ = _whole(F, M, sp, _params("fp64", 6, 1.5, True))
+    D2, _, _ = _whole(F, M, sp, _params("fp64", 6, 1.5, True, n_devices=2))
+    assert np.array_equal(D1, D2)
+
+
 def test_slab_group_anisotropic_literal_smoothing_and_ragged_split():
     """per-axis radii (k_smooth_axis path), slices not divisible by the number of slabs, 2 mm slices (r_z = 2)."""
     shape, sp = (37, 21, 19), (0.9, 1.1, 2.0)
