@@ -9,7 +9,9 @@
 #include "Alignment_Demons.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -180,6 +182,16 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
         // the reference's route (resample_image_to_reference_grid, then marshal) and fails in marshal exactly as the
         // reference does when the result is not a regular grid.
         if (params.verbosity >= 1) YLOGINFO("Resampling moving image to reference grid");
+        // DCMA_B200_TRACE: host-side phase times of this call on stderr (diagnostics; the library prints its own line)
+        const bool trace = std::getenv("DCMA_B200_TRACE") != nullptr;
+        using clk = std::chrono::steady_clock;
+        auto t_prev = clk::now();
+        auto lap = [&](const char *what) {
+            if (!trace) return;
+            const auto now = clk::now();
+            std::fprintf(stderr, "[AlignViaDemons] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+            t_prev = now;
+        };
         dcma_b200_grid fg, mg;
         demons_volume<float> fixed_vol;  // header only (extents, spacing); the voxels live in the pinned buffers
         Pinned<float> fixed_px, moving_px;
@@ -201,6 +213,7 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
             nfix = static_cast<size_t>(fg.geom.slices * fg.geom.rows * fg.geom.cols * fg.geom.channels);
             fixed_px = Pinned<float>(nfix);
             marshal_into(stationary, fixed_px.data());
+            lap("marshal fixed (pinned)");
         } else {
             // not a stack the GPU resampler can describe (e.g. slices out of order in the list): the reference's own
             // marshalling decides whether it is acceptable at all, and throws its diagnostics if not
@@ -216,9 +229,11 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
             const size_t nmov = static_cast<size_t>(mg.geom.slices * mg.geom.rows * mg.geom.cols * mg.geom.channels);
             Pinned<float> raw(nmov);
             marshal_into(moving_in, raw.data());
+            lap("marshal moving (pinned)");
             char rerr[512] = {0};
             check_rc(dcma_b200_resample_to_grid(&mg, raw.data(), &fg, std::numeric_limits<float>::quiet_NaN(), moving_px.data(),
                                                 params.device, rerr, sizeof rerr), rerr);
+            lap("resample moving (GPU)");
         } else {
             auto moving = resample_image_to_reference_grid(moving_in, stationary);
             const auto mv = marshal_collection_to_volume(moving);
@@ -302,11 +317,16 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
             }
         });
         const int rc = dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err));
+        lap("dcma_b200_demons_register");
         builder.join();
+        lap("wait for the output stack");
         check_rc(rc, err);
         if (alloc_error) std::rethrow_exception(alloc_error);
         fill_from_dense(def_coll, def.data(), fixed_vol.rows, fixed_vol.cols, 3);
-        return deformation_field(std::move(def_coll));
+        lap("copy field into the stack");
+        deformation_field out(std::move(def_coll));
+        lap("deformation_field(...)");
+        return out;
     } catch (const std::exception &e) {
         YLOGWARN("Demons registration failed: " << e.what());
     }
