@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the B200-native Demons registration hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-mode fp64|fp64_strict|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-mode fp64|fp64_strict|mixed|fp32]
 
 A "step" is one pass of the hot path over one batch of synthetic input: one Demons registration of `--iters`
 iterations (default 200) on the BASELINE config-2 workload -- synthetic CT pair 512x512x256, diffeomorphic,
@@ -15,9 +15,12 @@ sigma_d = sigma_u = 1.5 mm, convergence threshold 0 (exactly `iters` iterations 
                       exchange over NVLink every iteration), "scaling": "strong".  The throughput of N independent
                       config-2 registrations (no data-path collective) is reported beside it as `replicas`, and
                       `--replicas` makes that the headline instead.
-  e2e       : the same metric through the C-ABI one-shot call `dcma_b200_demons_register` with HOST (pinned) buffers:
-              H2D of fixed+moving, the loop, and D2H of the fp64 deformation field are all inside the timed region.
-  roofline  : dominant kernel (k_smooth3d): algorithmic bytes per launch / mean launch time from CUDA events.
+  e2e       : the same metric through the reference-facing call itself, the C++ drop-in AlignViaDemons(params, moving,
+              fixed) behind host/dropin_harness.cc: image stacks in, deformation_field out; marshalling both ways, GPU
+              resampling, H2D of fixed+moving, the loop and D2H of the fp64 field are all inside the timed region.  The
+              C-ABI one-shot call `dcma_b200_demons_register` with pinned caller buffers is timed beside it (`c_abi`).
+  roofline  : per-kernel table from the CUDA-event stage profile (algorithmic bytes per launch / mean launch time);
+              the headline object is the kernel with the largest share of the step.
   cpu_baseline : the reference's own engine (oracle/_ref, built from /root/reference sources) on the host cores.
 
 `--impl reference` times the reference CPU engine itself on a bounded sample of the same workload.
@@ -475,10 +478,11 @@ def run_ours(args):
                 "ms_per_iteration": ms / max(iters_done, 1), "final_mse": final_mse,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline,
                 "cpu_baseline": cpu, "other_modes": other,
-                "parity": "vs the reference engine compiled from its own sources, same inputs, 512x512x256, 200 "
-                          "iterations (profiles/r1_full_size_parity_512x512x256_200it.json): fp64_strict bit-identical; "
-                          "fp64 max |dD| 3.0e-7 mm, final MSE 1.9e-10 relative; fp32 max |dD| 1.8e-3 mm (99.99th "
-                          "percentile 4.1e-6 mm), final MSE 1.3e-6 relative.  Tolerance: 1e-3 mm / 1e-4."}
+                "parity": "vs fixtures written by the reference engine compiled from its own sources, same inputs, "
+                          "512x512x256, 200 iterations (tests/test_gpu_full_length.py, profiles/r2_full_length_parity.jsonl): "
+                          "fp64_strict bit-identical (sha256 of the whole field); fp64 max |dD| 2.8e-7 mm, final MSE 3.8e-10 "
+                          "relative; mixed 2.8e-7 mm / 7.5e-9; fp32 1.1e-3 mm (99.99th percentile 3.1e-6 mm) / 9.6e-7.  "
+                          "Tolerance: 1e-3 mm / 1e-4."}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -714,11 +718,11 @@ def main():
     ap.add_argument("--iters", type=int, default=200, help="Demons iterations per step (BASELINE config 2: 200)")
     ap.add_argument("--field-mode", default=os.environ.get("DCMA_B200_FIELD_MODE", "fp64"),
                     choices=["fp64", "fp64_strict", "mixed", "fp32"],
-                    help="field storage/arithmetic of the measured run.  Default fp64: the reference's own storage type, "
-                         "3e-7 mm from the reference engine after 200 iterations at full size.  fp32 (float fields, "
-                         "FFMA2 smoothing) is ~1.9x faster and is reported beside it in `other_modes`; at full size its "
-                         "worst voxel is 1.8e-3 mm off (99.99 %% of voxels within 4e-6 mm), i.e. outside the 1e-3 mm "
-                         "tolerance, so it is not the headline")
+                    help="field storage/arithmetic of the measured run.  Default fp64: the reference's own storage type and "
+                         "arithmetic, 3e-7 mm from the reference engine after 200 iterations at full size.  mixed (D double, "
+                         "U float; the same 3e-7 mm) is ~1.15x faster, fp32 (float fields, FFMA2 smoothing) ~1.55x; both are "
+                         "reported beside the headline in `other_modes`.  fp32's worst voxel at full size is 1.1e-3 mm off "
+                         "(99.99 %% of voxels within 3e-6 mm), i.e. outside the 1e-3 mm tolerance")
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other field modes reported beside the headline")
     ap.add_argument("--other-modes", default="mixed,fp32", help="field modes reported beside the headline (50-iteration runs)")
     ap.add_argument("--e2e-steps", type=int, default=3, help="timed steps of the pinned C-ABI end-to-end figure")
