@@ -37,6 +37,7 @@ UNITS = {
     "slab.cu": [],
     "pyramid.cu": [],
     "warp_grid.cu": [],
+    "virtual_field.cu": [],
     "histmatch.cu": ["-fmad=false"],
     "text_io.cu": [],
     "c_api.cu": [],

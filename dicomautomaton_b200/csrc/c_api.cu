@@ -422,6 +422,12 @@ int dcma_b200_warp_to_grid(const dcma_b200_grid *field_grid, const double *defor
         errbuf, errbuf_len);
 }
 
+int dcma_b200_virtual_field(int32_t kind, const dcma_b200_grid *grid, const double *bounds, double *field_out, double *extremes,
+                            int device, char *errbuf, size_t errbuf_len) {
+    if (!grid || !bounds || !field_out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    return guarded([&]() { dcma::virtual_field_host(kind, *grid, bounds, field_out, extremes, device); }, errbuf, errbuf_len);
+}
+
 int dcma_b200_resample_to_grid(const dcma_b200_grid *src_grid, const float *image, const dcma_b200_grid *dst_grid, float oob_value,
                                float *out, int device, char *errbuf, size_t errbuf_len) {
     if (!src_grid || !image || !dst_grid || !out) return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);

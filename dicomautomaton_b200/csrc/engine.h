@@ -86,6 +86,10 @@ void warp_to_grid_host(const dcma_b200_grid &field_grid, const double *deformati
 void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
                            float *out, int device);
 
+// the two synthetic deformation fields of the reference's generator operations (virtual_field.cu); extremes[2] (may be
+// null) receives the minimum and maximum displacement magnitude before normalisation
+void virtual_field_host(int kind, const dcma_b200_grid &grid, const double bounds[6], double *out_aos, double extremes[2], int device);
+
 // the numeric payload of deformation_field::write_to / read_from (src/Alignment_Field.cc:322-436) on the GPU (text_io.cu)
 long long format_doubles_host(const double *values, long long n, char *out, long long capacity, int device);
 long long parse_doubles_host(const char *text, long long nbytes, long long n, double *out, int device);

@@ -288,6 +288,27 @@ def warp_to_grid(field_grid: capi.Grid, deformation: np.ndarray, source_grid: ca
     return out
 
 
+VFIELD_KINDS = {"sinusoidal_v1": 0, "vortex_v1": 1}
+
+
+def virtual_field_v1(kind: str, shape=(100, 512, 512), bounds=(0.0, 512.0, 0.0, 512.0, 0.0, 100.0), device: int = -1):
+    """The synthetic deformation field of GenerateVirtualDataSinusoidalFieldV1 / GenerateVirtualDataVortexFieldV1 (reference
+    src/Operations/GenerateVirtualData{Sinusoidal,Vortex}FieldV1.cc) on the operations' grid: `shape` voxels across `bounds`,
+    in-plane positions at pxl * index (img.position of a stack anchored at the origin), slices at z_min + pxl_dz * (z + 1/2).
+    Returns (field (S,R,C,3) float64 mm, grid, (min, max) magnitude before normalisation)."""
+    lib = capi.lib()
+    S, R, Cn = (int(v) for v in shape)
+    b = np.asarray(bounds, dtype=np.float64)
+    sp = ((b[1] - b[0]) / Cn, (b[3] - b[2]) / R, (b[5] - b[4]) / S)
+    grid = make_grid((S, R, Cn), sp, origin=(0.0, 0.0, b[4] + 0.5 * sp[2]), channels=3)
+    out = np.empty((S, R, Cn, 3), dtype=np.float64)
+    ext = np.zeros(2, dtype=np.float64)
+    err = C.create_string_buffer(512)
+    capi.check(lib.dcma_b200_virtual_field(VFIELD_KINDS[kind], C.byref(grid), b.ctypes.data, out.ctypes.data, ext.ctypes.data,
+                                           device, err, len(err)), err)
+    return out, grid, (float(ext[0]), float(ext[1]))
+
+
 def resample_to_grid(src_grid: capi.Grid, image: np.ndarray, dst_grid: capi.Grid, oob_value: float = float("nan"),
                      device: int = -1) -> np.ndarray:
     """resample_image_to_reference_grid (reference src/Alignment_Demons.cc:709-755) for regular grids."""

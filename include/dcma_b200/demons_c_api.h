@@ -272,6 +272,18 @@ DCMA_B200_API int dcma_b200_warp_to_grid(const dcma_b200_grid *field_grid, const
                                          const unsigned char *mask, int32_t channel, float oob_value, float *out_inout,
                                          int device, char *errbuf, size_t errbuf_len);
 
+/* ---- synthetic deformation fields for testing a registration (the reference's generator operations) -------------- */
+/* field_out[z][y][x][3] (mm, AoS doubles, `grid` voxels) := the field of GenerateVirtualDataSinusoidalFieldV1
+ * (src/Operations/GenerateVirtualDataSinusoidalFieldV1.cc:77-193: three plane waves with 2, 3 and 1.5 periods across
+ * the bounds, magnitudes rescaled to [0, 1]) or of GenerateVirtualDataVortexFieldV1
+ * (src/Operations/GenerateVirtualDataVortexFieldV1.cc:75-178: a cylindrical vortex about the centre of the bounds,
+ * divided by its largest magnitude).  bounds = {x_min, x_max, y_min, y_max, z_min, z_max}; the operations use
+ * {0, 512, 0, 512, 0, 100} on a 512 x 512 x 100 grid whose slice z sits at z_min + pxl_dz * (z + 1/2).  extremes (may be
+ * NULL) := {min, max} displacement magnitude before normalisation (the operations record them as metadata).  HOST. */
+typedef enum { DCMA_B200_VFIELD_SINUSOIDAL_V1 = 0, DCMA_B200_VFIELD_VORTEX_V1 = 1 } dcma_b200_vfield_kind;
+DCMA_B200_API int dcma_b200_virtual_field(int32_t kind, const dcma_b200_grid *grid, const double *bounds, double *field_out,
+                                          double *extremes, int device, char *errbuf, size_t errbuf_len);
+
 /* resample_image_to_reference_grid (src/Alignment_Demons.cc:709-755): the source image sampled trilinearly at the
  * positions of the destination grid's voxels, `oob_value` (the reference passes NaN, cc:743) outside the source grid.
  * out: dst voxels x src channels.  The reference's lookup is Ygor's (unpinned); definition as dcma_b200_warp_image_grid. */

@@ -274,6 +274,44 @@ def warp_to_grid(field, f_spacing, f_origin, source, s_spacing, s_origin, placeh
     return out
 
 
+def virtual_field_v1(kind, shape=(100, 512, 512), bounds=(0.0, 512.0, 0.0, 512.0, 0.0, 100.0)):
+    """Row f4: the host loops of GenerateVirtualDataSinusoidalFieldV1.cc:77-193 / GenerateVirtualDataVortexFieldV1.cc:75-178
+    restated with numpy (libm sin/cos/exp, as the reference uses).  Returns (field (S,R,C,3), (min, max) magnitude)."""
+    S, R, C = shape
+    x_min, x_max, y_min, y_max, z_min, z_max = bounds
+    px, py, pz = (x_max - x_min) / C, (y_max - y_min) / R, (z_max - z_min) / S
+    z, y, x = np.meshgrid(z_min + pz * (np.arange(S) + 0.5), py * np.arange(R), px * np.arange(C), indexing="ij")
+    if kind == "sinusoidal_v1":
+        wlx, wly, wlz = (x_max - x_min) / 2.0, (y_max - y_min) / 3.0, (z_max - z_min) / 1.5
+        pi = np.arccos(-1.0)
+        sx, sy, cz = np.sin(2.0 * pi * (x - x_min) / wlx), np.sin(2.0 * pi * (y - y_min) / wly), np.cos(2.0 * pi * (z - z_min) / wlz)
+        d = np.stack([sy * cz, sx * cz, sx * sy], axis=-1)
+        m = np.sqrt((d * d).sum(-1))
+        mn, mx = float(m.min()), float(m.max())
+        if mx > mn and mx > 1e-10:
+            s = np.where(m > 1e-10, ((m - mn) / (mx - mn)) / np.where(m > 1e-10, m, 1.0), 0.0)
+            d = d * s[..., None]
+        return d, (mn, mx)
+    if kind != "vortex_v1":
+        raise ValueError(kind)
+    cx, cy, cz0 = 0.5 * (x_min + x_max), 0.5 * (y_min + y_max), 0.5 * (z_min + z_max)
+    fx, fy, fz = x - cx, y - cy, z - cz0
+    r = np.sqrt(fx * fx + fy * fy)
+    ok = r > 1e-6
+    rs = np.where(ok, r, 1.0)
+    rn = r / min(cx, cy)
+    prof = rn * np.exp(-2.0 * (rn - 0.5) * (rn - 0.5))
+    zn = np.abs(fz) / ((z_max - z_min) / 2.0)
+    zs = 0.3 * np.exp(-zn * zn)
+    d = np.stack([np.where(ok, -fy / rs * prof, 0.0), np.where(ok, fx / rs * prof, 0.0),
+                  np.where(ok, zs * prof * np.where(fz > 0, 1.0, -1.0), 0.0)], axis=-1)
+    m = np.sqrt((d * d).sum(-1))
+    mx = float(m.max())
+    if mx > 1e-10:
+        d = d / mx
+    return d, (float(m.min()), mx)
+
+
 # ---- row a14 / f4: histogram_match, reference src/Alignment_Demons.cc:760-891 (pure std:: code, no Ygor arithmetic) ----
 # PINNED: tests/test_oracle_extensions.py checks the reference's own known answers (10, 17.5, 25, 32.5 for a 2x2 ramp
 # with 4 bins, constants returned unchanged: src/Alignment_Demons_Tests.cc:204-236).

@@ -188,6 +188,41 @@ def test_warp_with_three_stacks_as_the_operation_has_them():
         warp_to_grid(fg, D, sg, src, og2, place2, channel=1)   # the source stack has no channel 1
 
 
+@pytest.mark.parametrize("kind", ["sinusoidal_v1", "vortex_v1"])
+def test_virtual_field_generators_match_the_host_loops(kind):
+    """Row f4: dcma_b200_virtual_field vs the numpy restatement of the generator operations' host loops
+    (src/Operations/GenerateVirtualData{Sinusoidal,Vortex}FieldV1.cc), on a reduced grid and on the operations' own
+    512 x 512 x 100 grid.  CUDA's sin/cos/exp are not libm's: equal to 1e-13, not bit for bit."""
+    from dicomautomaton_b200.demons import virtual_field_v1
+    from oracle import extensions as ext
+    for shape in ((12, 40, 56), (100, 512, 512)):
+        got, grid, (gmn, gmx) = virtual_field_v1(kind, shape)
+        ref, (rmn, rmx) = ext.virtual_field_v1(kind, shape)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-13
+        assert abs(gmx - rmx) <= 1e-13 and abs(gmn - rmn) <= 1e-13
+        assert abs(np.sqrt((got * got).sum(-1)).max() - 1.0) <= 1e-12
+        assert (grid.geom.slices, grid.geom.rows, grid.geom.cols) == shape and abs(grid.origin[2] - 0.5 * 100.0 / shape[0]) < 1e-12
+
+
+def test_generated_field_warps_an_image_and_demons_recovers_it():
+    """The use the reference makes of the generators: a known field -> warped image -> registration.  Field from
+    dcma_b200_virtual_field (scaled to 3 mm), moving = fixed warped through it (WarpImages' voxel body), then the loop."""
+    from dicomautomaton_b200.demons import (AlignViaDemons, AlignViaDemonsParams, demons_volume, make_grid, virtual_field_v1,
+                                            warp_image_on_grid)
+    shape = (24, 96, 96)
+    w, grid, _ = virtual_field_v1("sinusoidal_v1", shape, bounds=(0.0, 96.0, 0.0, 96.0, 0.0, 24.0))
+    w *= 3.0
+    F, _ = phantom_pair(shape)
+    ig = make_grid(shape, (1.0, 1.0, 1.0), origin=tuple(grid.origin))
+    M = warp_image_on_grid(grid, w, ig, F, oob_value=float("nan"))
+    M = np.where(np.isfinite(M), M, F)
+    par = AlignViaDemonsParams(max_iterations=80, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
+                               update_field_smoothing_sigma=1.5, use_diffeomorphic=True, verbosity=0, field_mode="fp64")
+    out, hist, st = AlignViaDemons(par, demons_volume(M), demons_volume(F), return_stats=True)
+    assert out is not None and st.iterations_done == 80
+    assert hist[-1] < 0.2 * hist[0]
+
+
 def test_gpu_histogram_match_is_bit_identical_to_the_reference_algorithm():
     """dcma_b200_histogram_match vs the pinned restatement of src/Alignment_Demons.cc:760-891: the reference's known
     answers, then random CT-like volumes with NaNs, outliers, different sizes and bin counts -- bit for bit."""

@@ -78,3 +78,27 @@ def test_histogram_match_restatement_reproduces_the_reference_known_answers():
     assert not m and np.array_equal(o, c5)
     o, m = ext.histogram_match(src, c10, 8, 0.0)
     assert not m and np.array_equal(o, src)
+
+
+def test_virtual_fields_have_the_properties_the_generator_operations_state():
+    """Row f4 restatement (oracle/extensions.py::virtual_field_v1) of GenerateVirtualData{Sinusoidal,Vortex}FieldV1: the
+    operations' own descriptions are the known answers -- sinusoidal: 'magnitude ... normalized everywhere to a maximum of
+    1.0 and a minimum of 0.0' (SinusoidalFieldV1.cc:33-35); vortex: tangential in the xy plane about the centre, largest
+    magnitude 1 (VortexFieldV1.cc:100-178)."""
+    from oracle import extensions as ext
+    shape, bounds = (20, 96, 96), (0.0, 512.0, 0.0, 512.0, 0.0, 100.0)
+    d, (mn, mx) = ext.virtual_field_v1("sinusoidal_v1", shape, bounds)
+    m = np.sqrt((d * d).sum(-1))
+    assert abs(m.max() - 1.0) < 1e-12 and m.min() < 1e-12 and 0.0 <= mn < mx <= np.sqrt(3.0) + 1e-12
+    assert np.all(d[:, 0, 0, :] == 0.0)   # x = y = 0: every component has a sin(0) factor
+    v, (vmn, vmx) = ext.virtual_field_v1("vortex_v1", shape, bounds)
+    vm = np.sqrt((v * v).sum(-1))
+    assert abs(vm.max() - 1.0) < 1e-12
+    S, R, C = shape
+    y, x = np.meshgrid(512.0 / R * np.arange(R) - 256.0, 512.0 / C * np.arange(C) - 256.0, indexing="ij")
+    radial = v[..., 0] * x[None] + v[..., 1] * y[None]
+    assert np.abs(radial).max() < 1e-9                      # in-plane displacement is tangential
+    assert np.all(v[S // 2:, ..., 2] >= 0.0) and np.all(v[:S // 2, ..., 2] <= 0.0)   # dz points away from the mid-plane
+    # the two-pass structure: the second pass is a pure rescale of the first
+    full, _ = ext.virtual_field_v1("vortex_v1", (4, 33, 47), bounds)
+    assert full.shape == (4, 33, 47, 3) and np.isfinite(full).all()
