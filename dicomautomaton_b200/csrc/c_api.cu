@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <limits>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -266,6 +267,81 @@ int dcma_b200_demons_register(const dcma_b200_geom *geom, const float *fixed, co
                 stats->d2h_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
                 stats->h2d_bytes = 2 * n * geom->channels * static_cast<long long>(sizeof(float));
                 stats->d2h_bytes = 3 * n * static_cast<long long>(sizeof(double));
+            }
+        },
+        errbuf, errbuf_len);
+}
+
+int dcma_b200_demons_register_stacks(const dcma_b200_grid *fixed_grid, const float *fixed, const dcma_b200_grid *moving_grid,
+                                     const float *moving, const dcma_b200_demons_params *params, double *deformation_out,
+                                     double *mse_history, dcma_b200_run_stats *stats, dcma_b200_chunk_fn on_field_chunk,
+                                     void *user, char *errbuf, size_t errbuf_len) {
+    if (!fixed_grid || !fixed || !moving_grid || !moving || !params || !deformation_out)
+        return fail(DCMA_B200_EINVAL, "null argument", errbuf, errbuf_len);
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    const dcma_b200_geom &geom = fixed_grid->geom;
+    const long long nvox = geom.slices * geom.rows * geom.cols;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    if (moving_grid->geom.channels != geom.channels)
+        return fail(DCMA_B200_EINVAL, "moving and fixed stacks differ in channel count", errbuf, errbuf_len);
+    if (params->pyramid_levels > 1 || params->n_devices > 1) {
+        // pyramids and sharded runs take whole host volumes: resample through the host-buffer call, then the one-shot call
+        std::vector<float> resampled;
+        int rc = guarded([&]() {
+            resampled.resize(static_cast<size_t>(nvox * geom.channels));
+            dcma::resample_to_grid_host(*moving_grid, moving, *fixed_grid, nan, resampled.data(), params->device);
+        }, errbuf, errbuf_len);
+        if (rc != DCMA_B200_OK) return rc;
+        rc = dcma_b200_demons_register(&geom, fixed, resampled.data(), params, deformation_out, mse_history, stats, errbuf, errbuf_len);
+        if (rc == DCMA_B200_OK && on_field_chunk) on_field_chunk(user, 0, nvox);
+        return rc;
+    }
+    return guarded(
+        [&]() {
+            using clk = std::chrono::steady_clock;
+            struct Holder {
+                dcma::EngineBase *p = nullptr;
+                float *d[3] = {nullptr, nullptr, nullptr};
+                ~Holder() {
+                    for (float *q : d) cudaFree(q);
+                    delete p;
+                }
+            } h;
+            const auto tc = clk::now();
+            h.p = make(geom, *params, nullptr);  // selects the device
+            cudaStream_t st = static_cast<cudaStream_t>(h.p->stream_handle());
+            const long long nmov = moving_grid->geom.slices * moving_grid->geom.rows * moving_grid->geom.cols * geom.channels;
+            const size_t bf = sizeof(float) * static_cast<size_t>(nvox * geom.channels), bm = sizeof(float) * static_cast<size_t>(nmov);
+            const auto t0 = clk::now();
+            DCMA_CUDA(cudaMalloc(&h.d[0], bf));
+            DCMA_CUDA(cudaMalloc(&h.d[1], bm));
+            DCMA_CUDA(cudaMalloc(&h.d[2], bf));
+            DCMA_CUDA(cudaMemcpyAsync(h.d[0], fixed, bf, cudaMemcpyHostToDevice, st));
+            DCMA_CUDA(cudaMemcpyAsync(h.d[1], moving, bm, cudaMemcpyHostToDevice, st));
+            dcma::resample_to_grid_device(*moving_grid, h.d[1], *fixed_grid, nan, h.d[2], st);   // = cc:964 on the device
+            h.p->load(h.d[0], h.d[2], true);
+            h.p->sync();
+            for (float *&q : h.d) {
+                cudaFree(q);
+                q = nullptr;
+            }
+            const auto t1 = clk::now();
+            dcma_b200_run_stats local;
+            h.p->run(params->max_iterations, false, mse_history, &local);
+            const auto t2 = clk::now();
+            h.p->get_deformation_chunked(deformation_out, on_field_chunk, user);
+            const auto t3 = clk::now();
+            if (std::getenv("DCMA_B200_TRACE")) {
+                auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                std::fprintf(stderr, "[dcma_b200] create %.2f ms, H2D + resample + load %.2f ms, run %.2f ms (device loop %.2f ms), get(D2H, chunked) %.2f ms\n",
+                             ms(tc, t0), ms(t0, t1), ms(t1, t2), local.loop_ms, ms(t2, t3));
+            }
+            if (stats) {
+                *stats = local;
+                stats->h2d_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+                stats->d2h_ms = std::chrono::duration<double, std::milli>(t3 - t2).count();
+                stats->h2d_bytes = static_cast<long long>(bf + bm);
+                stats->d2h_bytes = 3 * nvox * static_cast<long long>(sizeof(double));
             }
         },
         errbuf, errbuf_len);

@@ -45,6 +45,9 @@ class EngineBase {
     virtual void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) = 0;
     virtual void stage(int stage, double sigma_mm, double *mse_out, int64_t *n_valid_out) = 0;
     virtual void get(int buffer, void *host) = 0;
+    // the deformation field (AoS doubles, owned slices) with a notification per landed chunk: `on_chunk(user, v0, v1)` is
+    // called on the calling thread when voxels [v0, v1) of `host` are complete, ascending, while later chunks are in flight
+    virtual void get_deformation_chunked(double *host, void (*on_chunk)(void *, int64_t, int64_t), void *user) = 0;
     virtual void set(int buffer, const void *host) = 0;
     virtual void export_deformation_device(double *device_out) = 0;
     virtual void import_deformation_device(const double *device_aos) = 0;  // warm start: D := field, W := warp(M, D)
@@ -83,6 +86,9 @@ void warp_to_grid_host(const dcma_b200_grid &field_grid, const double *deformati
                        const float *source, const dcma_b200_grid &out_grid, const unsigned char *mask, int channel, float oob_value,
                        float *out_inout, int device);
 
+// device-pointer form of the same kernel, on `stream` (void* = cudaStream_t); out: dst voxels x src channels
+void resample_to_grid_device(const dcma_b200_grid &src_grid, const float *d_image, const dcma_b200_grid &dst_grid, float oob_value,
+                             float *d_out, void *stream);
 void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
                            float *out, int device);
 

@@ -533,8 +533,12 @@ class Engine final : public EngineBase {
         if (!d_stage_[half]) d_stage_[half] = alloc<double>(3 * kStageVoxels);
         return d_stage_[half];
     }
+    void get_deformation_chunked(double *host, void (*on_chunk)(void *, int64_t, int64_t), void *user) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        export_field_host(dD_, host, on_chunk, user);
+    }
     template <typename X>
-    void export_field_host(const X *field, double *host) {
+    void export_field_host(const X *field, double *host, void (*on_chunk)(void *, int64_t, int64_t) = nullptr, void *user = nullptr) {
         if (!ev_stage_[0]) {
             DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[0], cudaEventDisableTiming));
             DCMA_CUDA(cudaEventCreateWithFlags(&ev_stage_[1], cudaEventDisableTiming));
@@ -543,6 +547,7 @@ class Engine final : public EngineBase {
         cudaEvent_t done;
         DCMA_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         int k = 0;
+        long long last_v0 = 0, last_v1 = 0;
         const long long vb = owned_v0(), ve = owned_v1();  // owned slices only; the AoS output starts at the first of them
         for (long long v0 = vb; v0 < ve; v0 += kStageVoxels, ++k) {
             const long long v1 = std::min(ve, v0 + kStageVoxels);
@@ -556,9 +561,16 @@ class Engine final : public EngineBase {
             DCMA_CUDA(cudaStreamWaitEvent(copy_stream_, done, 0));
             DCMA_CUDA(cudaMemcpyAsync(host + 3 * (v0 - vb), st, sizeof(double) * 3 * (v1 - v0), cudaMemcpyDeviceToHost, copy_stream_));
             DCMA_CUDA(cudaEventRecord(ev_stage_[half], copy_stream_));
+            if (on_chunk && k >= 1) {  // the previous chunk's copy: its event is the other half's, recorded one step ago
+                DCMA_CUDA(cudaEventSynchronize(ev_stage_[half ^ 1]));
+                on_chunk(user, (v0 - kStageVoxels) - vb, v0 - vb);
+            }
+            last_v0 = v0;
+            last_v1 = v1;
         }
         DCMA_CUDA(cudaStreamSynchronize(copy_stream_));
         DCMA_CUDA(cudaStreamSynchronize(stream_));
+        if (on_chunk && last_v1 > last_v0) on_chunk(user, last_v0 - vb, last_v1 - vb);
         cudaEventDestroy(done);
     }
     template <typename X>

@@ -276,6 +276,16 @@ void warp_to_grid_host(const dcma_b200_grid &field_grid, const double *deformati
     cleanup();
 }
 
+void resample_to_grid_device(const dcma_b200_grid &src_grid, const float *d_image, const dcma_b200_grid &dst_grid, float oob_value,
+                             float *d_out, void *stream) {
+    const GridK sg = make_gridk(src_grid);
+    const GridK dg = make_gridk(dst_grid);
+    const long long nv = static_cast<long long>(dg.S) * dg.R * dg.C;
+    k_resample_grid<<<static_cast<int>(std::min<long long>((nv + 255) / 256, 148LL * 16)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        sg, d_image, dg, oob_value, d_out);
+    DCMA_CUDA(cudaGetLastError());
+}
+
 void resample_to_grid_host(const dcma_b200_grid &src_grid, const float *image, const dcma_b200_grid &dst_grid, float oob_value,
                            float *out, int device) {
     int ndev = 0;

@@ -288,6 +288,31 @@ def warp_to_grid(field_grid: capi.Grid, deformation: np.ndarray, source_grid: ca
     return out
 
 
+CHUNK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
+
+
+def register_stacks(params: "AlignViaDemonsParams", fixed_grid: capi.Grid, fixed: np.ndarray, moving_grid: capi.Grid,
+                    moving: np.ndarray, on_chunk=None):
+    """dcma_b200_demons_register_stacks: the moving stack (on its own regular grid) is resampled onto the fixed grid on the
+    device, registered, and the field comes back in chunks; `on_chunk(voxel_begin, voxel_end)` is called per landed chunk.
+    Returns (deformation (S,R,C,3) float64, mse_history, stats)."""
+    lib = capi.lib()
+    f = np.ascontiguousarray(fixed, dtype=np.float32)
+    m = np.ascontiguousarray(moving, dtype=np.float32)
+    g = fixed_grid.geom
+    out = np.empty((g.slices, g.rows, g.cols, 3), dtype=np.float64)
+    cp = params.to_c()
+    n_hist = int(params.max_iterations) * (1 if params.pyramid_levels <= 1 else 1) + sum(int(v) for v in params.pyramid_iterations)
+    hist = np.zeros(max(n_hist, 1), dtype=np.float64)
+    st = capi.RunStats()
+    err = C.create_string_buffer(512)
+    cb = CHUNK_FN(lambda user, a, b: on_chunk(int(a), int(b))) if on_chunk is not None else None
+    capi.check(lib.dcma_b200_demons_register_stacks(C.byref(fixed_grid), f.ctypes.data, C.byref(moving_grid), m.ctypes.data,
+                                                    C.byref(cp), out.ctypes.data, hist.ctypes.data, C.byref(st),
+                                                    C.cast(cb, C.c_void_p) if cb is not None else None, None, err, len(err)), err)
+    return out, hist[:st.iterations_done], st
+
+
 VFIELD_KINDS = {"sinusoidal_v1": 0, "vortex_v1": 1}
 
 

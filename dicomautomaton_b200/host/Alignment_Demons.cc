@@ -18,6 +18,7 @@
 #include <mutex>
 #include <string>
 #include <exception>
+#include <future>
 #include <thread>
 #include <vector>
 
@@ -224,12 +225,23 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
             fv.data.clear();
             fixed_vol = fv;
         }
-        moving_px = Pinned<float>(nfix);
-        if (fixed_regular && grid_of(moving_in, mg) && mg.geom.channels == fg.geom.channels) {
+        // Both stacks regular and no histogram matching (which needs the resampled image on the host): ONE call resamples on
+        // the device, iterates and streams the field back in chunks (dcma_b200_demons_register_stacks, below).
+        const bool moving_regular = fixed_regular && grid_of(moving_in, mg) && mg.geom.channels == fg.geom.channels;
+        // (the engine takes its slice spacing from the FIRST image's pxl_dz, Alignment_Demons.h:160-162, the resampling from the
+        // slice POSITIONS: the single call describes both with one grid, so it is used when the two agree)
+        const bool one_call = moving_regular && !params.use_histogram_matching && fixed_vol.pxl_dz == fg.geom.pxl_dz;
+        Pinned<float> raw;
+        if (moving_regular) {
             const size_t nmov = static_cast<size_t>(mg.geom.slices * mg.geom.rows * mg.geom.cols * mg.geom.channels);
-            Pinned<float> raw(nmov);
+            raw = Pinned<float>(nmov);
             marshal_into(moving_in, raw.data());
             lap("marshal moving (pinned)");
+        }
+        if (!one_call) moving_px = Pinned<float>(nfix);
+        if (one_call) {
+            // resampled on the device inside the registration call
+        } else if (moving_regular) {
             char rerr[512] = {0};
             check_rc(dcma_b200_resample_to_grid(&mg, raw.data(), &fg, std::numeric_limits<float>::quiet_NaN(), moving_px.data(),
                                                 params.device, rerr, sizeof rerr), rerr);
@@ -316,13 +328,74 @@ std::optional<deformation_field> AlignViaDemons(AlignViaDemonsParams &params,
                 alloc_error = std::current_exception();
             }
         });
-        const int rc = dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err));
-        lap("dcma_b200_demons_register");
-        builder.join();
+        // Chunks of the field are copied into the output stack as they land, by helper tasks, while the rest of the field
+        // is still crossing PCIe.  The callback runs on this thread inside the C call: it must not throw.
+        struct ChunkCopy {
+            std::thread *builder;
+            planar_image_collection<double, double> *coll;
+            const double *src;
+            int64_t R, C;
+            std::vector<planar_image<double, double> *> imgs;
+            std::vector<std::future<void>> tasks;
+            std::exception_ptr error;
+            bool dense = false;
+            void ready() {
+                if (builder->joinable()) builder->join();
+                if (!imgs.empty()) return;
+                for (auto &img : coll->images) imgs.push_back(&img);
+                if (imgs.empty()) return;
+                const auto &a = *imgs.front();
+                dense = (a.index(0, 0, 0) == 0) && (a.index(0, 0, 1) == 1) && (C == 1 || a.index(0, 1, 0) == 3) &&
+                        (R == 1 || a.index(1, 0, 0) == C * 3) && a.data.size() == static_cast<size_t>(R * C * 3);
+            }
+            void copy(int64_t v0, int64_t v1) {  // voxels [v0, v1) of the dense field -> the images they belong to
+                const int64_t per = R * C;
+                for (int64_t v = v0; v < v1;) {
+                    const int64_t z = v / per, in0 = v - z * per, n = std::min(per - in0, v1 - v);
+                    auto &img = *imgs.at(static_cast<size_t>(z));
+                    const double *s = src + 3 * v;
+                    if (dense) {
+                        std::memcpy(img.data.data() + 3 * in0, s, static_cast<size_t>(3 * n) * sizeof(double));
+                    } else {
+                        for (int64_t i = 0; i < n; ++i) {
+                            const int64_t y = (in0 + i) / C, x = (in0 + i) - y * C;
+                            for (int64_t c = 0; c < 3; ++c) img.reference(y, x, c) = s[3 * i + c];
+                        }
+                    }
+                    v += n;
+                }
+            }
+            static void on_chunk(void *user, int64_t v0, int64_t v1) {
+                auto *self = static_cast<ChunkCopy *>(user);
+                try {
+                    self->ready();
+                    if (self->imgs.empty()) return;  // the stack could not be built: reported after the call
+                    // a 48 MiB chunk in 4 pieces: one thread copies at a fraction of what the PCIe link delivers
+                    const int64_t step = std::max<int64_t>((v1 - v0 + 3) / 4, 1);
+                    for (int64_t a = v0; a < v1; a += step) {
+                        const int64_t b = std::min(v1, a + step);
+                        self->tasks.push_back(std::async(std::launch::async, [self, a, b]() { self->copy(a, b); }));
+                    }
+                } catch (...) {
+                    if (!self->error) self->error = std::current_exception();
+                }
+            }
+        } chunks{&builder, &def_coll, def.data(), fixed_vol.rows, fixed_vol.cols, {}, {}, nullptr, false};
+        int rc = DCMA_B200_OK;
+        if (one_call) {
+            rc = dcma_b200_demons_register_stacks(&fg, fixed_px.data(), &mg, raw.data(), &p, def.data(), nullptr, &stats,
+                                                  &ChunkCopy::on_chunk, &chunks, err, sizeof(err));
+        } else {
+            rc = dcma_b200_demons_register(&g, fixed_px.data(), moving_px.data(), &p, def.data(), nullptr, &stats, err, sizeof(err));
+        }
+        lap(one_call ? "dcma_b200_demons_register_stacks" : "dcma_b200_demons_register");
+        if (builder.joinable()) builder.join();
+        for (auto &t : chunks.tasks) t.get();
         lap("wait for the output stack");
         check_rc(rc, err);
         if (alloc_error) std::rethrow_exception(alloc_error);
-        fill_from_dense(def_coll, def.data(), fixed_vol.rows, fixed_vol.cols, 3);
+        if (chunks.error) std::rethrow_exception(chunks.error);
+        if (!one_call) fill_from_dense(def_coll, def.data(), fixed_vol.rows, fixed_vol.cols, 3);
         lap("copy field into the stack");
         deformation_field out(std::move(def_coll));
         lap("deformation_field(...)");

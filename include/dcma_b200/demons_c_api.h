@@ -253,6 +253,24 @@ typedef struct {
     double origin[3];
     double ex[3], ey[3], ez[3];
 } dcma_b200_grid;
+/* ---- one-shot registration of two image STACKS, each on its own regular grid --------------------------------------- */
+/* What AlignViaDemons does between marshalling and the construction of the deformation_field
+ * (src/Alignment_Demons.cc:964-997) in ONE call: the moving stack is resampled onto the fixed stack's grid on the device
+ * (resample_image_to_reference_grid, cc:709-755: trilinear, NaN outside the moving grid) and never travels back to the
+ * host; then the loop; then the field comes back in chunks.  `on_field_chunk` (may be NULL) is called on the calling
+ * thread each time voxels [voxel_begin, voxel_end) of deformation_out (N*3 doubles, AoS z,y,x,c) have landed, in
+ * ascending order, while later chunks are still in flight -- the caller can copy them into its own image stack in the
+ * meantime.  With pyramid_levels > 1 or n_devices > 1 the call is equivalent to dcma_b200_resample_to_grid +
+ * dcma_b200_demons_register and the callback fires once at the end.  Histogram matching is the caller's pre-step and
+ * needs the resampled image on the host: use the separate calls then.  All pointers HOST (pinned = asynchronous). */
+typedef void (*dcma_b200_chunk_fn)(void *user, int64_t voxel_begin, int64_t voxel_end);
+DCMA_B200_API int dcma_b200_demons_register_stacks(const dcma_b200_grid *fixed_grid, const float *fixed,
+                                                   const dcma_b200_grid *moving_grid, const float *moving,
+                                                   const dcma_b200_demons_params *params, double *deformation_out,
+                                                   double *mse_history, dcma_b200_run_stats *stats,
+                                                   dcma_b200_chunk_fn on_field_chunk, void *user, char *errbuf,
+                                                   size_t errbuf_len);
+
 /* The per-voxel body of WarpImages for a deformation_field transform (src/Operations/WarpImages.cc:418-456,
  * src/Alignment_Field.cc:138-153): out(p) = image(p + D(p)) with p running over `image_grid`, D sampled trilinearly
  * from the field on `field_grid` (displacement components along the field's axes, mm), the image sampled trilinearly at

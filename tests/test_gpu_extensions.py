@@ -188,6 +188,38 @@ def test_warp_with_three_stacks_as_the_operation_has_them():
         warp_to_grid(fg, D, sg, src, og2, place2, channel=1)   # the source stack has no channel 1
 
 
+def test_register_stacks_equals_resample_then_register_and_streams_the_field_in_order():
+    """dcma_b200_demons_register_stacks (what the C++ drop-in calls for regular stacks): device-side resampling of the moving
+    stack + the loop + chunked return of the field == dcma_b200_resample_to_grid followed by dcma_b200_demons_register, bit
+    for bit; the chunk notifications tile [0, N) in ascending order."""
+    from dicomautomaton_b200.demons import (AlignViaDemons, AlignViaDemonsParams, demons_volume, make_grid, register_stacks,
+                                            resample_to_grid)
+    fshape, fsp = (140, 128, 132), (1.0, 1.0, 1.5)      # 2.4 M voxels: more than one 2 Mi-voxel chunk
+    mshape, msp, morg = (100, 90, 96), (1.4, 1.5, 2.2), (-1.0, -2.0, -3.0)
+    F, _ = phantom_pair(fshape, fsp)
+    _, Mraw = phantom_pair(mshape, msp)
+    fg, mg = make_grid(fshape, fsp), make_grid(mshape, msp, morg)
+    par = AlignViaDemonsParams(max_iterations=6, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
+                               update_field_smoothing_sigma=1.5, use_diffeomorphic=True, verbosity=0, field_mode="fp64_strict")
+    chunks = []
+    D, hist, st = register_stacks(par, fg, F, mg, Mraw, on_chunk=lambda a, b: chunks.append((a, b)))
+    Mres = resample_to_grid(mg, Mraw, fg)
+    assert np.isnan(Mres).any() and np.isfinite(Mres).any()   # the moving grid does not cover the fixed one
+    ref, href, _ = AlignViaDemons(par, demons_volume(Mres, *fsp), demons_volume(F, *fsp), return_stats=True)
+    assert st.iterations_done == 6 and np.array_equal(D, ref.data) and np.array_equal(hist, href)
+    n = fshape[0] * fshape[1] * fshape[2]
+    assert len(chunks) >= 2 and chunks[0][0] == 0 and chunks[-1][1] == n
+    assert all(a < b for a, b in chunks) and all(chunks[i][1] == chunks[i + 1][0] for i in range(len(chunks) - 1))
+    # pyramids take the two-call route inside the library; one notification at the end
+    chunks.clear()
+    par2 = AlignViaDemonsParams(max_iterations=4, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
+                                update_field_smoothing_sigma=1.5, use_diffeomorphic=True, verbosity=0, pyramid_levels=2,
+                                pyramid_iterations=(5, 0, 0))
+    D2, h2, st2 = register_stacks(par2, fg, F, mg, Mraw, on_chunk=lambda a, b: chunks.append((a, b)))
+    ref2, _, _ = AlignViaDemons(par2, demons_volume(Mres, *fsp), demons_volume(F, *fsp), return_stats=True)
+    assert chunks == [(0, n)] and st2.iterations_done == 9 and np.array_equal(D2, ref2.data)
+
+
 @pytest.mark.parametrize("kind", ["sinusoidal_v1", "vortex_v1"])
 def test_virtual_field_generators_match_the_host_loops(kind):
     """Row f4: dcma_b200_virtual_field vs the numpy restatement of the generator operations' host loops
