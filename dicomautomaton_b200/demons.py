@@ -302,7 +302,7 @@ def register_stacks(params: "AlignViaDemonsParams", fixed_grid: capi.Grid, fixed
     g = fixed_grid.geom
     out = np.empty((g.slices, g.rows, g.cols, 3), dtype=np.float64)
     cp = params.to_c()
-    n_hist = int(params.max_iterations) * (1 if params.pyramid_levels <= 1 else 1) + sum(int(v) for v in params.pyramid_iterations)
+    n_hist = 4 * int(params.max_iterations) + sum(int(v) for v in params.pyramid_iterations)
     hist = np.zeros(max(n_hist, 1), dtype=np.float64)
     st = capi.RunStats()
     err = C.create_string_buffer(512)
