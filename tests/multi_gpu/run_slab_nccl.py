@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--shape", default="64,96,128")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--mode", default="fp64_strict")
+    ap.add_argument("--symmetric", action="store_true", help="use_symmetric_force (extension a11): W needs a z halo")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,7 +39,7 @@ def main():
     for diffeo in (False, True):
         par = AlignViaDemonsParams(max_iterations=a.iters, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
                                    update_field_smoothing_sigma=1.5, use_diffeomorphic=diffeo, verbosity=0,
-                                   field_mode=a.mode, device=local)
+                                   field_mode=a.mode, device=local, use_symmetric_force=a.symmetric)
         ident = [DemonsSlabGroup.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
         grp = DemonsSlabGroup.nccl(shape, sp, par, ident[0], rank, world, local)
@@ -55,7 +56,7 @@ def main():
         print(f"[rank {rank}/{world}] diffeo={diffeo} slices [{z0},{z1}) iters={st.iterations_done} loop_ms={st.loop_ms:.2f} "
               f"halo_bytes={hb} bit_identical={same} mse_rel={mse_rel:.2e} overlapped={xs['overlapped']} "
               f"exchange_ms={xs['exchange_ms']:.2f} transport='{xs['transport']}'", flush=True)
-        ok = ok and same and mse_rel < 1e-12 and st.iterations_done == a.iters
+        ok = ok and same and mse_rel < (1e-6 if a.mode in ("fp32", "mixed") else 1e-12) and st.iterations_done == a.iters
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
