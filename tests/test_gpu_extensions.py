@@ -195,7 +195,7 @@ def test_register_stacks_equals_resample_then_register_and_streams_the_field_in_
     from dicomautomaton_b200.demons import (AlignViaDemons, AlignViaDemonsParams, demons_volume, make_grid, register_stacks,
                                             resample_to_grid)
     fshape, fsp = (140, 128, 132), (1.0, 1.0, 1.5)      # 2.4 M voxels: more than one 2 Mi-voxel chunk
-    mshape, msp, morg = (100, 90, 96), (1.4, 1.5, 2.2), (-1.0, -2.0, -3.0)
+    mshape, msp, morg = (100, 90, 96), (1.4, 1.5, 2.2), (8.0, -2.0, -3.0)   # leaves x < 8 mm of the fixed grid uncovered
     F, _ = phantom_pair(fshape, fsp)
     _, Mraw = phantom_pair(mshape, msp)
     fg, mg = make_grid(fshape, fsp), make_grid(mshape, msp, morg)
