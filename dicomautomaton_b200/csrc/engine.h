@@ -42,6 +42,10 @@ class EngineBase {
     virtual void get_owned_deformation(double *host_aos) = 0;  // owned slices only, AoS doubles
     virtual SlabSpec slab() const = 0;
     virtual void load(const float *fixed, const float *moving, bool on_device) = 0;
+    // HOST pointers to whole volumes; of the moving image only slices [mz0, mz1) are uploaded -- the caller fills the
+    // rest of moving_dev_mutable() itself (slab groups: from the other ranks over NVLink) before the first run
+    virtual void load_partial_moving(const float *fixed, const float *moving, int64_t mz0, int64_t mz1) = 0;
+    virtual float *moving_dev_mutable() = 0;
     virtual void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) = 0;
     virtual void stage(int stage, double sigma_mm, double *mse_out, int64_t *n_valid_out) = 0;
     virtual void get(int buffer, void *host) = 0;

@@ -215,6 +215,22 @@ class Engine final : public EngineBase {
         loaded_ = true;
     }
 
+    void load_partial_moving(const float *fixed, const float *moving, int64_t mz0, int64_t mz1) override {
+        DCMA_CUDA(cudaSetDevice(dev_));
+        if (mz0 < 0 || mz1 > g_.Sg || mz0 > mz1) throw std::invalid_argument("bad moving slice range");
+        const size_t plane = static_cast<size_t>(g_.R) * g_.C * g_.CH;
+        DCMA_CUDA(cudaMemcpyAsync(dF_, fixed + static_cast<size_t>(g_.zoff) * plane, sizeof(float) * plane * g_.S, cudaMemcpyHostToDevice, stream_));
+        DCMA_CUDA(cudaMemcpyAsync(dM_ + static_cast<size_t>(mz0) * plane, moving + static_cast<size_t>(mz0) * plane,
+                                  sizeof(float) * plane * static_cast<size_t>(mz1 - mz0), cudaMemcpyHostToDevice, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dD_, 0, sizeof(T) * 3 * g_.N, stream_));
+        DCMA_CUDA(cudaMemsetAsync(dU_, 0, sizeof(TU) * 3 * g_.N, stream_));
+        w_src_ = 0;
+        reset_ctrl();
+        DCMA_CUDA(cudaStreamSynchronize(stream_));
+        loaded_ = true;
+    }
+    float *moving_dev_mutable() override { return dM_; }
+
     // ---- AlignViaDemons loop, cc:980-995 -----------------------------------------------------------------------
     void run(int64_t max_iterations, bool profile, double *mse_history_host, dcma_b200_run_stats *stats) override {
         DCMA_CUDA(cudaSetDevice(dev_));

@@ -529,8 +529,32 @@ void SlabGroup::token_sync() {
 }
 
 void SlabGroup::load(const float *fixed, const float *moving, bool on_device) {
-    if (on_device && locals_.size() > 1) {
-        // device pointers belong to one device; peer-readable copies work through UVA
+    // One rank per process, host volumes: every rank holds the whole moving image on ITS host, but pushing it whole through
+    // every rank's PCIe link (N x the volume through one host) is what bounds a sharded call end to end.  Each rank uploads
+    // 1/N of the moving image and the ranks replicate it among themselves over NVLink (grouped ncclSend/ncclRecv: an
+    // all-gather of contiguous, possibly unequal slice ranges).  DCMA_B200_SLAB_REPLICATE_VIA_PCIE=1 keeps the plain upload.
+    const char *plain = std::getenv("DCMA_B200_SLAB_REPLICATE_VIA_PCIE");
+    if (comm_ && world_ > 1 && !on_device && !(plain && *plain == '1')) {
+        Local &l = *locals_[0];
+        EngineBase *e = l.eng.get();
+        const SlabSpec mine = slab_for_rank(geom_.slices, world_, l.rank, 0);
+        e->load_partial_moving(fixed, moving, mine.zoff, mine.zoff + mine.local);
+        DCMA_CUDA(cudaSetDevice(l.device));
+        cudaStream_t st = static_cast<cudaStream_t>(e->stream_handle());
+        const size_t plane_bytes = sizeof(float) * static_cast<size_t>(geom_.rows) * geom_.cols * geom_.channels;
+        char *base = reinterpret_cast<char *>(e->moving_dev_mutable());
+        DCMA_NCCL(nccl().GroupStart());
+        for (int p = 0; p < world_; ++p) {
+            if (p == l.rank) continue;
+            const SlabSpec theirs = slab_for_rank(geom_.slices, world_, p, 0);
+            DCMA_NCCL(nccl().Send(base + static_cast<size_t>(mine.zoff) * plane_bytes, static_cast<size_t>(mine.local) * plane_bytes, ncclChar, p,
+                                  static_cast<ncclComm_t>(comm_), st));
+            DCMA_NCCL(nccl().Recv(base + static_cast<size_t>(theirs.zoff) * plane_bytes, static_cast<size_t>(theirs.local) * plane_bytes, ncclChar, p,
+                                  static_cast<ncclComm_t>(comm_), st));
+        }
+        DCMA_NCCL(nccl().GroupEnd());
+        DCMA_CUDA(cudaStreamSynchronize(st));
+        return;
     }
     for (auto &l : locals_) l->eng->load(fixed, moving, on_device);
 }
