@@ -638,7 +638,7 @@ def run_slab(args):
     final_mse = float(hist[-1]) if len(hist) else None
 
     # ---- end to end through the C ABI of the sharded path with pinned HOST buffers: every rank uploads its slab of the
-    # fixed image and the whole moving image, runs the loop and downloads its slab of the fp64 field
+    # fixed image and 1/N of the moving image (replicated over NVLink), runs the loop and downloads its slab of the fp64 field
     lib = capi.lib()
     z0, z1 = grp.owned_range()
     plane = shape[1] * shape[2]
@@ -665,12 +665,16 @@ def run_slab(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
-    h2d = ((z1 - z0) + (grp.exchange_stats()["halo_planes"] * 2) + shape[0]) * plane * 4  # slab of F (+halo) and whole M
+    # slab of F (+halo) and this rank's 1/N of M (the ranks replicate M among themselves over NVLink: csrc/slab.cu, load)
+    m_slices = shape[0] if world == 1 else -(-shape[0] // world)
+    h2d = ((z1 - z0) + (grp.exchange_stats()["halo_planes"] * 2) + m_slices) * plane * 4
     e2e = {"value": nvox * e2e_iters / e2e_s, "unit": "voxel-updates/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int((z1 - z0) * plane * 24), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "bytes_are": "per rank (rank 0)",
+           "nvlink_bytes_per_step": int((shape[0] - m_slices) * plane * 4) if world > 1 else 0,
            "api": "dcma_b200_slab_group_load / _run / _get_deformation (C ABI, pinned host buffers; each rank uploads its "
-                  "slab of the fixed image and the whole moving image, downloads its slab of the fp64 AoS field)"}
+                  "slab of the fixed image and 1/N of the moving image -- the ranks replicate the moving image among "
+                  "themselves over NVLink --, downloads its slab of the fp64 AoS field)"}
     xstats = grp.exchange_stats()
     grp.close()
     del hf, hm, hD, fixed, moving
