@@ -81,6 +81,8 @@ SYMBOLS = {
                                          C.c_int, _cp, C.c_size_t]),
     "dcma_b200_demons_register_stacks": (C.c_int, [C.POINTER(Grid), _vp, C.POINTER(Grid), _vp, C.POINTER(Params), _vp, _vp,
                                                    C.POINTER(RunStats), _vp, _vp, _cp, C.c_size_t]),
+    "dcma_b200_device_pool_trim": (None, []),
+    "dcma_b200_device_pool_bytes": (C.c_int64, []),
     "dcma_b200_virtual_field": (C.c_int, [C.c_int32, C.POINTER(Grid), _vp, _vp, _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_resample_to_grid": (C.c_int, [C.POINTER(Grid), _vp, C.POINTER(Grid), C.c_float, _vp, C.c_int, _cp, C.c_size_t]),
     "dcma_b200_format_doubles": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.POINTER(C.c_int64), C.c_int, _cp, C.c_size_t]),

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "device_pool.h"
 #include "engine.h"
 #include "pyramid.h"
 #include "slab.h"
@@ -86,6 +87,10 @@ extern "C" {
 int dcma_b200_abi_version(void) { return DCMA_B200_ABI_VERSION; }
 
 const char *dcma_b200_last_error(void) { return g_last_error.c_str(); }
+
+void dcma_b200_device_pool_trim(void) { dcma::DevicePool::instance().trim(); }
+
+int64_t dcma_b200_device_pool_bytes(void) { return static_cast<int64_t>(dcma::DevicePool::instance().cached_bytes()); }
 
 int dcma_b200_device_count(void) {
     int n = 0;
@@ -299,11 +304,19 @@ int dcma_b200_demons_register_stacks(const dcma_b200_grid *fixed_grid, const flo
     return guarded(
         [&]() {
             using clk = std::chrono::steady_clock;
-            struct Holder {
+            struct Holder {  // temporaries come from (and go back to) the device pool: no driver call per registration
                 dcma::EngineBase *p = nullptr;
+                int dev = 0;
                 float *d[3] = {nullptr, nullptr, nullptr};
+                size_t bytes[3] = {0, 0, 0};
+                void drop() {
+                    for (int i = 0; i < 3; ++i) {
+                        dcma::DevicePool::instance().release(dev, d[i], bytes[i]);
+                        d[i] = nullptr;
+                    }
+                }
                 ~Holder() {
-                    for (float *q : d) cudaFree(q);
+                    drop();
                     delete p;
                 }
             } h;
@@ -313,18 +326,20 @@ int dcma_b200_demons_register_stacks(const dcma_b200_grid *fixed_grid, const flo
             const long long nmov = moving_grid->geom.slices * moving_grid->geom.rows * moving_grid->geom.cols * geom.channels;
             const size_t bf = sizeof(float) * static_cast<size_t>(nvox * geom.channels), bm = sizeof(float) * static_cast<size_t>(nmov);
             const auto t0 = clk::now();
-            DCMA_CUDA(cudaMalloc(&h.d[0], bf));
-            DCMA_CUDA(cudaMalloc(&h.d[1], bm));
-            DCMA_CUDA(cudaMalloc(&h.d[2], bf));
+            h.dev = h.p->device();
+            const size_t want[3] = {bf, bm, bf};
+            for (int i = 0; i < 3; ++i) {
+                void *q = nullptr;
+                DCMA_CUDA(dcma::DevicePool::instance().acquire(h.dev, want[i], &q));
+                h.d[i] = static_cast<float *>(q);
+                h.bytes[i] = want[i];
+            }
             DCMA_CUDA(cudaMemcpyAsync(h.d[0], fixed, bf, cudaMemcpyHostToDevice, st));
             DCMA_CUDA(cudaMemcpyAsync(h.d[1], moving, bm, cudaMemcpyHostToDevice, st));
             dcma::resample_to_grid_device(*moving_grid, h.d[1], *fixed_grid, nan, h.d[2], st);   // = cc:964 on the device
             h.p->load(h.d[0], h.d[2], true);
             h.p->sync();
-            for (float *&q : h.d) {
-                cudaFree(q);
-                q = nullptr;
-            }
+            h.drop();
             const auto t1 = clk::now();
             dcma_b200_run_stats local;
             h.p->run(params->max_iterations, false, mse_history, &local);

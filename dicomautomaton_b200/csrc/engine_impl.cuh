@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "demons_kernels.cuh"
+#include "device_pool.h"
 #include "engine.h"
 #include "smooth_kernels.cuh"
 #include "smooth_tma.cuh"
@@ -164,7 +165,7 @@ class Engine final : public EngineBase {
     void release_all() noexcept {
         cudaSetDevice(dev_);
         if (stream_) cudaStreamSynchronize(stream_);
-        for (void *p : allocs_) cudaFree(p);
+        for (auto &q : allocs_) DevicePool::instance().release(dev_, q.first, q.second);
         allocs_.clear();
         if (h_ctrl_) cudaFreeHost(h_ctrl_);
         if (d_hist_) cudaFree(d_hist_);
@@ -613,14 +614,14 @@ class Engine final : public EngineBase {
     X *alloc(long long n) {
         void *p = nullptr;
         const size_t bytes = sizeof(X) * static_cast<size_t>(std::max<long long>(n, 1));
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = DevicePool::instance().acquire(dev_, bytes, &p);  // device_pool.h: reuses the last engine's blocks
         if (e != cudaSuccess) {
-            for (void *q : allocs_) cudaFree(q);
+            for (auto &q : allocs_) DevicePool::instance().release(dev_, q.first, q.second);
             allocs_.clear();
             throw CudaError(e, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " +
                                    cudaGetErrorString(e));
         }
-        allocs_.push_back(p);
+        allocs_.emplace_back(p, bytes);
         bytes_ += static_cast<int64_t>(bytes);
         return static_cast<X *>(p);
     }
@@ -1172,7 +1173,7 @@ class Engine final : public EngineBase {
     std::map<double, SmoothPlan<TU>> extra_plans_u_;  // used only when TU != T
     std::map<std::tuple<const void *, int, int>, CUtensorMap> tmaps_;
     int w_src_ = 0;
-    std::vector<void *> allocs_;
+    std::vector<std::pair<void *, size_t>> allocs_;  // (block, bytes): returned to the device pool, not to the driver
     int64_t bytes_ = 0;
     int64_t launches_ = 0, prof_launch_mark_ = 0;
     bool profiling_ = false;

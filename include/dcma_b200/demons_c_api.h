@@ -125,6 +125,12 @@ DCMA_B200_API int dcma_b200_abi_version(void);
 DCMA_B200_API const char *dcma_b200_last_error(void); /* thread-local message of the last failing call */
 DCMA_B200_API int dcma_b200_device_count(void);       /* number of CUDA devices visible, 0 if none (never fails) */
 DCMA_B200_API void dcma_b200_demons_params_default(dcma_b200_demons_params *p); /* defaults of Alignment_Demons.h:20-61 */
+/* Engines return their device blocks to a process-lifetime pool instead of the driver, so that the next registration of
+ * the same shape does not pay cudaMalloc / cudaFree of several GB again (10-25 ms per call, hundreds on a busy box).  The
+ * pool keeps at most DCMA_B200_DEVICE_POOL_MB per device (environment, default 12288; 0 = no caching).  _trim gives
+ * everything cached back to the driver; _bytes reports how much is cached.  The reference has no counterpart. */
+DCMA_B200_API void dcma_b200_device_pool_trim(void);
+DCMA_B200_API int64_t dcma_b200_device_pool_bytes(void);
 
 /* ---- one-shot registration on HOST buffers ----------------------------------------------------------------- */
 /* Replaces, inside AlignViaDemons, the block  `sycl_demons_engine engine(fixed_vol, moving_vol, params); for(iter...)

@@ -259,3 +259,28 @@ def test_warp_image_entry_point(oracle_mod):
     assert np.array_equal(got, ref, equal_nan=True)
     got0 = warp_image_with_field(demons_volume(M, *sp), D, oob_value=0.0)
     assert np.array_equal(got0, np.where(np.isnan(ref), 0.0, ref).astype(np.float32))
+
+
+def test_engine_blocks_are_reused_through_the_device_pool():
+    """Engines give their device blocks back to a process-lifetime pool (csrc/device_pool.h) and the next engine of the same
+    shape takes them from there: no cudaMalloc / cudaFree of several GB per registration.  Results do not depend on it
+    (a reused block holds the previous run's bytes; every buffer is written before it is read)."""
+    from dicomautomaton_b200 import capi
+    from dicomautomaton_b200.demons import AlignViaDemons, AlignViaDemonsParams, demons_volume
+    lib = capi.lib()
+    shape, sp = (24, 40, 56), (1.0, 1.0, 1.0)
+    F, M = phantom_pair(shape, sp)
+    par = AlignViaDemonsParams(max_iterations=6, convergence_threshold=0.0, deformation_field_smoothing_sigma=1.5,
+                               update_field_smoothing_sigma=1.5, use_diffeomorphic=True, verbosity=0, field_mode="fp64_strict")
+    lib.dcma_b200_device_pool_trim()
+    assert lib.dcma_b200_device_pool_bytes() == 0
+    a, ha, _ = AlignViaDemons(par, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
+    cached = lib.dcma_b200_device_pool_bytes()
+    assert cached >= 3 * 3 * 8 * F.size     # at least the three fp64 field allocations
+    # another registration in between with other inputs dirties the cached blocks
+    AlignViaDemons(par, demons_volume(F, *sp), demons_volume(M[::-1].copy(), *sp))
+    b, hb, _ = AlignViaDemons(par, demons_volume(M, *sp), demons_volume(F, *sp), return_stats=True)
+    assert lib.dcma_b200_device_pool_bytes() == cached      # same blocks went out and came back
+    assert np.array_equal(a.data, b.data) and np.array_equal(ha, hb)
+    lib.dcma_b200_device_pool_trim()
+    assert lib.dcma_b200_device_pool_bytes() == 0
