@@ -12,10 +12,12 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 namespace dcma {
 
@@ -98,5 +100,66 @@ class DevicePool {
     size_t cached_[kMaxDev] = {};
     size_t limit_ = 0;
 };
+
+// Small page-locked host blocks (the engines' 72-byte control mirror): cudaMallocHost / cudaFreeHost are system calls
+// that pin and unpin pages and can stall for tens of milliseconds; a handful of such blocks is kept for the life of the
+// process instead.
+class PinnedSmallPool {
+  public:
+    static PinnedSmallPool &instance() {
+        static PinnedSmallPool p;
+        return p;
+    }
+    static constexpr size_t kBlock = 256;
+    cudaError_t acquire(void **out) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!free_.empty()) {
+                *out = free_.back();
+                free_.pop_back();
+                return cudaSuccess;
+            }
+        }
+        return cudaMallocHost(out, kBlock);
+    }
+    void release(void *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu_);
+        free_.push_back(p);
+    }
+
+  private:
+    std::mutex mu_;
+    std::vector<void *> free_;
+};
+
+// cudaGetDeviceProperties fills ~1 KB from the driver on every call (milliseconds); the two fields the engines need
+inline cudaError_t cached_device_info(int dev, int *major, int *minor, int *sms, char name[256]) {
+    struct Info {
+        bool ok = false;
+        int major = 0, minor = 0, sms = 0;
+        char name[256] = {0};
+    };
+    static Info info[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    Info &i = info[dev];
+    if (!i.ok) {
+        cudaDeviceProp prop;
+        const cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return e;
+        i.major = prop.major;
+        i.minor = prop.minor;
+        i.sms = prop.multiProcessorCount;
+        std::snprintf(i.name, sizeof i.name, "%s", prop.name);
+        i.ok = true;
+    }
+    *major = i.major;
+    *minor = i.minor;
+    *sms = i.sms;
+    std::snprintf(name, 256, "%s", i.name);
+    return cudaSuccess;
+}
 
 }  // namespace dcma

@@ -96,13 +96,13 @@ class Engine final : public EngineBase {
         } else {
             DCMA_CUDA(cudaGetDevice(&dev_));
         }
-        cudaDeviceProp prop;
-        DCMA_CUDA(cudaGetDeviceProperties(&prop, dev_));
-        if (prop.major < 10)
+        int cc_major = 0, cc_minor = 0;
+        char dev_name[256] = {0};
+        DCMA_CUDA(cached_device_info(dev_, &cc_major, &cc_minor, &sms_, dev_name));
+        if (cc_major < 10)
             throw CudaError(cudaErrorInvalidDevice, std::string("dcma_b200 kernels are built for sm_100a only; device is ") +
-                                                        prop.name + " (sm_" + std::to_string(prop.major) +
-                                                        std::to_string(prop.minor) + ")");
-        sms_ = prop.multiProcessorCount;
+                                                        dev_name + " (sm_" + std::to_string(cc_major) +
+                                                        std::to_string(cc_minor) + ")");
         if (stream_in) {
             stream_ = static_cast<cudaStream_t>(stream_in);
         } else {
@@ -154,7 +154,12 @@ class Engine final : public EngineBase {
         d_part_sum_ = alloc<double>(part_cap_);
         d_part_cnt_ = alloc<long long>(part_cap_);
         d_ctrl_ = alloc<Ctrl>(1);
-        DCMA_CUDA(cudaMallocHost(&h_ctrl_, sizeof(Ctrl)));
+        static_assert(sizeof(Ctrl) <= PinnedSmallPool::kBlock, "control block larger than a pooled pinned block");
+        {
+            void *hp = nullptr;
+            DCMA_CUDA(PinnedSmallPool::instance().acquire(&hp));
+            h_ctrl_ = static_cast<Ctrl *>(hp);
+        }
 
         build_plan(plan_u_, p_.update_field_smoothing_sigma);
         build_plan(plan_d_, p_.deformation_field_smoothing_sigma);
@@ -167,8 +172,8 @@ class Engine final : public EngineBase {
         if (stream_) cudaStreamSynchronize(stream_);
         for (auto &q : allocs_) DevicePool::instance().release(dev_, q.first, q.second);
         allocs_.clear();
-        if (h_ctrl_) cudaFreeHost(h_ctrl_);
-        if (d_hist_) cudaFree(d_hist_);
+        PinnedSmallPool::instance().release(h_ctrl_);
+        drop_history();
         if (ev_run0_) cudaEventDestroy(ev_run0_);
         if (ev_run1_) cudaEventDestroy(ev_run1_);
         for (cudaEvent_t e : ev_stage_)
@@ -258,9 +263,13 @@ class Engine final : public EngineBase {
         DCMA_CUDA(cudaSetDevice(dev_));
         if (!loaded_) throw std::logic_error("run called before load");
         reset_ctrl();
-        if (d_hist_) cudaFree(d_hist_);
-        d_hist_ = nullptr;
-        DCMA_CUDA(cudaMalloc(&d_hist_, sizeof(double) * std::max<int64_t>(max_iterations, 1)));
+        drop_history();
+        d_hist_bytes_ = sizeof(double) * static_cast<size_t>(std::max<int64_t>(max_iterations, 1));
+        {
+            void *hp = nullptr;
+            DCMA_CUDA(DevicePool::instance().acquire(dev_, d_hist_bytes_, &hp));
+            d_hist_ = static_cast<double *>(hp);
+        }
         launches_ = 0;
         prof_.clear();
         profiling_ = false;
@@ -311,8 +320,7 @@ class Engine final : public EngineBase {
             if (h_ctrl_->converged_at != kNotConverged)
                 std::fprintf(stderr, "Converged after %lld iterations\n", (long long)h_ctrl_->converged_at);
         }
-        cudaFree(d_hist_);
-        d_hist_ = nullptr;
+        drop_history();
         float ms = 0.f;
         DCMA_CUDA(cudaEventElapsedTime(&ms, ev_run0_, ev_run1_));
         cudaEventDestroy(ev_run0_);
@@ -1144,6 +1152,11 @@ class Engine final : public EngineBase {
     long long Ng_ = 0;  // voxels of the whole volume
     SlabSpec slab_;
     double *d_hist_ = nullptr;
+    size_t d_hist_bytes_ = 0;
+    void drop_history() noexcept {
+        if (d_hist_) DevicePool::instance().release(dev_, d_hist_, d_hist_bytes_);
+        d_hist_ = nullptr;
+    }
     cudaEvent_t ev_run0_ = nullptr, ev_run1_ = nullptr;
     dcma_b200_demons_params p_;
     int dev_ = 0, sms_ = 148;
