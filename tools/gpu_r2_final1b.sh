@@ -1,7 +1,7 @@
 #!/bin/bash
 # Final one-GPU record after the device pool: whole GPU suite, smoke, bench.py as the driver runs it.
 tag=${1:-r2y}; out=gpurun_out; mkdir -p $out
-DCMA_PARITY_REPORT=$out/${tag}_parity.jsonl timeout 1500 python -m pytest tests -x -q -m gpu > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log; tail -6 $out/${tag}_pytest.log | cut -c1-300
+DCMA_PARITY_REPORT=$out/${tag}_parity.jsonl timeout 1500 python -m pytest tests -x -q -m gpu ${PYTEST_ARGS:-} > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest.log; tail -6 $out/${tag}_pytest.log | cut -c1-300
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
 DCMA_B200_TRACE=1 timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 grep "dcma_b200\] create" $out/${tag}_bench.err | tail -3
