@@ -122,6 +122,19 @@ def test_no_cpu_fallback_exists():
     assert ei.value.code == capi.ENODEVICE
     # the reference-shaped entry point reports failure the reference's way: nullopt
     assert AlignViaDemons(AlignViaDemonsParams(verbosity=0), v, v) is None
+    # the entry points added in round 2 keep the rule
+    from dicomautomaton_b200.demons import make_grid, register_stacks, virtual_field_v1, warp_to_grid
+    g = make_grid((4, 6, 8), (1.0, 1.0, 1.0))
+    img = np.zeros((4, 6, 8), np.float32)
+    for call in (lambda: register_stacks(AlignViaDemonsParams(verbosity=0, max_iterations=2), g, img, g, img),
+                 lambda: virtual_field_v1("vortex_v1", (4, 6, 8)),
+                 lambda: warp_to_grid(g, np.zeros((4, 6, 8, 3)), g, img, g, img)):
+        with pytest.raises(capi.DcmaError) as ei:
+            call()
+        assert ei.value.code == capi.ENODEVICE
+    # the device pool is pure bookkeeping: usable (and empty) without a device
+    capi.lib().dcma_b200_device_pool_trim()
+    assert capi.lib().dcma_b200_device_pool_bytes() == 0
 
 
 def test_product_package_never_imports_the_oracle():
