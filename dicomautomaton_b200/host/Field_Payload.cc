@@ -61,7 +61,8 @@ bool dcma_b200_io::read_payload(std::istream &is, double *out, int64_t n, int de
             is.seekg(start + static_cast<std::streamoff>(consumed));
             return true;
         }
-        if (whole_rest || rc == DCMA_B200_ENODEVICE) {
+        // only "too few / malformed numbers in this block" (EINVAL) can be cured by reading further ahead
+        if (whole_rest || (rc != DCMA_B200_OK && rc != DCMA_B200_EINVAL)) {
             YLOGWARN("Field payload could not be read: " << err);
             is.seekg(start);
             is.setstate(std::ios::failbit);
