@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define FAKE_EINVAL (-1) /* DCMA_B200_EINVAL, include/dcma_b200/demons_c_api.h */
+
 int dcma_b200_device_count(void) { return 1; }
 
 int dcma_b200_format_doubles(const double *values, int64_t n, char *text, int64_t capacity, int64_t *text_len, int device,
@@ -17,7 +19,7 @@ int dcma_b200_format_doubles(const double *values, int64_t n, char *text, int64_
     for (int64_t i = 0; i < n; ++i) {
         char line[64];
         const int len = snprintf(line, sizeof line, "%.17g\n", values[i]);
-        if (at + len > capacity) return 1;
+        if (at + len > capacity) return FAKE_EINVAL;
         memcpy(text + at, line, (size_t)len);
         at += len;
     }
@@ -34,14 +36,14 @@ int dcma_b200_parse_doubles(const char *text, int64_t text_len, int64_t n, doubl
         int64_t end = at;
         while (end < text_len && !isspace((unsigned char)text[end])) ++end;
         char tok[512];
-        if (end == at || end - at >= (int64_t)sizeof tok) { snprintf(errbuf, errbuf_len, "Pixel data could not be read"); return 1; }
+        if (end == at || end - at >= (int64_t)sizeof tok) { snprintf(errbuf, errbuf_len, "Pixel data could not be read"); return FAKE_EINVAL; }
         memcpy(tok, text + at, (size_t)(end - at));
         tok[end - at] = 0;
         char *stop = NULL;
         values[i] = strtod(tok, &stop);
         if (stop == tok || *stop != 0 || !(values[i] - values[i] == 0.0) || tok[0] == 'i' || tok[0] == 'n') {
             snprintf(errbuf, errbuf_len, "Pixel data could not be read (token '%s')", tok);
-            return 1;
+            return FAKE_EINVAL;
         }
         at = end;
     }
