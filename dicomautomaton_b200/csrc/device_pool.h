@@ -29,6 +29,7 @@ class DevicePool {
     }
     // the current device must be `dev`
     cudaError_t acquire(int dev, size_t bytes, void **out) {
+        if (dev < 0 || dev >= kMaxDev) return cudaMalloc(out, bytes);  // outside the table: plain driver allocation
         {
             std::lock_guard<std::mutex> lk(mu_);
             auto &m = free_[dev];
@@ -50,7 +51,7 @@ class DevicePool {
     }
     void release(int dev, void *p, size_t bytes) {
         if (!p) return;
-        {
+        if (dev >= 0 && dev < kMaxDev) {
             std::lock_guard<std::mutex> lk(mu_);
             if (limit_ > 0 && cached_[dev] + bytes <= limit_) {
                 free_[dev].emplace(bytes, p);
