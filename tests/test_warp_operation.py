@@ -57,6 +57,26 @@ def test_patched_operation_has_no_cpu_fallback():
     assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr
 
 
+def test_patched_operation_host_logic_on_cpu(tmp_path):
+    """The PATCHED operation end to end on CPU: its objects are linked against tests/native/fake_warp_capi.cc -- the
+    definition of dcma_b200_warp_to_grid evaluated on the host, malloc for the pinned allocator -- instead of the GPU
+    library.  Checks everything host-side that the patch and host/Warp_Images_Field.cc add: which voxels are marked, the
+    order of the mask, the marshalling of the three stacks and the write-back; the kernel itself is the GPU test's."""
+    import build_host_tests
+    if _exe(True) is None:
+        pytest.skip("reference sources not available")
+    objs = [os.path.join(build_host_tests.OUT, o) for o in ("ref_warp_operation_patched.o", "warp_operation_check.o", "Warp_Images_Field.o")]
+    if not all(os.path.isfile(o) for o in objs):
+        pytest.skip("objects of build_warp_operation not present (prebuilt executable only)")
+    fake = os.path.join(str(tmp_path), "fake_warp_capi.o")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "tests", "native", "fake_warp_capi.cc"), "-o", fake])
+    exe = os.path.join(str(tmp_path), "warp_operation_check_cpu")
+    subprocess.check_call(["g++", "-pthread", "-o", exe, *objs, fake])
+    r = _run(exe, "run")
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_warp_patch_is_current_and_minimal():
     ref = os.environ.get("DCMA_REFERENCE_SRC", "/root/reference/src")
     src = os.path.join(ref, "Operations", "WarpImages.cc")
