@@ -40,6 +40,23 @@ def _has_gpu():
         return False
 
 
+def test_dropin_host_logic_against_a_stand_in_library(tmp_path):
+    """Host side of AlignViaDemons on CPU: host/Alignment_Demons.cc linked against tests/native/fake_register_capi.cc (a
+    library that returns a KNOWN field, in chunks that straddle slices) instead of the GPU library.  Checks what the C call
+    is given (volumes, grids, which entry point) and that every voxel of the returned deformation_field is the one the
+    library wrote -- the chunk-by-chunk copy from the notification callback (tests/native/dropin_chunk_check.cc)."""
+    host = os.path.join(ROOT, "dicomautomaton_b200", "host")
+    inc = ["-I", os.path.join(host, "shim", "dcma_min"), "-I", os.path.join(host, "shim", "ygor_min"), "-I", host,
+           "-I", os.path.join(ROOT, "include")]
+    exe = os.path.join(str(tmp_path), "dropin_chunk_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-Wno-unused-function", *inc,
+                           os.path.join(ROOT, "tests", "native", "dropin_chunk_check.cc"),
+                           os.path.join(ROOT, "tests", "native", "fake_register_capi.cc"),
+                           os.path.join(host, "Alignment_Demons.cc"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, YLOG_VERBOSITY="0"))
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_reference_host_side_cases_pass_without_gpu(exe):
     """histogram_match (exact values 10, 17.5, 25, 32.5) and the empty-input contract are host code and need no device."""
     total, passed, failed, out = _run(exe, "-tc=histogram_match*,AlignViaDemons handles empty inputs")
